@@ -1,0 +1,136 @@
+/*
+ * vcd.h -- C ABI of the B200-native VCVITS HiFi-GAN waveform decoder ("vcd" = vcvits decoder).
+ *
+ * The reference has no FFI / plugin layer for this path: the decoder is a plain torch.nn.Module attribute
+ * `net_g.dec` (reference: vits/model/synthesizers/synthesizer_tts.py:71-78 constructor call,
+ * synthesizer_tts.py:140,166,176 and synthesizer_svc.py:87,108,118 forward call sites).  The entry points
+ * below are therefore the operator boundary a maintainer would bind with ctypes from the module that
+ * replaces `Generator` (see INTEGRATION.md for the binding); each one names the reference interface it
+ * stands in for.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / C++ types cross the boundary.
+ *   - every pointer named *_dev is device memory on the current CUDA device; *_host is host memory.
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream).  All work is enqueued
+ *     asynchronously on it; nothing synchronises the device unless stated.
+ *   - return value 0 = success; non-zero = error, message via vcd_last_error() (thread-local).
+ *     Nothing throws or aborts.
+ *   - the caller owns every tensor and the workspace; the library owns only the plan.
+ *   - one plan per (device, process); a plan must not be used from two host threads at once.
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point returns an error.
+ */
+#ifndef VCD_H_
+#define VCD_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VCD_MAX_KERNELS 8
+#define VCD_MAX_DILATIONS 3
+#define VCD_MAX_UPSAMPLES 8
+
+/* Arithmetic mode of the decoder activations / tensor-core operands. */
+#define VCD_MODE_FP32 0 /* fp32 storage, fp32 FFMA math: the parity mode (<=1e-4 max-abs vs. the oracle)   */
+#define VCD_MODE_BF16 1 /* bf16 operands on tcgen05 tensor cores, fp32 accumulation and residual stream */
+
+/* Constructor arguments of `Generator` (synthesizer_tts.py:71-78; values from configs/base.json:55-67). */
+typedef struct vcd_config {
+  int32_t initial_channel;                                   /* inter_channels                          */
+  int32_t resblock;                                          /* 1 -> ResBlock1 (modules.py:186), else 2 */
+  int32_t num_kernels;                                       /* len(resblock_kernel_sizes)              */
+  int32_t resblock_kernel_sizes[VCD_MAX_KERNELS];
+  int32_t resblock_dilation_sizes[VCD_MAX_KERNELS][VCD_MAX_DILATIONS];
+  int32_t num_upsamples;                                     /* len(upsample_rates)                     */
+  int32_t upsample_rates[VCD_MAX_UPSAMPLES];
+  int32_t upsample_kernel_sizes[VCD_MAX_UPSAMPLES];
+  int32_t upsample_initial_channel;
+  int32_t gin_channels;                                      /* 0 -> no `cond` conv                     */
+} vcd_config;
+
+typedef struct vcd_plan vcd_plan;
+
+/* Library / build info: returns e.g. "vcd 0.1 sm_100a".  Never fails. */
+const char* vcd_version(void);
+
+/* Last error message of the calling thread ("" if none). */
+const char* vcd_last_error(void);
+
+/* Stands in for Generator.__init__ (synthesizer_tts.py:71-78): validates the configuration, builds the
+ * layer table and the parameter table.  Needs a CUDA device (queries SM count / smem limits). */
+int vcd_plan_create(const vcd_config* cfg, vcd_plan** out_plan);
+void vcd_plan_destroy(vcd_plan* plan);
+
+/* Parameter table == the module's state_dict: name uses the reference's
+ * checkpoint keys ("conv_pre.weight", "ups.0.weight_g", "resblocks.3.convs1.0.weight_v", ...). */
+int vcd_num_params(const vcd_plan* plan);
+int vcd_param_info(const vcd_plan* plan, int index, const char** name, int64_t shape[3], int* ndim);
+int64_t vcd_total_param_elems(const vcd_plan* plan);
+
+/* Output samples per latent frame = prod(upsample_rates) (hop_length, configs/base.json:33). */
+int vcd_hop(const vcd_plan* plan);
+
+/* Bytes of caller-owned device workspace for a [B, initial_channel, T] call.  `save_for_backward` != 0
+ * keeps every activation the backward pass needs (training step); 0 recycles buffers (infer.py path). */
+size_t vcd_workspace_bytes(const vcd_plan* plan, int mode, int B, int T, int save_for_backward);
+
+/* Stands in for the weight_norm forward pre-hooks (modules.py:10,190-199,229-230: w = g * v / ||v||) plus
+ * `remove_weight_norm` (modules.py:218-222): folds all parameters into the packed operand layouts the
+ * kernels consume.  params_dev_ptrs: host array of vcd_num_params() DEVICE pointers (fp32, contiguous,
+ * shapes per vcd_param_info).  Must be called after every parameter update and before forward. */
+int vcd_fold_weights(vcd_plan* plan, int mode, const float* const* params_dev_ptrs, void* stream);
+
+/* Stands in for Generator.forward(x, g) (call sites synthesizer_tts.py:140, synthesizer_svc.py:87,108).
+ *   x_dev : fp32 [B, initial_channel, T] with element strides (xs_b, xs_c, xs_t) -- a non-contiguous
+ *           slice like (z*y_mask)[:, :, :max_len] (synthesizer_tts.py:166) is accepted as is.
+ *   g_dev : fp32 [B, gin_channels] contiguous (the [B, gin, 1] speaker embedding) or NULL.
+ *   y_dev : fp32 [B, 1, T*hop] contiguous, output waveform.
+ *   ws_dev/ws_bytes : workspace of at least vcd_workspace_bytes(...).  With save_for_backward the same
+ *           workspace must be handed, untouched, to vcd_backward. */
+int vcd_forward(vcd_plan* plan, int mode, const float* x_dev, int64_t xs_b, int64_t xs_c, int64_t xs_t,
+                const float* g_dev, float* y_dev, void* ws_dev, size_t ws_bytes, int B, int T,
+                int save_for_backward, void* stream);
+
+/* Stands in for autograd through Generator.forward (the backward of the train.py step: vcvits.py:54-148):
+ *   dy_dev      : fp32 [B, 1, T*hop] upstream gradient.
+ *   y_dev       : the waveform vcd_forward produced (tanh backward needs it); g_dev as in vcd_forward.
+ *   dx_dev      : fp32 [B, initial_channel, T] contiguous, or NULL to skip.
+ *   dg_dev      : fp32 [B, gin_channels], or NULL.
+ *   dparams_dev_ptrs : host array of vcd_num_params() DEVICE pointers receiving the parameter gradients
+ *                 (overwritten, not accumulated): weight_g / weight_v / bias exactly like autograd through
+ *                 old-style weight_norm.  Needs the params table of the preceding vcd_fold_weights.
+ *   segment_mask: bit i set -> run backward segment i (see vcd_num_backward_segments); ~0u runs everything.
+ *                 Segments must be executed in increasing order; gradients of segment i are final when the
+ *                 call that ran it returns (enqueued), which lets the caller overlap a gradient all-reduce
+ *                 of finished segments with the rest of backward (replaces the DDP reducer, train.py:99-100). */
+int vcd_backward(vcd_plan* plan, int mode, const float* dy_dev, const float* y_dev, const float* g_dev,
+                 float* dx_dev, float* dg_dev, float* const* dparams_dev_ptrs, void* ws_dev, size_t ws_bytes,
+                 int B, int T, uint32_t segment_mask, void* stream);
+
+/* Backward segments, in execution order: segment 0 = conv_post + last upsample stage, ...,
+ * last segment = conv_pre + cond.  vcd_segment_params lists the parameter indices finalised by a segment. */
+int vcd_num_backward_segments(const vcd_plan* plan);
+int vcd_segment_params(const vcd_plan* plan, int segment, int* indices, int cap);
+
+/* infer.py-style end-to-end call with HOST buffers (infer.py:83-91: latent in, waveform out):
+ * copies x_host (+ g_host) to the device, runs forward without saving activations, copies the waveform back
+ * and synchronises `stream`.  ws_dev as for vcd_forward with save_for_backward = 0, plus the staging the
+ * function reports through vcd_host_call_extra_bytes(). */
+size_t vcd_host_call_extra_bytes(const vcd_plan* plan, int B, int T);
+int vcd_synthesize_host(vcd_plan* plan, int mode, const float* x_host, const float* g_host, float* y_host,
+                        void* ws_dev, size_t ws_bytes, int B, int T, void* stream);
+
+/* Counters for bench.py: kernels launched by this library since the last reset. */
+uint64_t vcd_launch_count(int reset);
+
+/* Per-layer timing / debugging: name of the arithmetic path ("simt-fp32", "tcgen05-bf16", ...) used by
+ * layer `index` of the forward schedule in `mode`; NULL past the end. */
+const char* vcd_layer_path(const vcd_plan* plan, int mode, int index);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VCD_H_ */

@@ -1,0 +1,86 @@
+// Host-side plan: layer table, parameter table, packed-weight arenas, workspace layout.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/vcd.h"
+#include "common.cuh"
+#include "fold.cuh"
+
+namespace vcd {
+
+struct ParamInfo {
+  std::string name;
+  int64_t shape[3];
+  int ndim;
+  int64_t numel;
+};
+
+enum : int { LK_CONV = 0, LK_CONVT = 1 };
+
+struct Layer {
+  std::string name;
+  int kind;                   // LK_*
+  int cin, cout, k, dil, u, pad;
+  bool wn;
+  int p_w, p_g, p_b;          // parameter indices (p_w: weight or weight_v), -1 if absent
+  ConvGeo fwd, dgr;           // generalised geometries (common.cuh)
+  WeightMap map_fwd, map_dgr;
+  long long f32_fwd, f32_dgr; // offsets (elements) into the fp32 packed arena
+  long long tc_fwd, tc_dgr;   // offsets (elements) into the bf16 packed arena, -1 if no tensor-core path
+  int nt_fwd, nt_dgr;         // tensor-core column tile of the packed bf16 format
+  long long dwp;              // offset (floats) of dWp[taps][K][N] (fwd geometry) in the gradient scratch
+  long long dbias;            // offset (floats) of the bias gradient in the gradient scratch, -1 if none
+  int norm_off;               // offset into the norms arena (weight-normed only)
+  int segment;                // backward segment that finalises this layer's gradients
+  bool tc_ok_fwd, tc_ok_dgr, tc_ok_wgr;  // eligible for the tcgen05 kernels
+};
+
+struct SegmentJobs {
+  UnfoldJob* d_jobs = nullptr;
+  int njobs = 0, nblocks = 0;
+  long long scratch_begin = 0, scratch_end = 0;  // float range of the gradient scratch to zero
+  std::vector<int> params;
+};
+
+struct StageDesc {
+  int cin, cout, u, k;        // upsample conv
+  int up_layer;               // index into layers
+  // resblock branches: layers[branch][pair][0|1] (ResBlock2: [pair][0] only)
+  std::vector<std::vector<std::vector<int>>> convs;
+};
+
+}  // namespace vcd
+
+struct vcd_plan {
+  vcd_config cfg;
+  int device = 0, num_sms = 0;
+  int hop = 1;
+  std::vector<vcd::ParamInfo> params;
+  std::vector<vcd::Layer> layers;
+  std::vector<vcd::StageDesc> stages;
+  int l_pre = -1;
+  int p_post_w = -1, p_cond_w = -1, p_cond_b = -1;
+  long long post_dw = -1;     // gradient scratch offset of conv_post.weight (parameter layout)
+  long long cond_dw = -1, cond_db = -1;
+
+  // device arenas (library-owned)
+  float* d_f32 = nullptr;     // packed fp32 weights
+  vcd::bf16* d_bf16 = nullptr;  // packed bf16 weights
+  float* d_norms = nullptr;
+  float* d_gscratch = nullptr;  // packed weight gradients + bias gradients
+  long long n_f32 = 0, n_bf16 = 0, n_norms = 0, n_gscratch = 0;
+  const float** d_params = nullptr;  // device copy of the parameter pointer table
+  float** d_dparams = nullptr;
+  std::vector<const float*> h_params;
+  std::vector<float*> h_dparams;
+  bool folded[2] = {false, false};
+
+  vcd::NormJob* d_norm_jobs = nullptr;
+  int n_norm_jobs = 0, n_norm_blocks = 0;
+  vcd::PackJob* d_pack_jobs[2] = {nullptr, nullptr};  // per mode
+  int n_pack_jobs[2] = {0, 0}, n_pack_blocks[2] = {0, 0};
+  std::vector<vcd::SegmentJobs> segments;
+};

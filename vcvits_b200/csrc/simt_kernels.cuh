@@ -1,0 +1,419 @@
+// CUDA-core (FFMA) kernels on the blocked channels-last layout.
+//
+// Role: (1) the complete fp32 parity path (VCD_MODE_FP32, fp32 storage + FFMA math, bit-for-bit
+// independent of the tensor-core kernels so it doubles as their on-device cross-check); (2) in bf16 mode,
+// the layers that are too small or too thin for an implicit-GEMM tile (conv_post+tanh, cond, layout
+// transposes, bias/column reductions).  All kernels are templated on the storage type T (float | bf16) and
+// accumulate in fp32.
+#pragma once
+#include "common.cuh"
+
+namespace vcd {
+
+// -------------------------------------------------------------------------------------------------
+// Generalised convolution, direct form.  One thread = ROWS output positions (q, q+128, ...) x 8 output
+// columns; the 8x8 weight block of each (tap, channel group) is a block-uniform load (L1 broadcast).
+// grid = (ceil(Lq / (128*ROWS)), N/8, B), block = 128.
+// -------------------------------------------------------------------------------------------------
+template <typename T, int ROWS>
+__global__ void __launch_bounds__(128)
+gconv_simt_kernel(const T* __restrict__ in, const float* __restrict__ w, ConvGeo g, Epilogue e,
+                  int Lin, int Lq, int Lout) {
+  const int b = blockIdx.z;
+  const int n0 = blockIdx.y * 8;
+  const int q0 = blockIdx.x * (128 * ROWS) + threadIdx.x;
+  const int kch = g.K >> 3;
+
+  float acc[ROWS][8];
+#pragma unroll
+  for (int i = 0; i < ROWS; ++i)
+#pragma unroll
+    for (int n = 0; n < 8; ++n) acc[i][n] = 0.f;
+
+  const T* in_b = in + static_cast<size_t>(b) * kch * Lin * 8;
+  for (int j = 0; j < g.taps; ++j) {
+    int row[ROWS];
+    bool ok[ROWS];
+    bool any = false;
+#pragma unroll
+    for (int i = 0; i < ROWS; ++i) {
+      const int q = q0 + i * 128;
+      row[i] = q * g.is + g.off0 + j * g.step;
+      ok[i] = (q < Lq) && (row[i] >= 0) && (row[i] < Lin);
+      any |= ok[i];
+    }
+    if (!__syncthreads_or(any)) continue;
+    const float* wj = w + static_cast<size_t>(j) * g.K * g.N + n0;
+    for (int cc = 0; cc < kch; ++cc) {
+      float xin[ROWS][8];
+#pragma unroll
+      for (int i = 0; i < ROWS; ++i) {
+        if (ok[i]) {
+          load8<T>(in_b + (static_cast<size_t>(cc) * Lin + row[i]) * 8, xin[i]);
+        } else {
+#pragma unroll
+          for (int c = 0; c < 8; ++c) xin[i][c] = 0.f;
+        }
+      }
+      const float* wp = wj + static_cast<size_t>(cc) * 8 * g.N;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const float4 w0 = __ldg(reinterpret_cast<const float4*>(wp + static_cast<size_t>(c) * g.N));
+        const float4 w1 = __ldg(reinterpret_cast<const float4*>(wp + static_cast<size_t>(c) * g.N) + 1);
+#pragma unroll
+        for (int i = 0; i < ROWS; ++i) {
+          const float x = xin[i][c];
+          acc[i][0] = fmaf(x, w0.x, acc[i][0]);
+          acc[i][1] = fmaf(x, w0.y, acc[i][1]);
+          acc[i][2] = fmaf(x, w0.z, acc[i][2]);
+          acc[i][3] = fmaf(x, w0.w, acc[i][3]);
+          acc[i][4] = fmaf(x, w1.x, acc[i][4]);
+          acc[i][5] = fmaf(x, w1.y, acc[i][5]);
+          acc[i][6] = fmaf(x, w1.z, acc[i][6]);
+          acc[i][7] = fmaf(x, w1.w, acc[i][7]);
+        }
+      }
+    }
+  }
+
+  // epilogue
+  const int r = n0 / g.creal;
+  const int ch0 = n0 - r * g.creal;
+#pragma unroll
+  for (int i = 0; i < ROWS; ++i) {
+    const int q = q0 + i * 128;
+    if (q >= Lq) continue;
+    const int ro = q * g.os + r - g.p;
+    if (ro < 0 || ro >= Lout) continue;
+    const size_t o = blk_off(b, ch0, ro, g.creal, Lout);
+    float v[8];
+#pragma unroll
+    for (int n = 0; n < 8; ++n) v[n] = acc[i][n];
+    if (e.bias) {
+#pragma unroll
+      for (int n = 0; n < 8; ++n) v[n] += __ldg(e.bias + ch0 + n);
+    }
+    if (e.bias2) {
+#pragma unroll
+      for (int n = 0; n < 8; ++n) v[n] += __ldg(e.bias2 + static_cast<size_t>(b) * g.creal + ch0 + n);
+    }
+    if (e.mask) {
+      float m[8];
+      load8<T>(reinterpret_cast<const T*>(e.mask) + o, m);
+#pragma unroll
+      for (int n = 0; n < 8; ++n) v[n] *= (m[n] > 0.f ? 1.f : e.mask_slope);
+    }
+#pragma unroll
+    for (int n = 0; n < 8; ++n) v[n] *= e.scale;
+    if (e.res) {
+      float t[8];
+      load8<float>(e.res + o, t);
+#pragma unroll
+      for (int n = 0; n < 8; ++n) v[n] += t[n];
+    }
+    if (e.res2) {
+      float t[8];
+      load8<float>(e.res2 + o, t);
+#pragma unroll
+      for (int n = 0; n < 8; ++n) v[n] += t[n];
+    }
+    if (e.out_raw) store8<float>(e.out_raw + o, v);
+    if (e.out_t) {
+      float a[8];
+#pragma unroll
+      for (int n = 0; n < 8; ++n) a[n] = lrelu(v[n] * e.tscale, e.act_slope);
+      store8<T>(reinterpret_cast<T*>(e.out_t) + o, a);
+    }
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
+// Weight gradient of the generalised convolution (fwd geometry g):
+//   dWp[j][c][n] += sum_{b,q} in[b][q*is + off0 + j*step][c] * dout[b][q*os + n/creal - p][n % creal]
+// grid = (taps * K/8 * N/8, splits), block = 256; one 8x8 block of dWp per CTA, fp32 atomics to combine
+// the time splits (dWp must be zeroed by the caller).
+// -------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+gconv_wgrad_simt_kernel(const T* __restrict__ in, const T* __restrict__ dout, float* __restrict__ dwp,
+                        ConvGeo g, int B, int Lin, int Lq, int Lout, int rows_per_split) {
+  const int kch = g.K >> 3, nch = g.N >> 3;
+  int id = blockIdx.x;
+  const int nc = id % nch; id /= nch;
+  const int cc = id % kch; id /= kch;
+  const int j = id;
+  const int n0 = nc * 8;
+  const int r = n0 / g.creal;
+  const int ch0 = n0 - r * g.creal;
+
+  const long long total = static_cast<long long>(B) * Lq;
+  const long long begin = static_cast<long long>(blockIdx.y) * rows_per_split;
+  long long end = begin + rows_per_split;
+  if (end > total) end = total;
+
+  float acc[8][8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c)
+#pragma unroll
+    for (int n = 0; n < 8; ++n) acc[c][n] = 0.f;
+
+  for (long long idx = begin + threadIdx.x; idx < end; idx += 256) {
+    const int b = static_cast<int>(idx / Lq);
+    const int q = static_cast<int>(idx - static_cast<long long>(b) * Lq);
+    const int ri = q * g.is + g.off0 + j * g.step;
+    const int ro = q * g.os + r - g.p;
+    if (ri < 0 || ri >= Lin || ro < 0 || ro >= Lout) continue;
+    float x[8], d[8];
+    load8<T>(in + blk_off(b, cc * 8, ri, g.K, Lin), x);
+    load8<T>(dout + blk_off(b, ch0, ro, g.creal, Lout), d);
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+#pragma unroll
+      for (int n = 0; n < 8; ++n) acc[c][n] = fmaf(x[c], d[n], acc[c][n]);
+  }
+
+  __shared__ float red[8][64];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int c = 0; c < 8; ++c)
+#pragma unroll
+    for (int n = 0; n < 8; ++n) {
+      const float s = warp_sum(acc[c][n]);
+      if (lane == 0) red[warp][c * 8 + n] = s;
+    }
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    float s = 0.f;
+#pragma unroll
+    for (int wv = 0; wv < 8; ++wv) s += red[wv][threadIdx.x];
+    const int c = threadIdx.x >> 3, n = threadIdx.x & 7;
+    atomicAdd(dwp + (static_cast<size_t>(j) * g.K + cc * 8 + c) * g.N + n0 + n, s);
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
+// Column sums over time (bias gradients): out[(per_batch ? b*C : 0) + c] += sum_t d[b][c][t].
+// grid = (C/8, B, splits), block = 256.  `out` must be zeroed by the caller.
+// -------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+colsum_kernel(const T* __restrict__ d, float* __restrict__ out, int C, int L, int per_batch) {
+  const int cg = blockIdx.x, b = blockIdx.y;
+  const int chunk = (L + gridDim.z - 1) / gridDim.z;
+  const int t0 = blockIdx.z * chunk;
+  const int t1 = min(L, t0 + chunk);
+  float acc[8];
+#pragma unroll
+  for (int n = 0; n < 8; ++n) acc[n] = 0.f;
+  const T* base = d + (static_cast<size_t>(b) * (C >> 3) + cg) * L * 8;
+  for (int t = t0 + threadIdx.x; t < t1; t += 256) {
+    float v[8];
+    load8<T>(base + static_cast<size_t>(t) * 8, v);
+#pragma unroll
+    for (int n = 0; n < 8; ++n) acc[n] += v[n];
+  }
+  __shared__ float red[8][8];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int n = 0; n < 8; ++n) {
+    const float s = warp_sum(acc[n]);
+    if (lane == 0) red[warp][n] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    float s = 0.f;
+#pragma unroll
+    for (int wv = 0; wv < 8; ++wv) s += red[wv][threadIdx.x];
+    atomicAdd(out + (per_batch ? static_cast<size_t>(b) * C : 0) + cg * 8 + threadIdx.x, s);
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
+// Boundary layout changes.
+// -------------------------------------------------------------------------------------------------
+// x: fp32 [B, C, L] with element strides -> blocked T.  grid = (ceil(L/128), C/8, B), block = 128.
+template <typename T>
+__global__ void __launch_bounds__(128)
+ncl_to_blocked_kernel(const float* __restrict__ x, long long sb, long long sc, long long st,
+                      T* __restrict__ out, int C, int L) {
+  const int t = blockIdx.x * 128 + threadIdx.x;
+  if (t >= L) return;
+  const int cg = blockIdx.y, b = blockIdx.z;
+  float v[8];
+#pragma unroll
+  for (int n = 0; n < 8; ++n) v[n] = __ldg(x + b * sb + (cg * 8 + n) * sc + t * st);
+  store8<T>(out + blk_off(b, cg * 8, t, C, L), v);
+}
+
+// blocked fp32 -> contiguous fp32 [B, C, L].
+__global__ void __launch_bounds__(128)
+blocked_to_ncl_kernel(const float* __restrict__ in, float* __restrict__ out, int C, int L) {
+  const int t = blockIdx.x * 128 + threadIdx.x;
+  if (t >= L) return;
+  const int cg = blockIdx.y, b = blockIdx.z;
+  float v[8];
+  load8<float>(in + blk_off(b, cg * 8, t, C, L), v);
+#pragma unroll
+  for (int n = 0; n < 8; ++n) out[(static_cast<size_t>(b) * C + cg * 8 + n) * L + t] = v[n];
+}
+
+// -------------------------------------------------------------------------------------------------
+// cond (speaker conditioning, 1x1 conv on a length-1 input): cb[b][n] = bias[n] + sum_c w[n][c] g[b][c]
+// grid = (ceil(N/128), B), block = 128.
+// -------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+cond_fwd_kernel(const float* __restrict__ w, const float* __restrict__ bias, const float* __restrict__ gv,
+                float* __restrict__ cb, int N, int G) {
+  const int n = blockIdx.x * 128 + threadIdx.x, b = blockIdx.y;
+  if (n >= N) return;
+  float s = bias[n];
+  for (int c = 0; c < G; ++c) s = fmaf(w[static_cast<size_t>(n) * G + c], gv[static_cast<size_t>(b) * G + c], s);
+  cb[static_cast<size_t>(b) * N + n] = s;
+}
+
+// Backward of cond + conv_pre.bias from dcb[b][n] = sum_t d0[b][t][n].
+//   d_pre_bias[n] = sum_b dcb ; d_cond_bias[n] = same ; d_cond_w[n][c] = sum_b dcb[b][n] g[b][c]
+//   dg[b][c] = sum_n dcb[b][n] w[n][c]
+// grid = (ceil(max(N*G, B*G, N)/256)), block = 256.  Null pointers skip the respective output.
+__global__ void __launch_bounds__(256)
+cond_bwd_kernel(const float* __restrict__ dcb, const float* __restrict__ w, const float* __restrict__ gv,
+                float* __restrict__ d_pre_bias, float* __restrict__ d_cond_bias, float* __restrict__ d_cond_w,
+                float* __restrict__ dg, int B, int N, int G) {
+  const long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
+  if (i < N) {
+    float s = 0.f;
+    for (int b = 0; b < B; ++b) s += dcb[static_cast<size_t>(b) * N + i];
+    if (d_pre_bias) d_pre_bias[i] = s;
+    if (d_cond_bias) d_cond_bias[i] = s;
+  }
+  if (d_cond_w && i < static_cast<long long>(N) * G) {
+    const int n = static_cast<int>(i / G), c = static_cast<int>(i % G);
+    float s = 0.f;
+    for (int b = 0; b < B; ++b) s = fmaf(dcb[static_cast<size_t>(b) * N + n], gv[static_cast<size_t>(b) * G + c], s);
+    d_cond_w[i] = s;
+  }
+  if (dg && i < static_cast<long long>(B) * G) {
+    const int b = static_cast<int>(i / G), c = static_cast<int>(i % G);
+    float s = 0.f;
+    for (int n = 0; n < N; ++n) s = fmaf(dcb[static_cast<size_t>(b) * N + n], w[static_cast<size_t>(n) * G + c], s);
+    dg[i] = s;
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
+// conv_post (C -> 1, k = 7, no bias) + tanh.  HBM-bound: 2*C bytes read per output sample (bf16).
+// w is the raw parameter [1][C][7].  grid = (ceil(L/256), B), block = 256, smem = C*7 floats.
+// -------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+conv_post_fwd_kernel(const T* __restrict__ a, const float* __restrict__ w, float* __restrict__ y, int C, int L) {
+  extern __shared__ float ws[];  // [7][C]
+  for (int i = threadIdx.x; i < C * 7; i += 256) {
+    const int c = i / 7, j = i - c * 7;
+    ws[j * C + c] = w[i];
+  }
+  __syncthreads();
+  const int t = blockIdx.x * 256 + threadIdx.x, b = blockIdx.y;
+  if (t >= L) return;
+  float acc = 0.f;
+  for (int cg = 0; cg < (C >> 3); ++cg) {
+    const T* base = a + (static_cast<size_t>(b) * (C >> 3) + cg) * L * 8;
+#pragma unroll
+    for (int j = 0; j < 7; ++j) {
+      const int r = t + j - 3;
+      if (r < 0 || r >= L) continue;
+      float v[8];
+      load8<T>(base + static_cast<size_t>(r) * 8, v);
+      const float* wr = ws + j * C + cg * 8;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) acc = fmaf(v[c], wr[c], acc);
+    }
+  }
+  y[static_cast<size_t>(b) * L + t] = tanhf(acc);
+}
+
+// Data gradient of conv_post + tanh, fused with the final leaky_relu(0.01) mask and the 1/num_kernels of the
+// branch mean:  G[b][t][c] = mask(a) * scale * sum_j w[c][j] * dpost[t + 3 - j],  dpost = dy * (1 - y^2).
+// grid = (ceil(L/128), C/8, B), block = 128.
+template <typename T>
+__global__ void __launch_bounds__(128)
+conv_post_dgrad_kernel(const float* __restrict__ dy, const float* __restrict__ y, const float* __restrict__ w,
+                       const T* __restrict__ a, float mask_slope, float scale, float* __restrict__ out_raw,
+                       T* __restrict__ out_t, int C, int L) {
+  const int t = blockIdx.x * 128 + threadIdx.x;
+  const int cg = blockIdx.y, b = blockIdx.z;
+  if (t >= L) return;
+  float dp[7];
+#pragma unroll
+  for (int j = 0; j < 7; ++j) {
+    const int s = t + 3 - j;
+    if (s >= 0 && s < L) {
+      const float yy = __ldg(y + static_cast<size_t>(b) * L + s);
+      dp[j] = __ldg(dy + static_cast<size_t>(b) * L + s) * (1.f - yy * yy);
+    } else {
+      dp[j] = 0.f;
+    }
+  }
+  const size_t o = blk_off(b, cg * 8, t, C, L);
+  float m[8], v[8];
+  load8<T>(a + o, m);
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < 7; ++j) s = fmaf(__ldg(w + (cg * 8 + c) * 7 + j), dp[j], s);
+    v[c] = s * (m[c] > 0.f ? 1.f : mask_slope) * scale;
+  }
+  if (out_raw) store8<float>(out_raw + o, v);
+  if (out_t) store8<T>(out_t + o, v);
+}
+
+// Weight gradient of conv_post: dw[c][j] += sum_{b,t} dpost[b][t] * a[b][t + j - 3][c]   (param layout [1][C][7]).
+// grid = (C/8, B, splits), block = 256.  dw must be zeroed.
+template <typename T>
+__global__ void __launch_bounds__(256)
+conv_post_wgrad_kernel(const float* __restrict__ dy, const float* __restrict__ y, const T* __restrict__ a,
+                       float* __restrict__ dw, int C, int L) {
+  const int cg = blockIdx.x, b = blockIdx.y;
+  const int chunk = (L + gridDim.z - 1) / gridDim.z;
+  const int r0 = blockIdx.z * chunk, r1 = min(L, r0 + chunk);
+  float acc[8][7];
+#pragma unroll
+  for (int c = 0; c < 8; ++c)
+#pragma unroll
+    for (int j = 0; j < 7; ++j) acc[c][j] = 0.f;
+  const T* base = a + (static_cast<size_t>(b) * (C >> 3) + cg) * L * 8;
+  for (int r = r0 + threadIdx.x; r < r1; r += 256) {
+    float v[8];
+    load8<T>(base + static_cast<size_t>(r) * 8, v);
+#pragma unroll
+    for (int j = 0; j < 7; ++j) {
+      const int t = r - j + 3;  // output position that reads row r with tap j
+      float dp = 0.f;
+      if (t >= 0 && t < L) {
+        const float yy = __ldg(y + static_cast<size_t>(b) * L + t);
+        dp = __ldg(dy + static_cast<size_t>(b) * L + t) * (1.f - yy * yy);
+      }
+#pragma unroll
+      for (int c = 0; c < 8; ++c) acc[c][j] = fmaf(v[c], dp, acc[c][j]);
+    }
+  }
+  __shared__ float red[8][56];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int c = 0; c < 8; ++c)
+#pragma unroll
+    for (int j = 0; j < 7; ++j) {
+      const float s = warp_sum(acc[c][j]);
+      if (lane == 0) red[warp][c * 7 + j] = s;
+    }
+  __syncthreads();
+  if (threadIdx.x < 56) {
+    float s = 0.f;
+#pragma unroll
+    for (int wv = 0; wv < 8; ++wv) s += red[wv][threadIdx.x];
+    atomicAdd(dw + cg * 56 + threadIdx.x, s);
+  }
+}
+
+}  // namespace vcd

@@ -1,0 +1,897 @@
+// C ABI of the B200-native VCVITS HiFi-GAN decoder (include/vcd.h).  Host-side schedule + launches.
+//
+// Reference interfaces replaced (all in /root/reference): Generator.__init__ / forward behind
+// SynthesizerTTS.dec (vits/model/synthesizers/synthesizer_tts.py:71-78,140), ResBlock1/ResBlock2
+// (vits/model/modules.py:186-247), weight_norm pre-hooks (modules.py:10), autograd backward of the train.py
+// step (vits/light/vcvits.py:54-148).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "plan.h"
+#include "simt_kernels.cuh"
+#include "tc_conv.cuh"
+
+using namespace vcd;
+
+// ---------------------------------------------------------------------------------------------------
+// error handling / counters
+// ---------------------------------------------------------------------------------------------------
+static thread_local char g_err[1024] = "";
+static std::atomic<uint64_t> g_launches{0};
+
+static int fail(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return 1;
+}
+
+#define CU_TRY(expr)                                                                           \
+  do {                                                                                         \
+    cudaError_t e__ = (expr);                                                                  \
+    if (e__ != cudaSuccess) return fail("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+  } while (0)
+
+#define LAUNCH_CHECK(what)                                                                     \
+  do {                                                                                         \
+    g_launches.fetch_add(1, std::memory_order_relaxed);                                        \
+    cudaError_t e__ = cudaGetLastError();                                                      \
+    if (e__ != cudaSuccess) return fail("launch of %s failed: %s", what, cudaGetErrorString(e__)); \
+  } while (0)
+
+#define TRY(expr)            \
+  do {                       \
+    int rc__ = (expr);       \
+    if (rc__) return rc__;   \
+  } while (0)
+
+extern "C" const char* vcd_version(void) { return "vcd 0.1 (sm_100a; tcgen05/TMA + FFMA paths)"; }
+extern "C" const char* vcd_last_error(void) { return g_err; }
+extern "C" uint64_t vcd_launch_count(int reset) {
+  return reset ? g_launches.exchange(0) : g_launches.load();
+}
+
+static inline size_t esize(int mode) { return mode == VCD_MODE_FP32 ? 4 : 2; }
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// ---------------------------------------------------------------------------------------------------
+// plan construction
+// ---------------------------------------------------------------------------------------------------
+static int add_param(vcd_plan* p, const std::string& name, std::initializer_list<int64_t> shape) {
+  ParamInfo pi;
+  pi.name = name;
+  pi.ndim = static_cast<int>(shape.size());
+  pi.numel = 1;
+  int i = 0;
+  pi.shape[0] = pi.shape[1] = pi.shape[2] = 1;
+  for (int64_t s : shape) {
+    pi.shape[i++] = s;
+    pi.numel *= s;
+  }
+  p->params.push_back(pi);
+  return static_cast<int>(p->params.size()) - 1;
+}
+
+static int add_conv(vcd_plan* p, const std::string& name, int cin, int cout, int k, int dil, bool wn, bool bias) {
+  Layer L{};
+  L.name = name;
+  L.kind = LK_CONV;
+  L.cin = cin; L.cout = cout; L.k = k; L.dil = dil; L.u = 1;
+  L.pad = dil * (k - 1) / 2;
+  L.wn = wn;
+  // state_dict order of old-style weight_norm: bias, weight_g, weight_v ; plain conv: weight, bias
+  if (wn) {
+    L.p_b = bias ? add_param(p, name + ".bias", {cout}) : -1;
+    L.p_g = add_param(p, name + ".weight_g", {cout, 1, 1});
+    L.p_w = add_param(p, name + ".weight_v", {cout, cin, k});
+  } else {
+    L.p_w = add_param(p, name + ".weight", {cout, cin, k});
+    L.p_g = -1;
+    L.p_b = bias ? add_param(p, name + ".bias", {cout}) : -1;
+  }
+  L.fwd = ConvGeo{k, cin, cout, 1, -L.pad, dil, 1, 0, cout};
+  L.dgr = ConvGeo{k, cout, cin, 1, -L.pad, dil, 1, 0, cin};
+  L.map_fwd = WeightMap{SRC_CONV_FWD, cin, cout, k, 1};
+  L.map_dgr = WeightMap{SRC_CONV_DGRAD, cin, cout, k, 1};
+  p->layers.push_back(L);
+  return static_cast<int>(p->layers.size()) - 1;
+}
+
+static int add_convt(vcd_plan* p, const std::string& name, int cin, int cout, int k, int u) {
+  Layer L{};
+  L.name = name;
+  L.kind = LK_CONVT;
+  L.cin = cin; L.cout = cout; L.k = k; L.dil = 1; L.u = u;
+  L.pad = (k - u) / 2;
+  L.wn = true;
+  L.p_b = add_param(p, name + ".bias", {cout});
+  L.p_g = add_param(p, name + ".weight_g", {cin, 1, 1});
+  L.p_w = add_param(p, name + ".weight_v", {cin, cout, k});
+  const int m = (k + u - 1) / u;
+  // forward, scatter form: Z[q][(r,co)] = sum_{s<m} x[q-s] W[:,co,s*u+r]  ->  y[q*u + r - pad][co]
+  L.fwd = ConvGeo{m, cin, u * cout, 1, 0, -1, u, L.pad, cout};
+  // data gradient: dx[i][ci] = sum_j sum_co dy[i*u - pad + j][co] W[ci][co][j]
+  L.dgr = ConvGeo{k, cout, cin, u, -L.pad, 1, 1, 0, cin};
+  L.map_fwd = WeightMap{SRC_CONVT_FWD, cin, cout, k, u};
+  L.map_dgr = WeightMap{SRC_CONVT_DGRAD, cin, cout, k, u};
+  p->layers.push_back(L);
+  return static_cast<int>(p->layers.size()) - 1;
+}
+
+template <typename J>
+static int upload_jobs(const std::vector<J>& jobs, J** dptr) {
+  *dptr = nullptr;
+  if (jobs.empty()) return 0;
+  CU_TRY(cudaMalloc(dptr, jobs.size() * sizeof(J)));
+  CU_TRY(cudaMemcpy(*dptr, jobs.data(), jobs.size() * sizeof(J), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+extern "C" int vcd_plan_create(const vcd_config* cfg, vcd_plan** out_plan) {
+  if (!cfg || !out_plan) return fail("vcd_plan_create: null argument");
+  *out_plan = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail("vcd_plan_create: no CUDA device available (this library has no CPU fallback)");
+  const int S = cfg->num_upsamples, NB = cfg->num_kernels;
+  if (S < 1 || S > VCD_MAX_UPSAMPLES) return fail("num_upsamples must be in [1,%d]", VCD_MAX_UPSAMPLES);
+  if (NB < 1 || NB > VCD_MAX_KERNELS) return fail("num_kernels must be in [1,%d]", VCD_MAX_KERNELS);
+  if (cfg->initial_channel % 8) return fail("initial_channel (%d) must be a multiple of 8", cfg->initial_channel);
+  if (cfg->gin_channels < 0) return fail("gin_channels must be >= 0");
+  if (cfg->upsample_initial_channel % (8 << S))
+    return fail("upsample_initial_channel (%d) must be a multiple of %d so that every stage keeps a multiple "
+                "of 8 channels (blocked channels-last layout)", cfg->upsample_initial_channel, 8 << S);
+  for (int i = 0; i < S; ++i) {
+    const int u = cfg->upsample_rates[i], k = cfg->upsample_kernel_sizes[i];
+    if (u < 1 || k < u || ((k - u) & 1))
+      return fail("upsample %d: need kernel >= rate and (kernel - rate) even (got k=%d, u=%d)", i, k, u);
+  }
+  for (int j = 0; j < NB; ++j) {
+    if (!(cfg->resblock_kernel_sizes[j] & 1)) return fail("resblock kernel sizes must be odd");
+    for (int d = 0; d < (cfg->resblock == 1 ? 3 : 2); ++d)
+      if (cfg->resblock_dilation_sizes[j][d] < 1) return fail("resblock dilations must be >= 1");
+  }
+
+  vcd_plan* p = new vcd_plan();
+  p->cfg = *cfg;
+  CU_TRY(cudaGetDevice(&p->device));
+  CU_TRY(cudaDeviceGetAttribute(&p->num_sms, cudaDevAttrMultiProcessorCount, p->device));
+
+  // ---- layers + parameters, in the reference's state_dict order ----
+  const int C0 = cfg->upsample_initial_channel;
+  p->l_pre = add_conv(p, "conv_pre", cfg->initial_channel, C0, 7, 1, false, true);
+  p->stages.resize(S);
+  int ch = C0;
+  p->hop = 1;
+  for (int i = 0; i < S; ++i) {
+    StageDesc& st = p->stages[i];
+    st.cin = ch; st.cout = ch / 2; st.u = cfg->upsample_rates[i]; st.k = cfg->upsample_kernel_sizes[i];
+    st.up_layer = add_convt(p, "ups." + std::to_string(i), st.cin, st.cout, st.k, st.u);
+    ch /= 2;
+    p->hop *= st.u;
+  }
+  ch = C0;
+  const int npairs = cfg->resblock == 1 ? 3 : 2;
+  for (int i = 0; i < S; ++i) {
+    ch /= 2;
+    StageDesc& st = p->stages[i];
+    st.convs.resize(NB);
+    for (int j = 0; j < NB; ++j) {
+      const std::string rb = "resblocks." + std::to_string(i * NB + j);
+      const int k = cfg->resblock_kernel_sizes[j];
+      st.convs[j].resize(npairs);
+      if (cfg->resblock == 1) {
+        // state_dict order: convs1.0..2 then convs2.0..2 (modules.py:189-201)
+        for (int q = 0; q < npairs; ++q)
+          st.convs[j][q].push_back(add_conv(p, rb + ".convs1." + std::to_string(q), ch, ch, k,
+                                            cfg->resblock_dilation_sizes[j][q], true, true));
+        for (int q = 0; q < npairs; ++q)
+          st.convs[j][q].push_back(add_conv(p, rb + ".convs2." + std::to_string(q), ch, ch, k, 1, true, true));
+      } else {
+        for (int q = 0; q < npairs; ++q)
+          st.convs[j][q].push_back(add_conv(p, rb + ".convs." + std::to_string(q), ch, ch, k,
+                                            cfg->resblock_dilation_sizes[j][q], true, true));
+      }
+    }
+  }
+  p->p_post_w = add_param(p, "conv_post.weight", {1, ch, 7});
+  if (cfg->gin_channels) {
+    p->p_cond_w = add_param(p, "cond.weight", {C0, cfg->gin_channels, 1});
+    p->p_cond_b = add_param(p, "cond.bias", {C0});
+  }
+
+  // ---- backward segments ----
+  p->layers[p->l_pre].segment = S;
+  for (int i = 0; i < S; ++i) {
+    const int seg = S - 1 - i;
+    p->layers[p->stages[i].up_layer].segment = seg;
+    for (auto& br : p->stages[i].convs)
+      for (auto& pr : br)
+        for (int l : pr) p->layers[l].segment = seg;
+  }
+
+  // ---- arenas ----
+  long long nf32 = 0, nbf = 0, nnorm = 0;
+  for (Layer& L : p->layers) {
+    const long long nf = 1LL * L.fwd.taps * L.fwd.K * L.fwd.N, nd = 1LL * L.dgr.taps * L.dgr.K * L.dgr.N;
+    L.f32_fwd = nf32; nf32 += nf;
+    L.f32_dgr = nf32; nf32 += nd;
+    tc_layer_eligibility(L);
+    L.tc_fwd = L.tc_dgr = -1;
+    if (L.tc_ok_fwd) { L.tc_fwd = nbf; nbf += nf; }
+    if (L.tc_ok_dgr) { L.tc_dgr = nbf; nbf += nd; }
+    if (L.wn) { L.norm_off = static_cast<int>(nnorm); nnorm += p->params[L.p_w].shape[0]; }
+  }
+  // gradient scratch, grouped by segment so each segment zeroes one contiguous range
+  p->segments.resize(S + 1);
+  long long ng = 0;
+  for (int seg = 0; seg <= S; ++seg) {
+    p->segments[seg].scratch_begin = ng;
+    if (seg == 0) { p->post_dw = ng; ng += p->params[p->p_post_w].numel; }
+    for (Layer& L : p->layers) {
+      if (L.segment != seg) continue;
+      L.dwp = ng; ng += 1LL * L.fwd.taps * L.fwd.K * L.fwd.N;
+      L.dbias = -1;
+      if (L.p_b >= 0 && &L != &p->layers[p->l_pre]) { L.dbias = ng; ng += L.cout; }
+      ng = (ng + 63) / 64 * 64;
+    }
+    p->segments[seg].scratch_end = ng;
+  }
+  p->n_f32 = nf32; p->n_bf16 = nbf; p->n_norms = nnorm; p->n_gscratch = ng;
+  CU_TRY(cudaMalloc(&p->d_f32, std::max<long long>(nf32, 1) * sizeof(float)));
+  CU_TRY(cudaMalloc(&p->d_bf16, std::max<long long>(nbf, 1) * sizeof(bf16)));
+  CU_TRY(cudaMalloc(&p->d_norms, std::max<long long>(nnorm, 1) * sizeof(float)));
+  CU_TRY(cudaMalloc(&p->d_gscratch, std::max<long long>(ng, 1) * sizeof(float)));
+  const size_t np = p->params.size();
+  CU_TRY(cudaMalloc(&p->d_params, np * sizeof(float*)));
+  CU_TRY(cudaMalloc(&p->d_dparams, np * sizeof(float*)));
+  p->h_params.assign(np, nullptr);
+  p->h_dparams.assign(np, nullptr);
+
+  // ---- fold job tables ----
+  {
+    std::vector<NormJob> nj;
+    int blk = 0;
+    for (const Layer& L : p->layers) {
+      if (!L.wn) continue;
+      const ParamInfo& pv = p->params[L.p_w];
+      NormJob j{L.p_w, static_cast<int>(pv.shape[0]), static_cast<int>(pv.numel / pv.shape[0]), L.norm_off, blk};
+      blk += j.rows;
+      nj.push_back(j);
+    }
+    p->n_norm_jobs = static_cast<int>(nj.size());
+    p->n_norm_blocks = blk;
+    TRY(upload_jobs(nj, &p->d_norm_jobs));
+  }
+  for (int mode = 0; mode < 2; ++mode) {
+    std::vector<PackJob> pj;
+    int blk = 0;
+    auto push = [&](const Layer& L, bool dgrad, int fmt) {
+      const ConvGeo& g = dgrad ? L.dgr : L.fwd;
+      PackJob j{};
+      j.map = dgrad ? L.map_dgr : L.map_fwd;
+      j.p_w = L.p_w; j.p_g = L.p_g; j.norm_off = L.wn ? L.norm_off : 0;
+      j.taps = g.taps; j.K = g.K; j.N = g.N;
+      j.NT = dgrad ? L.nt_dgr : L.nt_fwd;
+      j.fmt = fmt;
+      j.dst_off = fmt == FMT_F32 ? (dgrad ? L.f32_dgr : L.f32_fwd) : (dgrad ? L.tc_dgr : L.tc_fwd);
+      j.numel = 1LL * g.taps * g.K * g.N;
+      j.first_block = blk;
+      blk += static_cast<int>((j.numel + 255) / 256);
+      pj.push_back(j);
+    };
+    for (const Layer& L : p->layers) {
+      const bool tcf = mode == VCD_MODE_BF16 && L.tc_ok_fwd, tcd = mode == VCD_MODE_BF16 && L.tc_ok_dgr;
+      push(L, false, tcf ? FMT_TC : FMT_F32);
+      push(L, true, tcd ? FMT_TC : FMT_F32);
+    }
+    p->n_pack_jobs[mode] = static_cast<int>(pj.size());
+    p->n_pack_blocks[mode] = blk;
+    TRY(upload_jobs(pj, &p->d_pack_jobs[mode]));
+  }
+  // ---- unfold job tables (per segment) ----
+  for (int seg = 0; seg <= S; ++seg) {
+    std::vector<UnfoldJob> uj;
+    int blk = 0;
+    SegmentJobs& sj = p->segments[seg];
+    auto copy_job = [&](int param, long long src) {
+      UnfoldJob j{};
+      j.kind = 1; j.p_w = param; j.p_g = -1; j.src_off = src; j.numel = p->params[param].numel;
+      j.rows = static_cast<int>((j.numel + 255) / 256);
+      j.first_block = blk; blk += j.rows;
+      uj.push_back(j);
+      sj.params.push_back(param);
+    };
+    if (seg == 0) copy_job(p->p_post_w, p->post_dw);
+    for (const Layer& L : p->layers) {
+      if (L.segment != seg) continue;
+      const ParamInfo& pw = p->params[L.p_w];
+      UnfoldJob j{};
+      j.map = L.map_fwd; j.kind = 0; j.p_w = L.p_w; j.p_g = L.p_g; j.norm_off = L.wn ? L.norm_off : 0;
+      j.rows = static_cast<int>(pw.shape[0]); j.row_len = static_cast<int>(pw.numel / pw.shape[0]);
+      j.K = L.fwd.K; j.N = L.fwd.N; j.src_off = L.dwp;
+      j.first_block = blk; blk += j.rows;
+      uj.push_back(j);
+      sj.params.push_back(L.p_w);
+      if (L.p_g >= 0) sj.params.push_back(L.p_g);
+      if (L.dbias >= 0) copy_job(L.p_b, L.dbias);
+    }
+    if (seg == S) {  // written directly by cond_bwd_kernel
+      sj.params.push_back(p->layers[p->l_pre].p_b);
+      if (p->p_cond_w >= 0) { sj.params.push_back(p->p_cond_w); sj.params.push_back(p->p_cond_b); }
+    }
+    sj.njobs = static_cast<int>(uj.size());
+    sj.nblocks = blk;
+    TRY(upload_jobs(uj, &sj.d_jobs));
+  }
+  TRY(tc_plan_init(p));
+  *out_plan = p;
+  return 0;
+}
+
+extern "C" void vcd_plan_destroy(vcd_plan* p) {
+  if (!p) return;
+  cudaFree(p->d_f32); cudaFree(p->d_bf16); cudaFree(p->d_norms); cudaFree(p->d_gscratch);
+  cudaFree(p->d_params); cudaFree(p->d_dparams); cudaFree(p->d_norm_jobs);
+  cudaFree(p->d_pack_jobs[0]); cudaFree(p->d_pack_jobs[1]);
+  for (auto& s : p->segments) cudaFree(s.d_jobs);
+  delete p;
+}
+
+extern "C" int vcd_num_params(const vcd_plan* p) { return p ? static_cast<int>(p->params.size()) : 0; }
+extern "C" int vcd_param_info(const vcd_plan* p, int i, const char** name, int64_t shape[3], int* ndim) {
+  if (!p || i < 0 || i >= static_cast<int>(p->params.size())) return fail("vcd_param_info: bad index");
+  const ParamInfo& pi = p->params[i];
+  if (name) *name = pi.name.c_str();
+  if (shape) { shape[0] = pi.shape[0]; shape[1] = pi.shape[1]; shape[2] = pi.shape[2]; }
+  if (ndim) *ndim = pi.ndim;
+  return 0;
+}
+extern "C" int64_t vcd_total_param_elems(const vcd_plan* p) {
+  int64_t n = 0;
+  if (p) for (auto& pi : p->params) n += pi.numel;
+  return n;
+}
+extern "C" int vcd_hop(const vcd_plan* p) { return p ? p->hop : 0; }
+extern "C" int vcd_num_backward_segments(const vcd_plan* p) { return p ? static_cast<int>(p->segments.size()) : 0; }
+extern "C" int vcd_segment_params(const vcd_plan* p, int seg, int* idx, int cap) {
+  if (!p || seg < 0 || seg >= static_cast<int>(p->segments.size())) return -1;
+  const auto& v = p->segments[seg].params;
+  for (int i = 0; i < static_cast<int>(v.size()) && i < cap; ++i) idx[i] = v[i];
+  return static_cast<int>(v.size());
+}
+
+// ---------------------------------------------------------------------------------------------------
+// workspace layout
+// ---------------------------------------------------------------------------------------------------
+namespace {
+struct StageWs {
+  size_t u_raw = 0, ua = 0;
+  std::vector<std::vector<size_t>> ma, xa;  // [branch][pair]
+};
+struct WsLayout {
+  size_t xin = 0, cb = 0, dcb = 0;
+  std::vector<size_t> a;
+  std::vector<StageWs> st;
+  size_t xr[2] = {0, 0}, sum[2] = {0, 0};
+  size_t Gr[2] = {0, 0}, Gt[2] = {0, 0}, dm = 0, bsum[2] = {0, 0}, du = 0, Gi_r[2] = {0, 0}, Gi_t[2] = {0, 0};
+  size_t d0 = 0, dxb = 0;
+  size_t total = 0;
+};
+
+WsLayout make_layout(const vcd_plan* p, int mode, int B, int T, bool save) {
+  WsLayout w;
+  const size_t es = esize(mode);
+  size_t top = 0;
+  auto alloc = [&](size_t bytes) {
+    const size_t o = top;
+    top = align_up(top + bytes, 256);
+    return o;
+  };
+  const int S = static_cast<int>(p->stages.size()), NB = p->cfg.num_kernels;
+  const int npairs = p->cfg.resblock == 1 ? 3 : 2;
+  const size_t C0 = p->cfg.upsample_initial_channel;
+  w.xin = alloc(es * B * p->cfg.initial_channel * T);
+  w.cb = alloc(4 * B * C0);
+  w.dcb = alloc(4 * B * C0);
+  w.a.resize(S + 1);
+  w.a[0] = alloc(es * B * C0 * T);
+  size_t L = T, emax = 0;
+  std::vector<size_t> E(S);
+  for (int i = 0; i < S; ++i) {
+    L *= p->stages[i].u;
+    E[i] = static_cast<size_t>(B) * p->stages[i].cout * L;
+    emax = std::max(emax, E[i]);
+    w.a[i + 1] = alloc(es * E[i]);
+  }
+  w.st.resize(S);
+  size_t shared_ua = 0, shared_ma = 0, shared_xa[2] = {0, 0};
+  if (!save) {
+    shared_ua = alloc(es * emax);
+    shared_ma = alloc(es * emax);
+    shared_xa[0] = alloc(es * emax);
+    shared_xa[1] = alloc(es * emax);
+  }
+  const size_t u_raw = alloc(4 * emax);
+  for (int i = 0; i < S; ++i) {
+    StageWs& s = w.st[i];
+    s.u_raw = u_raw;
+    s.ua = save ? alloc(es * E[i]) : shared_ua;
+    s.ma.assign(NB, std::vector<size_t>(npairs, 0));
+    s.xa.assign(NB, std::vector<size_t>(npairs, 0));
+    for (int j = 0; j < NB; ++j)
+      for (int q = 0; q < npairs; ++q) {
+        if (p->cfg.resblock == 1) s.ma[j][q] = save ? alloc(es * E[i]) : shared_ma;
+        if (q < npairs - 1) s.xa[j][q] = save ? alloc(es * E[i]) : shared_xa[q & 1];
+      }
+  }
+  for (int i = 0; i < 2; ++i) { w.xr[i] = alloc(4 * emax); w.sum[i] = alloc(4 * emax); }
+  if (save) {
+    // backward scratch: the fp32 forward scratch (u_raw, xr, sum) is dead by then and is reused
+    w.Gr[0] = w.xr[0]; w.Gr[1] = w.xr[1]; w.bsum[0] = w.sum[0]; w.bsum[1] = w.sum[1];
+    w.Gi_r[0] = u_raw; w.Gi_r[1] = alloc(4 * emax);
+    w.Gt[0] = alloc(es * emax); w.Gt[1] = alloc(es * emax);
+    w.dm = alloc(es * emax); w.du = alloc(es * emax);
+    w.Gi_t[0] = alloc(es * emax); w.Gi_t[1] = alloc(es * emax);
+    w.d0 = alloc(es * B * C0 * T);
+    w.dxb = alloc(4 * static_cast<size_t>(B) * p->cfg.initial_channel * T);
+  }
+  w.total = top;
+  return w;
+}
+}  // namespace
+
+extern "C" size_t vcd_workspace_bytes(const vcd_plan* p, int mode, int B, int T, int save) {
+  if (!p || B < 1 || T < 1) return 0;
+  return make_layout(p, mode, B, T, save != 0).total;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// fold
+// ---------------------------------------------------------------------------------------------------
+extern "C" int vcd_fold_weights(vcd_plan* p, int mode, const float* const* params, void* stream_) {
+  if (!p || !params) return fail("vcd_fold_weights: null argument");
+  if (mode != VCD_MODE_FP32 && mode != VCD_MODE_BF16) return fail("bad mode %d", mode);
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const size_t np = p->params.size();
+  bool changed = false;
+  for (size_t i = 0; i < np; ++i) {
+    if (!params[i]) return fail("vcd_fold_weights: parameter %s is null", p->params[i].name.c_str());
+    changed |= p->h_params[i] != params[i];
+  }
+  if (changed) {
+    std::copy(params, params + np, p->h_params.begin());
+    // pageable->device async copy is staged by the runtime before returning, so h_params may change later
+    CU_TRY(cudaMemcpyAsync(p->d_params, p->h_params.data(), np * sizeof(float*), cudaMemcpyHostToDevice, stream));
+  }
+  if (p->n_norm_blocks) {
+    wn_norm_kernel<<<p->n_norm_blocks, 128, 0, stream>>>(p->d_norm_jobs, p->n_norm_jobs, p->d_params, p->d_norms);
+    LAUNCH_CHECK("wn_norm_kernel");
+  }
+  wn_pack_kernel<<<p->n_pack_blocks[mode], 256, 0, stream>>>(p->d_pack_jobs[mode], p->n_pack_jobs[mode],
+                                                              p->d_params, p->d_norms, p->d_f32, p->d_bf16);
+  LAUNCH_CHECK("wn_pack_kernel");
+  p->folded[mode] = true;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// launch helpers
+// ---------------------------------------------------------------------------------------------------
+namespace {
+
+struct Ctx {
+  vcd_plan* p;
+  int mode, B;
+  cudaStream_t stream;
+  char* ws;
+};
+
+template <typename T>
+int launch_gconv_simt(const Ctx& c, const void* in, const float* w, const ConvGeo& g, const Epilogue& e,
+                      int Lin, int Lq, int Lout) {
+  if (Lq <= 128) {
+    dim3 grid((Lq + 127) / 128, g.N / 8, c.B);
+    gconv_simt_kernel<T, 1><<<grid, 128, 0, c.stream>>>(static_cast<const T*>(in), w, g, e, Lin, Lq, Lout);
+  } else {
+    dim3 grid((Lq + 255) / 256, g.N / 8, c.B);
+    gconv_simt_kernel<T, 2><<<grid, 128, 0, c.stream>>>(static_cast<const T*>(in), w, g, e, Lin, Lq, Lout);
+  }
+  LAUNCH_CHECK("gconv_simt_kernel");
+  return 0;
+}
+
+// One convolution (forward or data-gradient direction) of layer L.
+int run_conv(const Ctx& c, const Layer& L, bool dgrad, const void* in, int Lin, int Lq, int Lout, Epilogue e) {
+  const ConvGeo& g = dgrad ? L.dgr : L.fwd;
+  if (c.mode == VCD_MODE_BF16 && (dgrad ? L.tc_ok_dgr : L.tc_ok_fwd))
+    return tc_run_conv(c.p, L, dgrad, in, c.B, Lin, Lq, Lout, e, c.stream, g_launches, g_err, sizeof(g_err));
+  const float* w = c.p->d_f32 + (dgrad ? L.f32_dgr : L.f32_fwd);
+  if (c.mode == VCD_MODE_FP32) return launch_gconv_simt<float>(c, in, w, g, e, Lin, Lq, Lout);
+  return launch_gconv_simt<bf16>(c, in, w, g, e, Lin, Lq, Lout);
+}
+
+// Weight gradient (+ bias gradient) of layer L: in = layer input, dout = gradient w.r.t. the layer output.
+int run_wgrad(const Ctx& c, const Layer& L, const void* in, const void* dout, int Lin, int Lq, int Lout) {
+  const ConvGeo& g = L.fwd;
+  float* dwp = c.p->d_gscratch + L.dwp;
+  if (c.mode == VCD_MODE_BF16 && L.tc_ok_wgr) {
+    TRY(tc_run_wgrad(c.p, L, in, dout, dwp, c.B, Lin, Lq, Lout, c.stream, g_launches, g_err, sizeof(g_err)));
+  } else {
+    const long long total = 1LL * c.B * Lq;
+    const int blocks_x = g.taps * (g.K / 8) * (g.N / 8);
+    long long splits = std::max<long long>(1, std::min<long long>((total + 2047) / 2048,
+                                                                    std::max(1, 4 * c.p->num_sms * 8 / blocks_x)));
+    const int rows_per_split = static_cast<int>((total + splits - 1) / splits);
+    splits = (total + rows_per_split - 1) / rows_per_split;
+    dim3 grid(blocks_x, static_cast<unsigned>(splits));
+    if (c.mode == VCD_MODE_FP32)
+      gconv_wgrad_simt_kernel<float><<<grid, 256, 0, c.stream>>>(static_cast<const float*>(in),
+          static_cast<const float*>(dout), dwp, g, c.B, Lin, Lq, Lout, rows_per_split);
+    else
+      gconv_wgrad_simt_kernel<bf16><<<grid, 256, 0, c.stream>>>(static_cast<const bf16*>(in),
+          static_cast<const bf16*>(dout), dwp, g, c.B, Lin, Lq, Lout, rows_per_split);
+    LAUNCH_CHECK("gconv_wgrad_simt_kernel");
+  }
+  if (L.dbias >= 0) {
+    const int splits = std::max(1, std::min(64, Lout / 2048));
+    dim3 grid(L.cout / 8, c.B, splits);
+    if (c.mode == VCD_MODE_FP32)
+      colsum_kernel<float><<<grid, 256, 0, c.stream>>>(static_cast<const float*>(dout), c.p->d_gscratch + L.dbias, L.cout, Lout, 0);
+    else
+      colsum_kernel<bf16><<<grid, 256, 0, c.stream>>>(static_cast<const bf16*>(dout), c.p->d_gscratch + L.dbias, L.cout, Lout, 0);
+    LAUNCH_CHECK("colsum_kernel");
+  }
+  return 0;
+}
+
+Epilogue epi() {
+  Epilogue e{};
+  e.mask_slope = 1.f; e.scale = 1.f; e.tscale = 1.f; e.act_slope = 1.f;
+  return e;
+}
+
+int check_common(vcd_plan* p, int mode, int B, int T, void* ws, size_t ws_bytes, bool save) {
+  if (!p) return fail("null plan");
+  if (mode != VCD_MODE_FP32 && mode != VCD_MODE_BF16) return fail("bad mode %d", mode);
+  if (B < 1 || T < 1) return fail("B and T must be >= 1 (got B=%d, T=%d)", B, T);
+  if (!p->folded[mode]) return fail("vcd_fold_weights(mode=%d) must be called before forward/backward", mode);
+  const size_t need = make_layout(p, mode, B, T, save).total;
+  if (!ws || ws_bytes < need) return fail("workspace too small: need %zu bytes, got %zu", need, ws_bytes);
+  if (reinterpret_cast<uintptr_t>(ws) % 256) return fail("workspace must be 256-byte aligned");
+  return 0;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------
+// forward
+// ---------------------------------------------------------------------------------------------------
+extern "C" int vcd_forward(vcd_plan* p, int mode, const float* x, int64_t xs_b, int64_t xs_c, int64_t xs_t,
+                           const float* gvec, float* y, void* ws, size_t ws_bytes, int B, int T, int save_,
+                           void* stream_) {
+  const bool save = save_ != 0;
+  TRY(check_common(p, mode, B, T, ws, ws_bytes, save));
+  if (!x || !y) return fail("vcd_forward: null x or y");
+  if (gvec && !p->cfg.gin_channels) return fail("vcd_forward: g given but the plan has gin_channels = 0");
+  const WsLayout w = make_layout(p, mode, B, T, save);
+  Ctx c{p, mode, B, static_cast<cudaStream_t>(stream_), static_cast<char*>(ws)};
+  cudaStream_t stream = c.stream;
+  const bool f32 = mode == VCD_MODE_FP32;
+  const int S = static_cast<int>(p->stages.size()), NB = p->cfg.num_kernels;
+  const int npairs = p->cfg.resblock == 1 ? 3 : 2;
+  const int C0 = p->cfg.upsample_initial_channel, Cin0 = p->cfg.initial_channel;
+  auto P = [&](size_t off) { return static_cast<void*>(c.ws + off); };
+  auto PF = [&](size_t off) { return reinterpret_cast<float*>(c.ws + off); };
+
+  {  // latent -> blocked layout
+    dim3 grid((T + 127) / 128, Cin0 / 8, B);
+    if (f32) ncl_to_blocked_kernel<float><<<grid, 128, 0, stream>>>(x, xs_b, xs_c, xs_t, static_cast<float*>(P(w.xin)), Cin0, T);
+    else ncl_to_blocked_kernel<bf16><<<grid, 128, 0, stream>>>(x, xs_b, xs_c, xs_t, static_cast<bf16*>(P(w.xin)), Cin0, T);
+    LAUNCH_CHECK("ncl_to_blocked_kernel");
+  }
+  if (gvec) {
+    dim3 grid((C0 + 127) / 128, B);
+    cond_fwd_kernel<<<grid, 128, 0, stream>>>(p->h_params[p->p_cond_w], p->h_params[p->p_cond_b], gvec, PF(w.cb), C0,
+                                              p->cfg.gin_channels);
+    LAUNCH_CHECK("cond_fwd_kernel");
+  }
+  {  // conv_pre (+ cond) -> a[0] = lrelu(., 0.1)
+    const Layer& L = p->layers[p->l_pre];
+    Epilogue e = epi();
+    e.bias = p->h_params[L.p_b];
+    e.bias2 = gvec ? PF(w.cb) : nullptr;
+    e.out_t = P(w.a[0]);
+    e.act_slope = 0.1f;
+    TRY(run_conv(c, L, false, P(w.xin), T, T, T, e));
+  }
+  int Lcur = T;
+  for (int i = 0; i < S; ++i) {
+    const StageDesc& sd = p->stages[i];
+    const StageWs& sw = w.st[i];
+    const Layer& U = p->layers[sd.up_layer];
+    {
+      Epilogue e = epi();
+      e.bias = p->h_params[U.p_b];
+      e.out_raw = PF(sw.u_raw);
+      e.out_t = P(sw.ua);
+      e.act_slope = 0.1f;
+      TRY(run_conv(c, U, false, P(w.a[i]), Lcur, Lcur + U.fwd.taps - 1, Lcur * sd.u, e));
+    }
+    Lcur *= sd.u;
+    for (int j = 0; j < NB; ++j) {
+      const void* xin_t = P(sw.ua);
+      const float* xres = PF(sw.u_raw);
+      for (int q = 0; q < npairs; ++q) {
+        const bool last = q == npairs - 1;
+        const void* conv_in = xin_t;
+        if (p->cfg.resblock == 1) {
+          const Layer& L1 = p->layers[sd.convs[j][q][0]];
+          Epilogue e = epi();
+          e.bias = p->h_params[L1.p_b];
+          e.out_t = P(sw.ma[j][q]);
+          e.act_slope = 0.1f;
+          TRY(run_conv(c, L1, false, xin_t, Lcur, Lcur, Lcur, e));
+          conv_in = P(sw.ma[j][q]);
+        }
+        const Layer& L2 = p->layers[sd.convs[j][q].back()];
+        Epilogue e = epi();
+        e.bias = p->h_params[L2.p_b];
+        e.res = xres;
+        if (!last) {
+          e.out_raw = PF(w.xr[q & 1]);
+          e.out_t = P(sw.xa[j][q]);
+          e.act_slope = 0.1f;
+          xres = PF(w.xr[q & 1]);
+          xin_t = P(sw.xa[j][q]);
+        } else {
+          e.res2 = j > 0 ? PF(w.sum[(j - 1) & 1]) : nullptr;
+          if (j < NB - 1) {
+            e.out_raw = PF(w.sum[j & 1]);
+          } else {  // mean over branches + the next leaky_relu, fused
+            e.out_t = P(w.a[i + 1]);
+            e.tscale = 1.f / NB;
+            e.act_slope = (i == S - 1) ? 0.01f : 0.1f;
+          }
+        }
+        TRY(run_conv(c, L2, false, conv_in, Lcur, Lcur, Lcur, e));
+      }
+    }
+  }
+  {  // conv_post + tanh
+    const int C = p->stages[S - 1].cout;
+    dim3 grid((Lcur + 255) / 256, B);
+    const size_t smem = sizeof(float) * C * 7;
+    if (f32) conv_post_fwd_kernel<float><<<grid, 256, smem, stream>>>(static_cast<const float*>(P(w.a[S])), p->h_params[p->p_post_w], y, C, Lcur);
+    else conv_post_fwd_kernel<bf16><<<grid, 256, smem, stream>>>(static_cast<const bf16*>(P(w.a[S])), p->h_params[p->p_post_w], y, C, Lcur);
+    LAUNCH_CHECK("conv_post_fwd_kernel");
+  }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// backward
+// ---------------------------------------------------------------------------------------------------
+extern "C" int vcd_backward(vcd_plan* p, int mode, const float* dy, const float* y, const float* gvec, float* dx,
+                            float* dg, float* const* dparams, void* ws, size_t ws_bytes, int B, int T,
+                            uint32_t segment_mask, void* stream_) {
+  TRY(check_common(p, mode, B, T, ws, ws_bytes, true));
+  if (!dy || !y || !dparams) return fail("vcd_backward: null dy, y or dparams");
+  const WsLayout w = make_layout(p, mode, B, T, true);
+  Ctx c{p, mode, B, static_cast<cudaStream_t>(stream_), static_cast<char*>(ws)};
+  cudaStream_t stream = c.stream;
+  const bool f32 = mode == VCD_MODE_FP32;
+  const int S = static_cast<int>(p->stages.size()), NB = p->cfg.num_kernels;
+  const int npairs = p->cfg.resblock == 1 ? 3 : 2;
+  const int C0 = p->cfg.upsample_initial_channel, Cin0 = p->cfg.initial_channel;
+  auto P = [&](size_t off) { return static_cast<void*>(c.ws + off); };
+  auto PF = [&](size_t off) { return reinterpret_cast<float*>(c.ws + off); };
+
+  const size_t np = p->params.size();
+  bool changed = false;
+  for (size_t i = 0; i < np; ++i) {
+    if (!dparams[i]) return fail("vcd_backward: gradient pointer of %s is null", p->params[i].name.c_str());
+    changed |= p->h_dparams[i] != dparams[i];
+  }
+  if (changed) {
+    std::copy(dparams, dparams + np, p->h_dparams.begin());
+    CU_TRY(cudaMemcpyAsync(p->d_dparams, p->h_dparams.data(), np * sizeof(float*), cudaMemcpyHostToDevice, stream));
+  }
+
+  std::vector<int> Ls(S + 1);
+  Ls[0] = T;
+  for (int i = 0; i < S; ++i) Ls[i + 1] = Ls[i] * p->stages[i].u;
+
+  auto begin_segment = [&](int seg) -> int {
+    const SegmentJobs& sj = p->segments[seg];
+    if (sj.scratch_end > sj.scratch_begin)
+      CU_TRY(cudaMemsetAsync(p->d_gscratch + sj.scratch_begin, 0, (sj.scratch_end - sj.scratch_begin) * sizeof(float), stream));
+    return 0;
+  };
+  auto end_segment = [&](int seg) -> int {
+    const SegmentJobs& sj = p->segments[seg];
+    if (sj.nblocks) {
+      wn_unfold_kernel<<<sj.nblocks, 256, 0, stream>>>(sj.d_jobs, sj.njobs, p->d_params, p->d_dparams, p->d_norms, p->d_gscratch);
+      LAUNCH_CHECK("wn_unfold_kernel");
+    }
+    return 0;
+  };
+
+  for (int seg = 0; seg <= S; ++seg) {
+    if (!(segment_mask & (1u << seg))) continue;
+    TRY(begin_segment(seg));
+    if (seg == 0) {  // conv_post + tanh backward -> G_init of the last stage
+      const int C = p->stages[S - 1].cout, L = Ls[S];
+      const int splits = std::max(1, std::min(64, L / 2048));
+      dim3 gw(C / 8, B, splits);
+      dim3 gd((L + 127) / 128, C / 8, B);
+      const float* wpost = p->h_params[p->p_post_w];
+      const int slot = (S - 1) & 1;
+      if (f32) {
+        conv_post_wgrad_kernel<float><<<gw, 256, 0, stream>>>(dy, y, static_cast<const float*>(P(w.a[S])), p->d_gscratch + p->post_dw, C, L);
+        LAUNCH_CHECK("conv_post_wgrad_kernel");
+        conv_post_dgrad_kernel<float><<<gd, 128, 0, stream>>>(dy, y, wpost, static_cast<const float*>(P(w.a[S])), 0.01f, 1.f / NB,
+                                                               PF(w.Gi_r[slot]), static_cast<float*>(P(w.Gi_t[slot])), C, L);
+      } else {
+        conv_post_wgrad_kernel<bf16><<<gw, 256, 0, stream>>>(dy, y, static_cast<const bf16*>(P(w.a[S])), p->d_gscratch + p->post_dw, C, L);
+        LAUNCH_CHECK("conv_post_wgrad_kernel");
+        conv_post_dgrad_kernel<bf16><<<gd, 128, 0, stream>>>(dy, y, wpost, static_cast<const bf16*>(P(w.a[S])), 0.01f, 1.f / NB,
+                                                              PF(w.Gi_r[slot]), static_cast<bf16*>(P(w.Gi_t[slot])), C, L);
+      }
+      LAUNCH_CHECK("conv_post_dgrad_kernel");
+    }
+    if (seg < S) {
+      const int i = S - 1 - seg;
+      const StageDesc& sd = p->stages[i];
+      const StageWs& sw = w.st[i];
+      const int L = Ls[i + 1];
+      const float* Gi_r = PF(w.Gi_r[i & 1]);
+      const void* Gi_t = P(w.Gi_t[i & 1]);
+      for (int j = 0; j < NB; ++j) {
+        const float* Gr_cur = Gi_r;
+        const void* Gt_cur = Gi_t;
+        int pp = 0;
+        for (int q = npairs - 1; q >= 0; --q) {
+          const void* in_first = q == 0 ? P(sw.ua) : P(sw.xa[j][q - 1]);  // input of the pair's first conv
+          const void* d_first = Gt_cur;                                   // gradient w.r.t. that conv's output
+          if (p->cfg.resblock == 1) {
+            const Layer& L2 = p->layers[sd.convs[j][q][1]];
+            TRY(run_wgrad(c, L2, P(sw.ma[j][q]), Gt_cur, L, L, L));
+            Epilogue e = epi();
+            e.mask = P(sw.ma[j][q]);
+            e.mask_slope = 0.1f;
+            e.out_t = P(w.dm);
+            TRY(run_conv(c, L2, true, Gt_cur, L, L, L, e));
+            d_first = P(w.dm);
+          }
+          const Layer& L1 = p->layers[sd.convs[j][q][0]];
+          TRY(run_wgrad(c, L1, in_first, d_first, L, L, L));
+          Epilogue e = epi();
+          e.mask = in_first;
+          e.mask_slope = 0.1f;
+          e.res = Gr_cur;
+          if (q > 0) {
+            e.out_raw = PF(w.Gr[pp]);
+            e.out_t = P(w.Gt[pp]);
+            Gr_cur = PF(w.Gr[pp]);
+            Gt_cur = P(w.Gt[pp]);
+            pp ^= 1;
+          } else {
+            e.res2 = j > 0 ? PF(w.bsum[(j - 1) & 1]) : nullptr;
+            if (j < NB - 1) e.out_raw = PF(w.bsum[j & 1]);
+            else e.out_t = P(w.du);
+          }
+          TRY(run_conv(c, L1, true, d_first, L, L, L, e));
+        }
+      }
+      // upsample conv: weight/bias gradients and data gradient (fused with lrelu mask and the 1/NB of the
+      // previous stage's branch mean)
+      const Layer& U = p->layers[sd.up_layer];
+      const int Lprev = Ls[i];
+      TRY(run_wgrad(c, U, P(w.a[i]), P(w.du), Lprev, Lprev + U.fwd.taps - 1, L));
+      Epilogue e = epi();
+      e.mask = P(w.a[i]);
+      e.mask_slope = 0.1f;
+      if (i > 0) {
+        e.scale = 1.f / NB;
+        e.out_raw = PF(w.Gi_r[(i - 1) & 1]);
+        e.out_t = P(w.Gi_t[(i - 1) & 1]);
+      } else {
+        e.out_t = P(w.d0);
+      }
+      TRY(run_conv(c, U, true, P(w.du), L, Lprev, Lprev, e));
+    } else {  // conv_pre + cond
+      const Layer& L = p->layers[p->l_pre];
+      TRY(run_wgrad(c, L, P(w.xin), P(w.d0), T, T, T));
+      CU_TRY(cudaMemsetAsync(PF(w.dcb), 0, sizeof(float) * B * C0, stream));
+      {
+        const int splits = std::max(1, std::min(64, T / 2048));
+        dim3 grid(C0 / 8, B, splits);
+        if (f32) colsum_kernel<float><<<grid, 256, 0, stream>>>(static_cast<const float*>(P(w.d0)), PF(w.dcb), C0, T, 1);
+        else colsum_kernel<bf16><<<grid, 256, 0, stream>>>(static_cast<const bf16*>(P(w.d0)), PF(w.dcb), C0, T, 1);
+        LAUNCH_CHECK("colsum_kernel");
+      }
+      {
+        const int G = p->cfg.gin_channels;
+        const bool have_g = gvec != nullptr && G > 0;
+        long long n = C0;
+        if (have_g) n = std::max<long long>(n, std::max<long long>(1LL * C0 * G, 1LL * B * G));
+        cond_bwd_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(
+            PF(w.dcb), have_g ? p->h_params[p->p_cond_w] : nullptr, gvec, p->h_dparams[L.p_b],
+            have_g ? p->h_dparams[p->p_cond_b] : nullptr, have_g ? p->h_dparams[p->p_cond_w] : nullptr,
+            have_g ? dg : nullptr, B, C0, std::max(G, 1));
+        LAUNCH_CHECK("cond_bwd_kernel");
+        if (!have_g && G > 0) {
+          CU_TRY(cudaMemsetAsync(p->h_dparams[p->p_cond_w], 0, sizeof(float) * p->params[p->p_cond_w].numel, stream));
+          CU_TRY(cudaMemsetAsync(p->h_dparams[p->p_cond_b], 0, sizeof(float) * p->params[p->p_cond_b].numel, stream));
+          if (dg) CU_TRY(cudaMemsetAsync(dg, 0, sizeof(float) * B * G, stream));
+        }
+      }
+      if (dx) {
+        Epilogue e = epi();
+        e.out_raw = PF(w.dxb);
+        TRY(run_conv(c, L, true, P(w.d0), T, T, T, e));
+        dim3 grid((T + 127) / 128, Cin0 / 8, B);
+        blocked_to_ncl_kernel<<<grid, 128, 0, stream>>>(PF(w.dxb), dx, Cin0, T);
+        LAUNCH_CHECK("blocked_to_ncl_kernel");
+      }
+    }
+    TRY(end_segment(seg));
+  }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host-buffer entry point (infer.py path)
+// ---------------------------------------------------------------------------------------------------
+extern "C" size_t vcd_host_call_extra_bytes(const vcd_plan* p, int B, int T) {
+  if (!p || B < 1 || T < 1) return 0;
+  size_t n = align_up(sizeof(float) * B * p->cfg.initial_channel * T, 256);
+  n += align_up(sizeof(float) * B * std::max(p->cfg.gin_channels, 1), 256);
+  n += align_up(sizeof(float) * static_cast<size_t>(B) * T * p->hop, 256);
+  return n;
+}
+
+extern "C" int vcd_synthesize_host(vcd_plan* p, int mode, const float* x_host, const float* g_host, float* y_host,
+                                   void* ws, size_t ws_bytes, int B, int T, void* stream_) {
+  if (!p || !x_host || !y_host) return fail("vcd_synthesize_host: null argument");
+  if (B < 1 || T < 1) return fail("B and T must be >= 1");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const size_t core = align_up(vcd_workspace_bytes(p, mode, B, T, 0), 256);
+  const size_t extra = vcd_host_call_extra_bytes(p, B, T);
+  if (!ws || ws_bytes < core + extra) return fail("workspace too small: need %zu bytes, got %zu", core + extra, ws_bytes);
+  char* base = static_cast<char*>(ws) + core;
+  const int Cin = p->cfg.initial_channel, G = p->cfg.gin_channels;
+  float* xd = reinterpret_cast<float*>(base);
+  float* gd = reinterpret_cast<float*>(base + align_up(sizeof(float) * B * Cin * T, 256));
+  float* yd = reinterpret_cast<float*>(reinterpret_cast<char*>(gd) + align_up(sizeof(float) * B * std::max(G, 1), 256));
+  CU_TRY(cudaMemcpyAsync(xd, x_host, sizeof(float) * B * Cin * T, cudaMemcpyHostToDevice, stream));
+  if (g_host) {
+    if (!G) return fail("g_host given but the plan has gin_channels = 0");
+    CU_TRY(cudaMemcpyAsync(gd, g_host, sizeof(float) * B * G, cudaMemcpyHostToDevice, stream));
+  }
+  TRY(vcd_forward(p, mode, xd, static_cast<int64_t>(Cin) * T, T, 1, g_host ? gd : nullptr, yd, ws, core, B, T, 0, stream_));
+  CU_TRY(cudaMemcpyAsync(y_host, yd, sizeof(float) * static_cast<size_t>(B) * T * p->hop, cudaMemcpyDeviceToHost, stream));
+  CU_TRY(cudaStreamSynchronize(stream));
+  return 0;
+}
+
+extern "C" const char* vcd_layer_path(const vcd_plan* p, int mode, int index) {
+  if (!p || index < 0 || index >= static_cast<int>(p->layers.size())) return nullptr;
+  static thread_local char buf[256];
+  const Layer& L = p->layers[index];
+  const bool bf = mode == VCD_MODE_BF16;
+  snprintf(buf, sizeof(buf), "%s fwd=%s dgrad=%s wgrad=%s", L.name.c_str(),
+           bf && L.tc_ok_fwd ? "tcgen05-bf16" : (bf ? "ffma-bf16io" : "ffma-fp32"),
+           bf && L.tc_ok_dgr ? "tcgen05-bf16" : (bf ? "ffma-bf16io" : "ffma-fp32"),
+           bf && L.tc_ok_wgr ? "tcgen05-bf16" : (bf ? "ffma-bf16io" : "ffma-fp32"));
+  return buf;
+}

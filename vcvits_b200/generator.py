@@ -1,0 +1,428 @@
+"""Drop-in replacement for the reference's ``Generator`` (the HiFi-GAN decoder behind ``net_g.dec``).
+
+Mirrors the reference interface for this path:
+  * constructor arguments  -- vits/model/synthesizers/synthesizer_tts.py:71-78
+  * ``forward(x, g=None)``  -- call sites synthesizer_tts.py:140,166,176 and synthesizer_svc.py:87,108,118
+  * parameter names/shapes -- old-style ``weight_norm`` layout (``weight_g``/``weight_v``/``bias``) used by
+    vits/model/modules.py:10,190-199,229-230, i.e. checkpoints saved under ``net_g.dec.*`` load unchanged
+  * ``remove_weight_norm()`` -- convention of modules.py:218-222
+
+All arithmetic runs in the CUDA library behind the C ABI of ``include/vcd.h`` through ONE
+``torch.autograd.Function``; PyTorch only owns memory, streams and (optionally) the process group.  There is
+no CPU or eager fallback: calling the module on a CPU tensor raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import warnings
+from typing import List, Optional, Sequence
+
+import torch
+from torch import nn
+
+from . import _lib
+
+__all__ = ["Generator", "LRELU_SLOPE"]
+
+LRELU_SLOPE = 0.1  # vits/model/modules.py:16
+
+
+class _ConvParams(nn.Module):
+    """Parameter holder for a plain Conv1d (``weight``[, ``bias``])."""
+
+    def __init__(self, weight: torch.Tensor, bias: Optional[torch.Tensor]):
+        super().__init__()
+        self.weight = nn.Parameter(weight)
+        if bias is not None:
+            self.bias = nn.Parameter(bias)
+        else:
+            self.register_parameter("bias", None)
+
+
+class _WeightNormParams(nn.Module):
+    """Parameter holder with the old-style weight_norm layout: ``bias``, ``weight_g``, ``weight_v``."""
+
+    def __init__(self, weight: torch.Tensor, bias: torch.Tensor):
+        super().__init__()
+        self.bias = nn.Parameter(bias)
+        norm = weight.reshape(weight.shape[0], -1).norm(dim=1).reshape(-1, *([1] * (weight.dim() - 1)))
+        self.weight_g = nn.Parameter(norm)
+        self.weight_v = nn.Parameter(weight)
+
+
+class _ResBlock1Params(nn.Module):
+    def __init__(self, convs1: Sequence[nn.Module], convs2: Sequence[nn.Module]):
+        super().__init__()
+        self.convs1 = nn.ModuleList(convs1)
+        self.convs2 = nn.ModuleList(convs2)
+
+
+class _ResBlock2Params(nn.Module):
+    def __init__(self, convs: Sequence[nn.Module]):
+        super().__init__()
+        self.convs = nn.ModuleList(convs)
+
+
+def _default_conv_init(cout: int, cin: int, k: int, transposed: bool = False):
+    """PyTorch's default Conv1d / ConvTranspose1d init (kaiming_uniform(a=sqrt(5)) + uniform bias), drawn in the
+    same RNG order as constructing the torch module, so a seeded construction matches the reference's."""
+    shape = (cin, cout, k) if transposed else (cout, cin, k)
+    w = torch.empty(shape)
+    nn.init.kaiming_uniform_(w, a=math.sqrt(5))
+    fan_in = shape[1] * k
+    bound = 1.0 / math.sqrt(fan_in) if fan_in > 0 else 0.0
+    b = torch.empty(cout).uniform_(-bound, bound)
+    return w, b
+
+
+def _consume_init_weights_rng(mods: Sequence[_WeightNormParams]) -> None:
+    # vits/commons.py:8-11 init_weights is a no-op on the effective weights of weight-normed convs
+    #  but advances the RNG; mirror that so seeded constructions agree with the reference.
+    for m in mods:
+        torch.empty_like(m.weight_v).normal_(0.0, 0.01)
+
+
+class _DecoderFunction(torch.autograd.Function):
+    """forward = vcd_forward, backward = vcd_backward (+ optional overlapped gradient all-reduce)."""
+
+    @staticmethod
+    def forward(ctx, module: "Generator", need_grad: bool, x: torch.Tensor, g: Optional[torch.Tensor],
+                *params: torch.Tensor):
+        lib = _lib.load()
+        B, _, T = x.shape
+        plan = module._plan_for(x.device)
+        mode = module._mode
+        module._fold_if_needed(params)
+        stream = torch.cuda.current_stream(x.device).cuda_stream
+        xf = x if x.dtype == torch.float32 else x.float()
+        gf = None
+        if g is not None:
+            gf = g.reshape(B, -1).float().contiguous()
+        ws_bytes = lib.vcd_workspace_bytes(plan, mode, B, T, 1 if need_grad else 0)
+        ws = module._workspace(ws_bytes, x.device, cache=not need_grad)
+        y = torch.empty((B, 1, T * module.hop), dtype=torch.float32, device=x.device)
+        _lib.check(lib.vcd_forward(plan, mode, xf.data_ptr(), xf.stride(0), xf.stride(1), xf.stride(2),
+                                   gf.data_ptr() if gf is not None else None, y.data_ptr(), ws.data_ptr(),
+                                   ws_bytes, B, T, 1 if need_grad else 0, stream), "vcd_forward")
+        if need_grad:
+            ctx.module = module
+            ctx.ws = ws
+            ctx.ws_bytes = ws_bytes
+            ctx.shape = (B, T)
+            ctx.has_g = g is not None
+            ctx.g_shape = g.shape if g is not None else None
+            ctx.x_dtype, ctx.g_dtype = x.dtype, (g.dtype if g is not None else None)
+            ctx.save_for_backward(y, gf if gf is not None else y)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy: torch.Tensor):
+        lib = _lib.load()
+        module: Generator = ctx.module
+        y, gf = ctx.saved_tensors
+        if not ctx.has_g:
+            gf = None
+        B, T = ctx.shape
+        dev = y.device
+        plan = module._plan_for(dev)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        dy = dy.contiguous().float()
+        need_dx, need_dg = ctx.needs_input_grad[2], ctx.has_g and ctx.needs_input_grad[3]
+        dx = torch.empty((B, module.initial_channel, T), dtype=torch.float32, device=dev) if need_dx else None
+        dg = torch.empty((B, module.gin_channels), dtype=torch.float32, device=dev) if need_dg else None
+        flat = torch.empty(module._flat_numel, dtype=torch.float32, device=dev)
+        views = module._grad_views(flat)
+        ptrs = (C.c_void_p * len(views))(*[v.data_ptr() for v in views])
+        group = module._grad_sync_group
+        works = []
+        for seg in range(module._num_segments):
+            _lib.check(lib.vcd_backward(plan, module._mode, dy.data_ptr(), y.data_ptr(),
+                                        gf.data_ptr() if gf is not None else None,
+                                        dx.data_ptr() if dx is not None else None,
+                                        dg.data_ptr() if dg is not None else None,
+                                        ptrs, ctx.ws.data_ptr(), ctx.ws_bytes, B, T, 1 << seg, stream),
+                       "vcd_backward")
+            if group is not None:
+                # gradients of this segment are final: all-reduce them on NCCL's stream while the next
+                # segment's kernels run (replaces the DDP reducer implied by train.py:99-100)
+                lo, hi = module._segment_ranges[seg]
+                works.append(torch.distributed.all_reduce(flat[lo:hi], op=torch.distributed.ReduceOp.AVG,
+                                                          group=group, async_op=True))
+        for wk in works:
+            wk.wait()
+        ctx.ws = None
+        grads = [v if p.requires_grad else None for v, p in zip(views, module._ordered_params())]
+        gx = dx.to(ctx.x_dtype) if dx is not None else None
+        gg = dg.reshape(ctx.g_shape).to(ctx.g_dtype) if dg is not None else None
+        return (None, None, gx, gg, *grads)
+
+
+class Generator(nn.Module):
+    """B200-native HiFi-GAN decoder with the reference ``Generator`` constructor (synthesizer_tts.py:71-78).
+
+    Extra keyword ``mode``: ``"bf16"`` (default; tcgen05 tensor-core kernels, fp32 accumulation) or ``"fp32"``
+    (FFMA parity mode)."""
+
+    def __init__(self, initial_channel, resblock, resblock_kernel_sizes, resblock_dilation_sizes,
+                 upsample_rates, upsample_initial_channel, upsample_kernel_sizes, gin_channels=0, mode="bf16"):
+        super().__init__()
+        self.initial_channel = int(initial_channel)
+        self.resblock = "1" if str(resblock) == "1" else "2"
+        self.resblock_kernel_sizes = [int(k) for k in resblock_kernel_sizes]
+        self.resblock_dilation_sizes = [[int(d) for d in ds] for ds in resblock_dilation_sizes]
+        self.upsample_rates = [int(u) for u in upsample_rates]
+        self.upsample_initial_channel = int(upsample_initial_channel)
+        self.upsample_kernel_sizes = [int(k) for k in upsample_kernel_sizes]
+        self.gin_channels = int(gin_channels)
+        self.num_kernels = len(self.resblock_kernel_sizes)
+        self.num_upsamples = len(self.upsample_rates)
+        self.hop = 1
+        for u in self.upsample_rates:
+            self.hop *= u
+        self.set_mode(mode)
+        npairs = 3 if self.resblock == "1" else 2
+        for ds in self.resblock_dilation_sizes:
+            if len(ds) < npairs:
+                raise ValueError(f"ResBlock{self.resblock} needs {npairs} dilations per kernel size "
+                                 f"(vits/model/modules.py:190-199,229-230), got {ds}")
+
+        c0 = self.upsample_initial_channel
+        # construction order mirrors upstream (conv_pre, ups, resblocks, conv_post, init_weights draws, cond)
+        self.conv_pre = _ConvParams(*_default_conv_init(c0, self.initial_channel, 7))
+        ups = []
+        ch = c0
+        for u, k in zip(self.upsample_rates, self.upsample_kernel_sizes):
+            ups.append(_WeightNormParams(*_default_conv_init(ch // 2, ch, k, transposed=True)))
+            ch //= 2
+        self.ups = nn.ModuleList(ups)
+        blocks = []
+        ch = c0
+        for _ in self.upsample_rates:
+            ch //= 2
+            for k in self.resblock_kernel_sizes:
+                if self.resblock == "1":
+                    c1 = [_WeightNormParams(*_default_conv_init(ch, ch, k)) for _ in range(3)]
+                    _consume_init_weights_rng(c1)
+                    c2 = [_WeightNormParams(*_default_conv_init(ch, ch, k)) for _ in range(3)]
+                    _consume_init_weights_rng(c2)
+                    blocks.append(_ResBlock1Params(c1, c2))
+                else:
+                    cs = [_WeightNormParams(*_default_conv_init(ch, ch, k)) for _ in range(2)]
+                    _consume_init_weights_rng(cs)
+                    blocks.append(_ResBlock2Params(cs))
+        self.resblocks = nn.ModuleList(blocks)
+        w_post = torch.empty(1, ch, 7)
+        nn.init.kaiming_uniform_(w_post, a=math.sqrt(5))
+        self.conv_post = _ConvParams(w_post, None)
+        _consume_init_weights_rng(self.ups)
+        if self.gin_channels != 0:
+            self.cond = _ConvParams(*_default_conv_init(c0, self.gin_channels, 1))
+
+        self._plans = {}
+        self._fold_key = None
+        self._ws_cache = {}
+        self._grad_sync_group = None
+        self._names: Optional[List[str]] = None
+
+    # ------------------------------------------------------------------ configuration helpers
+    def set_mode(self, mode) -> "Generator":
+        if mode in ("bf16", torch.bfloat16, _lib.MODE_BF16):
+            self._mode = _lib.MODE_BF16
+        elif mode in ("fp32", torch.float32, _lib.MODE_FP32):
+            self._mode = _lib.MODE_FP32
+        else:
+            raise ValueError(f"mode must be 'bf16' or 'fp32', got {mode!r}")
+        self._fold_key = None
+        return self
+
+    @property
+    def mode(self) -> str:
+        return "bf16" if self._mode == _lib.MODE_BF16 else "fp32"
+
+    def set_gradient_sync(self, group) -> "Generator":
+        """Average parameter gradients over ``group`` (a torch.distributed process group, or
+        ``torch.distributed.group.WORLD``) inside backward, segment by segment, overlapped with the remaining
+        backward kernels.  ``None`` disables it (e.g. when wrapped in DistributedDataParallel instead)."""
+        self._grad_sync_group = group
+        return self
+
+    def remove_weight_norm(self) -> "Generator":
+        """Reference convention (modules.py:218-222).  The fold ``w = g*v/||v||`` already happens once per
+        parameter version inside ``vcd_fold_weights``, so inference pays it once; parameters keep the
+        weight_g/weight_v layout so checkpoints stay loadable."""
+        self._fold_key = None
+        return self
+
+    def config_struct(self) -> _lib.VcdConfig:
+        cfg = _lib.VcdConfig()
+        cfg.initial_channel = self.initial_channel
+        cfg.resblock = 1 if self.resblock == "1" else 2
+        cfg.num_kernels = self.num_kernels
+        if self.num_kernels > _lib.MAX_KERNELS or self.num_upsamples > _lib.MAX_UPSAMPLES:
+            raise ValueError("too many resblock kernels / upsample stages for the C ABI")
+        for i, k in enumerate(self.resblock_kernel_sizes):
+            cfg.resblock_kernel_sizes[i] = k
+            for j, d in enumerate(self.resblock_dilation_sizes[i][:_lib.MAX_DILATIONS]):
+                cfg.resblock_dilation_sizes[i][j] = d
+        cfg.num_upsamples = self.num_upsamples
+        for i, (u, k) in enumerate(zip(self.upsample_rates, self.upsample_kernel_sizes)):
+            cfg.upsample_rates[i] = u
+            cfg.upsample_kernel_sizes[i] = k
+        cfg.upsample_initial_channel = self.upsample_initial_channel
+        cfg.gin_channels = self.gin_channels
+        return cfg
+
+    # ------------------------------------------------------------------ plan / parameters
+    def _plan_for(self, device: torch.device):
+        key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
+        plan = self._plans.get(key)
+        if plan is None:
+            lib = _lib.load()
+            handle = C.c_void_p()
+            cfg = self.config_struct()
+            with torch.cuda.device(device):
+                _lib.check(lib.vcd_plan_create(C.byref(cfg), C.byref(handle)), "vcd_plan_create")
+            plan = handle
+            self._plans[key] = plan
+            n = lib.vcd_num_params(plan)
+            names, numels = [], []
+            for i in range(n):
+                name = C.c_char_p()
+                shape = (C.c_int64 * 3)()
+                ndim = C.c_int()
+                _lib.check(lib.vcd_param_info(plan, i, C.byref(name), shape, C.byref(ndim)), "vcd_param_info")
+                names.append(name.value.decode())
+                numels.append(tuple(shape[: ndim.value]))
+            own = dict(self.named_parameters())
+            if set(names) != set(own):
+                raise RuntimeError(f"parameter table mismatch between module and library: "
+                                   f"{sorted(set(names) ^ set(own))[:8]}")
+            for nme, shp in zip(names, numels):
+                if tuple(own[nme].shape) != shp:
+                    raise RuntimeError(f"shape mismatch for {nme}: module {tuple(own[nme].shape)} vs library {shp}")
+            self._names = names
+            # flat gradient buffer layout: parameters grouped by backward segment, in completion order
+            nseg = lib.vcd_num_backward_segments(plan)
+            self._num_segments = nseg
+            order, ranges, off = {}, [], 0
+            for seg in range(nseg):
+                buf = (C.c_int * n)()
+                cnt = lib.vcd_segment_params(plan, seg, buf, n)
+                lo = off
+                for j in range(cnt):
+                    idx = buf[j]
+                    order[idx] = off
+                    off += own[names[idx]].numel()
+                ranges.append((lo, off))
+            if len(order) != n:
+                raise RuntimeError("backward segments do not cover every parameter")
+            self._flat_offsets = [order[i] for i in range(n)]
+            self._flat_numel = off
+            self._segment_ranges = ranges
+        return plan
+
+    def _ordered_params(self) -> List[torch.Tensor]:
+        own = dict(self.named_parameters())
+        return [own[n] for n in self._names]
+
+    def _grad_views(self, flat: torch.Tensor) -> List[torch.Tensor]:
+        out = []
+        for p, off in zip(self._ordered_params(), self._flat_offsets):
+            out.append(flat[off: off + p.numel()].view(p.shape))
+        return out
+
+    def _fold_if_needed(self, params: Sequence[torch.Tensor]) -> None:
+        key = (self._mode, tuple((p.data_ptr(), p._version) for p in params))
+        if key == self._fold_key:
+            return
+        lib = _lib.load()
+        dev = params[0].device
+        for p in params:
+            if p.dtype != torch.float32 or not p.is_contiguous():
+                raise RuntimeError("decoder parameters must be contiguous fp32 tensors")
+        ptrs = (C.c_void_p * len(params))(*[p.data_ptr() for p in params])
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        _lib.check(lib.vcd_fold_weights(self._plan_for(dev), self._mode, ptrs, stream), "vcd_fold_weights")
+        self._fold_key = key
+
+    def _workspace(self, nbytes: int, device: torch.device, cache: bool) -> torch.Tensor:
+        if not cache:
+            return torch.empty(nbytes, dtype=torch.uint8, device=device)
+        ws = self._ws_cache.get(device)
+        if ws is None or ws.numel() < nbytes:
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
+            self._ws_cache = {device: ws}
+        return ws
+
+    def _apply(self, fn, *args, **kwargs):
+        out = super()._apply(fn, *args, **kwargs)
+        self._fold_key = None
+        self._ws_cache = {}
+        return out
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, x: torch.Tensor, g: Optional[torch.Tensor] = None) -> torch.Tensor:
+        if not x.is_cuda:
+            raise RuntimeError("vcvits_b200.Generator runs only on CUDA (sm_100a); there is no CPU fallback")
+        if x.dim() != 3 or x.shape[1] != self.initial_channel:
+            raise ValueError(f"expected x of shape [B, {self.initial_channel}, T], got {tuple(x.shape)}")
+        if g is not None:
+            if self.gin_channels == 0:
+                raise ValueError("g given but the decoder was built with gin_channels=0")
+            if g.shape[0] != x.shape[0] or g.numel() != x.shape[0] * self.gin_channels:
+                raise ValueError(f"expected g of shape [B, {self.gin_channels}, 1], got {tuple(g.shape)}")
+        self._plan_for(x.device)
+        params = self._ordered_params()
+        need_grad = torch.is_grad_enabled() and (x.requires_grad or (g is not None and g.requires_grad)
+                                                 or any(p.requires_grad for p in params))
+        with torch.autocast(device_type="cuda", enabled=False):
+            return _DecoderFunction.apply(self, need_grad, x, g, *params)
+
+    def synthesize_host(self, x_host: torch.Tensor, g_host: Optional[torch.Tensor] = None,
+                        device: Optional[torch.device] = None) -> torch.Tensor:
+        """infer.py-style call on HOST tensors through ``vcd_synthesize_host``: H2D copy, decode, D2H copy."""
+        lib = _lib.load()
+        device = device or next(self.parameters()).device
+        plan = self._plan_for(device)
+        self._fold_if_needed(self._ordered_params())
+        B, _, T = x_host.shape
+        xh = x_host.contiguous().float()
+        gh = g_host.reshape(B, -1).contiguous().float() if g_host is not None else None
+        y = torch.empty((B, 1, T * self.hop), dtype=torch.float32, pin_memory=True)
+        nbytes = lib.vcd_workspace_bytes(plan, self._mode, B, T, 0)
+        nbytes = (nbytes + 255) // 256 * 256 + lib.vcd_host_call_extra_bytes(plan, B, T)
+        ws = self._workspace(nbytes, device, cache=True)
+        stream = torch.cuda.current_stream(device).cuda_stream
+        with torch.cuda.device(device):
+            _lib.check(lib.vcd_synthesize_host(plan, self._mode, xh.data_ptr(),
+                                               gh.data_ptr() if gh is not None else None, y.data_ptr(),
+                                               ws.data_ptr(), ws.numel(), B, T, stream), "vcd_synthesize_host")
+        return y
+
+    def layer_paths(self) -> List[str]:
+        lib = _lib.load()
+        plan = self._plan_for(next(self.parameters()).device)
+        out, i = [], 0
+        while True:
+            s = lib.vcd_layer_path(plan, self._mode, i)
+            if s is None:
+                return out
+            out.append(s.decode())
+            i += 1
+
+    def __getstate__(self):
+        state = dict(self.__dict__)
+        state["_plans"] = {}        # library handles are per process / per device; rebuilt lazily
+        state["_ws_cache"] = {}
+        state["_fold_key"] = None
+        state["_grad_sync_group"] = None
+        return state
+
+    def __del__(self):
+        try:
+            lib = _lib.load()
+            for plan in self._plans.values():
+                lib.vcd_plan_destroy(plan)
+        except Exception:
+            pass
