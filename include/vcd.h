@@ -126,6 +126,15 @@ int vcd_synthesize_host(vcd_plan* plan, int mode, const float* x_host, const flo
 /* Counters for bench.py: kernels launched by this library since the last reset. */
 uint64_t vcd_launch_count(int reset);
 
+/* Optional per-launch profiler for bench.py's roofline object: when enabled every kernel launch is bracketed
+ * by CUDA events on the launch stream and accumulated per kernel class (adds overhead: never enabled while the
+ * throughput value is timed).  vcd_profile_read synchronises the device and fills arrays of
+ * vcd_profile_num_classes() entries: device milliseconds, launches, algorithmic FLOPs, algorithmic bytes. */
+int vcd_profile_enable(int on);
+int vcd_profile_num_classes(void);
+const char* vcd_profile_class_name(int class_id);
+int vcd_profile_read(int reset, double* ms, uint64_t* launches, double* flops, double* bytes);
+
 /* Per-layer timing / debugging: name of the arithmetic path ("simt-fp32", "tcgen05-bf16", ...) used by
  * layer `index` of the forward schedule in `mode`; NULL past the end. */
 const char* vcd_layer_path(const vcd_plan* plan, int mode, int index);

@@ -156,6 +156,11 @@ TINY_CFG = dict(initial_channel=16, resblock="1", resblock_kernel_sizes=[3, 5],
                 resblock_dilation_sizes=[[1, 3, 5], [1, 2, 3]], upsample_rates=[4, 2],
                 upsample_initial_channel=32, upsample_kernel_sizes=[8, 4], gin_channels=8)
 TINY2_CFG = dict(TINY_CFG, resblock="2")
+# smallest config whose every stage is wide enough for the tcgen05 tiles (64- and 32-channel stages)
+SMALL_CFG = dict(initial_channel=64, resblock="1", resblock_kernel_sizes=[3, 7, 11],
+                 resblock_dilation_sizes=[[1, 3, 5], [1, 3, 5], [1, 3, 5]], upsample_rates=[4, 4],
+                 upsample_initial_channel=128, upsample_kernel_sizes=[8, 8], gin_channels=16)
+SMALL2_CFG = dict(SMALL_CFG, resblock="2")
 
 
 def seeded_state_dict(cfg: dict, seed: int = 1234, gain: float = 1.0) -> "dict[str, torch.Tensor]":

@@ -94,8 +94,15 @@ def test_base_config_fp32_gradients():
     total_num = sum(float((grads[n].double() - gref[n]).pow(2).sum()) for n in gref)
     total_den = sum(float(gref[n].pow(2).sum()) for n in gref)
     assert (total_num / total_den) ** 0.5 <= GRAD_REL
-    worst = max((rel_l2(grads[n], gref[n]), n) for n in gref)
-    assert worst[0] <= 2e-3, worst  # PyTorch fp32 itself reaches 1.8e-3 on some tensors
+    # per tensor: <= max(1e-3, 2x PyTorch-fp32's own error for that tensor) -- SURVEY.md F8 / §8c: PyTorch fp32
+    # itself reaches ~2e-3 on a few weight_v tensors whose gradient is dominated by the cancelling radial part
+    _, g32 = oracle_run(O.BASE_CFG, sd, x, g, dy, dtype=torch.float32)
+    report = []
+    for n in gref:
+        mine, torch32 = rel_l2(grads[n], gref[n]), rel_l2(g32[n], gref[n])
+        report.append((mine / max(1e-3, 2.0 * torch32), mine, torch32, n))
+    worst = max(report)
+    assert worst[0] <= 1.0, worst
 
 
 @pytest.mark.parametrize("cfg", [O.TINY_CFG, O.TINY2_CFG])

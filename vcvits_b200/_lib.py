@@ -99,6 +99,11 @@ _SIGNATURES = {
     "vcd_synthesize_host": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                       C.c_size_t, C.c_int, C.c_int, C.c_void_p]),
     "vcd_launch_count": (C.c_uint64, [C.c_int]),
+    "vcd_profile_enable": (C.c_int, [C.c_int]),
+    "vcd_profile_num_classes": (C.c_int, []),
+    "vcd_profile_class_name": (C.c_char_p, [C.c_int]),
+    "vcd_profile_read": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.POINTER(C.c_double),
+                                   C.POINTER(C.c_double)]),
     "vcd_layer_path": (C.c_char_p, [C.c_void_p, C.c_int, C.c_int]),
 }
 

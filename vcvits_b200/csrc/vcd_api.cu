@@ -53,6 +53,53 @@ static int fail(const char* fmt, ...) {
     if (rc__) return rc__;   \
   } while (0)
 
+// ---------------------------------------------------------------------------------------------------
+// optional per-launch profiler (CUDA events around every kernel, grouped by kernel class)
+// ---------------------------------------------------------------------------------------------------
+namespace {
+enum : int { PC_TC_CONV = 0, PC_TC_WGRAD, PC_FFMA_CONV, PC_FFMA_WGRAD, PC_POST, PC_FOLD, PC_MISC, PC_COUNT };
+const char* kProfNames[PC_COUNT] = {"tc_conv(fwd+dgrad)", "tc_wgrad", "ffma_conv", "ffma_wgrad", "conv_post", "weight_norm_fold", "misc"};
+struct ProfRec { int cls; cudaEvent_t a, b; double flops, bytes; };
+bool g_prof_on = false;
+std::vector<ProfRec> g_prof;
+std::vector<cudaEvent_t> g_prof_pool;
+cudaEvent_t prof_event() {
+  cudaEvent_t e;
+  if (!g_prof_pool.empty()) { e = g_prof_pool.back(); g_prof_pool.pop_back(); return e; }
+  cudaEventCreate(&e);
+  return e;
+}
+struct ProfScope {
+  cudaStream_t s; bool on;
+  ProfScope(int cls, double flops, double bytes, cudaStream_t stream) : s(stream), on(g_prof_on) {
+    if (!on) return;
+    ProfRec r{cls, prof_event(), prof_event(), flops, bytes};
+    cudaEventRecord(r.a, s);
+    g_prof.push_back(r);
+  }
+  ~ProfScope() { if (on) cudaEventRecord(g_prof.back().b, s); }
+};
+}  // namespace
+
+extern "C" int vcd_profile_enable(int on) { g_prof_on = on != 0; return 0; }
+extern "C" int vcd_profile_num_classes(void) { return PC_COUNT; }
+extern "C" const char* vcd_profile_class_name(int c) { return c >= 0 && c < PC_COUNT ? kProfNames[c] : nullptr; }
+// Sums over the records since the last reset: device ms, launches, algorithmic flops and bytes per class.
+extern "C" int vcd_profile_read(int reset, double* ms, uint64_t* launches, double* flops, double* bytes) {
+  cudaDeviceSynchronize();
+  for (int c = 0; c < PC_COUNT; ++c) { ms[c] = 0; launches[c] = 0; flops[c] = 0; bytes[c] = 0; }
+  for (const ProfRec& r : g_prof) {
+    float t = 0.f;
+    cudaEventElapsedTime(&t, r.a, r.b);
+    ms[r.cls] += t; launches[r.cls] += 1; flops[r.cls] += r.flops; bytes[r.cls] += r.bytes;
+  }
+  if (reset) {
+    for (const ProfRec& r : g_prof) { g_prof_pool.push_back(r.a); g_prof_pool.push_back(r.b); }
+    g_prof.clear();
+  }
+  return 0;
+}
+
 extern "C" const char* vcd_version(void) { return "vcd 0.1 (sm_100a; tcgen05/TMA + FFMA paths)"; }
 extern "C" const char* vcd_last_error(void) { return g_err; }
 extern "C" uint64_t vcd_launch_count(int reset) {
@@ -472,6 +519,7 @@ extern "C" int vcd_fold_weights(vcd_plan* p, int mode, const float* const* param
     // pageable->device async copy is staged by the runtime before returning, so h_params may change later
     CU_TRY(cudaMemcpyAsync(p->d_params, p->h_params.data(), np * sizeof(float*), cudaMemcpyHostToDevice, stream));
   }
+  ProfScope ps__(PC_FOLD, 0, 4.0 * p->n_f32, stream);
   if (p->n_norm_blocks) {
     wn_norm_kernel<<<p->n_norm_blocks, 128, 0, stream>>>(p->d_norm_jobs, p->n_norm_jobs, p->d_params, p->d_norms);
     LAUNCH_CHECK("wn_norm_kernel");
@@ -497,7 +545,8 @@ struct Ctx {
 
 template <typename T>
 int launch_gconv_simt(const Ctx& c, const void* in, const float* w, const ConvGeo& g, const Epilogue& e,
-                      int Lin, int Lq, int Lout) {
+                      int Lin, int Lq, int Lout, double flops) {
+  ProfScope ps__(PC_FFMA_CONV, flops, 0, c.stream);
   if (Lq <= 128) {
     dim3 grid((Lq + 127) / 128, g.N / 8, c.B);
     gconv_simt_kernel<T, 1><<<grid, 128, 0, c.stream>>>(static_cast<const T*>(in), w, g, e, Lin, Lq, Lout);
@@ -512,18 +561,25 @@ int launch_gconv_simt(const Ctx& c, const void* in, const float* w, const ConvGe
 // One convolution (forward or data-gradient direction) of layer L.
 int run_conv(const Ctx& c, const Layer& L, bool dgrad, const void* in, int Lin, int Lq, int Lout, Epilogue e) {
   const ConvGeo& g = dgrad ? L.dgr : L.fwd;
-  if (c.mode == VCD_MODE_BF16 && (dgrad ? L.tc_ok_dgr : L.tc_ok_fwd))
+  // algorithmic FLOPs: 2*Cin*Cout*k per forward-input position (ConvT) / output position (Conv)
+  const int lpos = L.kind == LK_CONVT ? (dgrad ? Lout : Lin) : Lout;
+  const double flops = 2.0 * L.cin * L.cout * L.k * static_cast<double>(c.B) * lpos;
+  if (c.mode == VCD_MODE_BF16 && (dgrad ? L.tc_ok_dgr : L.tc_ok_fwd)) {
+    ProfScope ps__(PC_TC_CONV, flops, 0, c.stream);
     return tc_run_conv(c.p, L, dgrad, in, c.B, Lin, Lq, Lout, e, c.stream, g_launches, g_err, sizeof(g_err));
+  }
   const float* w = c.p->d_f32 + (dgrad ? L.f32_dgr : L.f32_fwd);
-  if (c.mode == VCD_MODE_FP32) return launch_gconv_simt<float>(c, in, w, g, e, Lin, Lq, Lout);
-  return launch_gconv_simt<bf16>(c, in, w, g, e, Lin, Lq, Lout);
+  if (c.mode == VCD_MODE_FP32) return launch_gconv_simt<float>(c, in, w, g, e, Lin, Lq, Lout, flops);
+  return launch_gconv_simt<bf16>(c, in, w, g, e, Lin, Lq, Lout, flops);
 }
 
 // Weight gradient (+ bias gradient) of layer L: in = layer input, dout = gradient w.r.t. the layer output.
 int run_wgrad(const Ctx& c, const Layer& L, const void* in, const void* dout, int Lin, int Lq, int Lout) {
   const ConvGeo& g = L.fwd;
   float* dwp = c.p->d_gscratch + L.dwp;
+  const double flops = 2.0 * L.cin * L.cout * L.k * static_cast<double>(c.B) * (L.kind == LK_CONVT ? Lin : Lout);
   if (c.mode == VCD_MODE_BF16 && L.tc_ok_wgr) {
+    ProfScope ps__(PC_TC_WGRAD, flops, 0, c.stream);
     TRY(tc_run_wgrad(c.p, L, in, dout, dwp, c.B, Lin, Lq, Lout, c.stream, g_launches, g_err, sizeof(g_err)));
   } else {
     const long long total = 1LL * c.B * Lq;
@@ -533,6 +589,7 @@ int run_wgrad(const Ctx& c, const Layer& L, const void* in, const void* dout, in
     const int rows_per_split = static_cast<int>((total + splits - 1) / splits);
     splits = (total + rows_per_split - 1) / rows_per_split;
     dim3 grid(blocks_x, static_cast<unsigned>(splits));
+    ProfScope ps__(PC_FFMA_WGRAD, flops, 0, c.stream);
     if (c.mode == VCD_MODE_FP32)
       gconv_wgrad_simt_kernel<float><<<grid, 256, 0, c.stream>>>(static_cast<const float*>(in),
           static_cast<const float*>(dout), dwp, g, c.B, Lin, Lq, Lout, rows_per_split);
@@ -544,6 +601,7 @@ int run_wgrad(const Ctx& c, const Layer& L, const void* in, const void* dout, in
   if (L.dbias >= 0) {
     const int splits = std::max(1, std::min(64, Lout / 2048));
     dim3 grid(L.cout / 8, c.B, splits);
+    ProfScope ps__(PC_MISC, 0, esize(c.mode) * static_cast<double>(c.B) * L.cout * Lout, c.stream);
     if (c.mode == VCD_MODE_FP32)
       colsum_kernel<float><<<grid, 256, 0, c.stream>>>(static_cast<const float*>(dout), c.p->d_gscratch + L.dbias, L.cout, Lout, 0);
     else
@@ -670,6 +728,7 @@ extern "C" int vcd_forward(vcd_plan* p, int mode, const float* x, int64_t xs_b, 
     const int C = p->stages[S - 1].cout;
     dim3 grid((Lcur + 255) / 256, B);
     const size_t smem = sizeof(float) * C * 7;
+    ProfScope ps__(PC_POST, 2.0 * C * 7 * B * Lcur, static_cast<double>(B) * Lcur * (C * esize(mode) + 4), stream);
     if (f32) conv_post_fwd_kernel<float><<<grid, 256, smem, stream>>>(static_cast<const float*>(P(w.a[S])), p->h_params[p->p_post_w], y, C, Lcur);
     else conv_post_fwd_kernel<bf16><<<grid, 256, smem, stream>>>(static_cast<const bf16*>(P(w.a[S])), p->h_params[p->p_post_w], y, C, Lcur);
     LAUNCH_CHECK("conv_post_fwd_kernel");
@@ -719,6 +778,7 @@ extern "C" int vcd_backward(vcd_plan* p, int mode, const float* dy, const float*
   auto end_segment = [&](int seg) -> int {
     const SegmentJobs& sj = p->segments[seg];
     if (sj.nblocks) {
+      ProfScope ps__(PC_FOLD, 0, 8.0 * (sj.scratch_end - sj.scratch_begin), stream);
       wn_unfold_kernel<<<sj.nblocks, 256, 0, stream>>>(sj.d_jobs, sj.njobs, p->d_params, p->d_dparams, p->d_norms, p->d_gscratch);
       LAUNCH_CHECK("wn_unfold_kernel");
     }
@@ -735,6 +795,7 @@ extern "C" int vcd_backward(vcd_plan* p, int mode, const float* dy, const float*
       dim3 gd((L + 127) / 128, C / 8, B);
       const float* wpost = p->h_params[p->p_post_w];
       const int slot = (S - 1) & 1;
+      ProfScope ps__(PC_POST, 4.0 * C * 7 * B * L, static_cast<double>(B) * L * (C * (3 * esize(mode) + 4) + 16), stream);
       if (f32) {
         conv_post_wgrad_kernel<float><<<gw, 256, 0, stream>>>(dy, y, static_cast<const float*>(P(w.a[S])), p->d_gscratch + p->post_dw, C, L);
         LAUNCH_CHECK("conv_post_wgrad_kernel");
