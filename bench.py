@@ -54,6 +54,7 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed steps")
     ap.add_argument("--profile-classes", action="store_true", help="print the per-kernel-class table to stderr")
+    ap.add_argument("--dump-launches", default=None, help="write the per-launch CSV of the profiled steps here")
     return ap.parse_args()
 
 
@@ -306,6 +307,8 @@ def run_b200(args):
             if flush_buf is not None:
                 flush_buf.fill_(1)
             step_device()
+        if args.dump_launches:
+            lib.vcd_profile_dump(args.dump_launches.encode())
         lib.vcd_profile_read(1, arr_ms, arr_l, arr_f, arr_b)
         lib.vcd_profile_enable(0)
         classes = []

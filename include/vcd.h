@@ -134,6 +134,7 @@ int vcd_profile_enable(int on);
 int vcd_profile_num_classes(void);
 const char* vcd_profile_class_name(int class_id);
 int vcd_profile_read(int reset, double* ms, uint64_t* launches, double* flops, double* bytes);
+int vcd_profile_dump(const char* csv_path); /* one line per recorded launch: class, layer tag, ms, GFLOP */
 
 /* Per-layer timing / debugging: name of the arithmetic path ("simt-fp32", "tcgen05-bf16", ...) used by
  * layer `index` of the forward schedule in `mode`; NULL past the end. */

@@ -106,18 +106,71 @@ struct ConvGeo {
   int os, p, creal;      // output row = q*os + n/creal - p ; output channel = n % creal
 };
 
-// Epilogue description shared by all conv kernels:
-//   v = acc + bias[ch] + bias2[b][ch];  v *= (mask>0 ? 1 : mask_slope);  v *= scale;  v += res + res2;
+// Epilogue shared by all conv kernels (T = activation storage type):
+//   v = acc + bias[ch] + bias2[b][ch];  v *= (mask > 0 ? 1 : mask_slope);  v *= scale;
+//   v += inv_lrelu(res_t) + res2;       inv_lrelu(r) = r > 0 ? r : r * res_inv
 //   out_raw = v (fp32);  out_t = T(lrelu(v * tscale, act_slope))
+// Only ACTIVATED tensors are stored between layers: the raw residual stream x of a ResBlock
+// (modules.py:203-216, `x = xt + x`) is recovered from the stored leaky_relu(x) through the exact inverse of
+// the (monotonic) leaky_relu, which removes one tensor write + read per residual add.
 struct Epilogue {
   const float* bias;     // [creal] or null
   const float* bias2;    // [B][creal] or null
   const void* mask;      // T, same layout as the output, or null
-  const float* res;      // fp32, same layout as the output, or null
+  const void* res_t;     // T, same layout as the output, or null
   const float* res2;     // fp32, same layout as the output, or null
   float* out_raw;        // fp32 or null
   void* out_t;           // T or null
-  float mask_slope, scale, tscale, act_slope;
+  float mask_slope, scale, res_inv, tscale, act_slope;
+  // Optional phase-packed ("Z") store of out_t, the operand layout of the ConvTranspose1d backward GEMMs:
+  // element (row, ch) goes to Z[b][(r*creal + ch)][q] with q = (row + zp) / zu, r = (row + zp) % zu.
+  int zu, zp, zLq;
 };
+
+template <typename T>
+__device__ __forceinline__ void apply_epilogue(const Epilogue& e, const ConvGeo& g, int b, int ro, int ch0,
+                                               int Lout, float (&v)[8]) {
+  const size_t o = blk_off(b, ch0, ro, g.creal, Lout);
+  if (e.bias) {
+#pragma unroll
+    for (int n = 0; n < 8; ++n) v[n] += __ldg(e.bias + ch0 + n);
+  }
+  if (e.bias2) {
+#pragma unroll
+    for (int n = 0; n < 8; ++n) v[n] += __ldg(e.bias2 + static_cast<size_t>(b) * g.creal + ch0 + n);
+  }
+  if (e.mask) {
+    float m[8];
+    load8<T>(reinterpret_cast<const T*>(e.mask) + o, m);
+#pragma unroll
+    for (int n = 0; n < 8; ++n) v[n] *= (m[n] > 0.f ? 1.f : e.mask_slope);
+  }
+#pragma unroll
+  for (int n = 0; n < 8; ++n) v[n] *= e.scale;
+  if (e.res_t) {
+    float t[8];
+    load8<T>(reinterpret_cast<const T*>(e.res_t) + o, t);
+#pragma unroll
+    for (int n = 0; n < 8; ++n) v[n] += (t[n] > 0.f ? t[n] : t[n] * e.res_inv);
+  }
+  if (e.res2) {
+    float t[8];
+    load8<float>(e.res2 + o, t);
+#pragma unroll
+    for (int n = 0; n < 8; ++n) v[n] += t[n];
+  }
+  if (e.out_raw) store8<float>(e.out_raw + o, v);
+  if (e.out_t) {
+    float a[8];
+#pragma unroll
+    for (int n = 0; n < 8; ++n) a[n] = lrelu(v[n] * e.tscale, e.act_slope);
+    if (e.zu > 0) {
+      const int q = (ro + e.zp) / e.zu, r = (ro + e.zp) - q * e.zu;
+      store8<T>(reinterpret_cast<T*>(e.out_t) + blk_off(b, r * g.creal + ch0, q, e.zu * g.creal, e.zLq), a);
+    } else {
+      store8<T>(reinterpret_cast<T*>(e.out_t) + o, a);
+    }
+  }
+}
 
 }  // namespace vcd

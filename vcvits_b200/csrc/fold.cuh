@@ -40,10 +40,13 @@ struct WeightMap {
         idx = (static_cast<size_t>(c) * cout + co) * k + jj;
         return true;
       }
-      default:  // SRC_CONVT_DGRAD: Wp[j][co][ci] = w[ci][co][j]
+      default: {  // SRC_CONVT_DGRAD: Wp[s][r*cout+co][ci] = w[ci][co][s*u+r]
+        const int r = c / cout, co = c - r * cout, jj = j * u + r;
+        if (jj >= k) return false;
         row = n;
-        idx = (static_cast<size_t>(n) * cout + c) * k + j;
+        idx = (static_cast<size_t>(n) * cout + co) * k + jj;
         return true;
+      }
     }
   }
 };

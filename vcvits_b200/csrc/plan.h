@@ -26,7 +26,7 @@ struct Layer {
   int cin, cout, k, dil, u, pad;
   bool wn;
   int p_w, p_g, p_b;          // parameter indices (p_w: weight or weight_v), -1 if absent
-  ConvGeo fwd, dgr;           // generalised geometries (common.cuh)
+  ConvGeo fwd, dgr, wgr;      // generalised geometries (common.cuh); wgr = weight-gradient view of fwd
   WeightMap map_fwd, map_dgr;
   long long f32_fwd, f32_dgr; // offsets (elements) into the fp32 packed arena
   long long tc_fwd, tc_dgr;   // offsets (elements) into the bf16 packed arena, -1 if no tensor-core path
@@ -83,4 +83,10 @@ struct vcd_plan {
   vcd::PackJob* d_pack_jobs[2] = {nullptr, nullptr};  // per mode
   int n_pack_jobs[2] = {0, 0}, n_pack_blocks[2] = {0, 0};
   std::vector<vcd::SegmentJobs> segments;
+
+  // auxiliary streams / events for intra-step concurrency (ResBlock branches, weight-gradient kernels)
+  static constexpr int kMaxAux = 12, kMaxEvents = 256;
+  cudaStream_t aux[kMaxAux] = {};
+  cudaEvent_t events[kMaxEvents] = {};
+  int next_event = 0;
 };

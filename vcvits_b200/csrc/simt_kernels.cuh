@@ -85,45 +85,10 @@ gconv_simt_kernel(const T* __restrict__ in, const float* __restrict__ w, ConvGeo
     if (q >= Lq) continue;
     const int ro = q * g.os + r - g.p;
     if (ro < 0 || ro >= Lout) continue;
-    const size_t o = blk_off(b, ch0, ro, g.creal, Lout);
     float v[8];
 #pragma unroll
     for (int n = 0; n < 8; ++n) v[n] = acc[i][n];
-    if (e.bias) {
-#pragma unroll
-      for (int n = 0; n < 8; ++n) v[n] += __ldg(e.bias + ch0 + n);
-    }
-    if (e.bias2) {
-#pragma unroll
-      for (int n = 0; n < 8; ++n) v[n] += __ldg(e.bias2 + static_cast<size_t>(b) * g.creal + ch0 + n);
-    }
-    if (e.mask) {
-      float m[8];
-      load8<T>(reinterpret_cast<const T*>(e.mask) + o, m);
-#pragma unroll
-      for (int n = 0; n < 8; ++n) v[n] *= (m[n] > 0.f ? 1.f : e.mask_slope);
-    }
-#pragma unroll
-    for (int n = 0; n < 8; ++n) v[n] *= e.scale;
-    if (e.res) {
-      float t[8];
-      load8<float>(e.res + o, t);
-#pragma unroll
-      for (int n = 0; n < 8; ++n) v[n] += t[n];
-    }
-    if (e.res2) {
-      float t[8];
-      load8<float>(e.res2 + o, t);
-#pragma unroll
-      for (int n = 0; n < 8; ++n) v[n] += t[n];
-    }
-    if (e.out_raw) store8<float>(e.out_raw + o, v);
-    if (e.out_t) {
-      float a[8];
-#pragma unroll
-      for (int n = 0; n < 8; ++n) a[n] = lrelu(v[n] * e.tscale, e.act_slope);
-      store8<T>(reinterpret_cast<T*>(e.out_t) + o, a);
-    }
+    apply_epilogue<T>(e, g, b, ro, ch0, Lout, v);
   }
 }
 
@@ -192,12 +157,13 @@ gconv_wgrad_simt_kernel(const T* __restrict__ in, const T* __restrict__ dout, fl
 }
 
 // -------------------------------------------------------------------------------------------------
-// Column sums over time (bias gradients): out[(per_batch ? b*C : 0) + c] += sum_t d[b][c][t].
+// Column sums over time (bias gradients): out[(per_batch ? b*cmod : 0) + c % cmod] += sum_t d[b][c][t]
+// (cmod < C folds the u phase groups of a phase-packed ConvTranspose gradient onto the real channels).
 // grid = (C/8, B, splits), block = 256.  `out` must be zeroed by the caller.
 // -------------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(256)
-colsum_kernel(const T* __restrict__ d, float* __restrict__ out, int C, int L, int per_batch) {
+colsum_kernel(const T* __restrict__ d, float* __restrict__ out, int C, int L, int per_batch, int cmod) {
   const int cg = blockIdx.x, b = blockIdx.y;
   const int chunk = (L + gridDim.z - 1) / gridDim.z;
   const int t0 = blockIdx.z * chunk;
@@ -224,7 +190,7 @@ colsum_kernel(const T* __restrict__ d, float* __restrict__ out, int C, int L, in
     float s = 0.f;
 #pragma unroll
     for (int wv = 0; wv < 8; ++wv) s += red[wv][threadIdx.x];
-    atomicAdd(out + (per_batch ? static_cast<size_t>(b) * C : 0) + cg * 8 + threadIdx.x, s);
+    atomicAdd(out + (per_batch ? static_cast<size_t>(b) * cmod : 0) + (cg * 8 + threadIdx.x) % cmod, s);
   }
 }
 

@@ -42,7 +42,7 @@ inline void tc_layer_eligibility(Layer& L) {
   L.tc_ok_dgr = en_dgr && tc_geo_ok(L.dgr);
   static const int en_m64 = tc_env_int("VCD_TC_WGRAD_M64", 1);
   {
-    const ConvGeo& g = L.fwd;
+    const ConvGeo& g = L.wgr;
     const int halo = (g.taps - 1) * (g.step < 0 ? -g.step : g.step);
     const bool shape_ok = g.is == 1 && g.os == 1 && g.p == 0 && g.creal == g.N && g.N % 16 == 0 &&
                           (g.N <= 256 || g.N % 256 == 0) && 64 + halo <= 256;
@@ -119,10 +119,31 @@ inline int tc_run_conv(vcd_plan* p, const Layer& L, bool dgrad, const void* in, 
   while (cols < static_cast<uint32_t>(2 * MT * P.BN)) cols <<= 1;
   P.tmem_cols = cols;
   const size_t a_stage = static_cast<size_t>(MT) * (P.KB / 8) * P.RA * 16;
-  const size_t w_stage = static_cast<size_t>(P.KB / 8) * P.BN * 16;
-  P.NA = 2;
-  P.NW = 4;
-  size_t smem = 128 + P.NA * a_stage + P.NW * w_stage + (2 * P.NA + 2 * P.NW + 4) * 8 + 16;
+  const size_t w_tap = static_cast<size_t>(P.KB / 8) * P.BN * 16;
+  const size_t w_all = w_tap * g.taps * (g.K / P.KB);
+  const size_t budget = 220 * 1024;
+  P.NA = (g.K / P.KB) > 1 ? 3 : 2;
+  if (P.NA * a_stage > budget / 2) P.NA = 2;
+  P.w_resident = (P.n_tiles_n == 1 && w_all <= 100 * 1024 && P.NA * a_stage + w_all <= budget) ? 1 : 0;
+  size_t w_region;
+  if (P.w_resident) {
+    P.TPS = g.taps; P.NW = 1;
+    w_region = w_all;
+  } else {
+    int tps = static_cast<int>((32 * 1024) / w_tap);
+    if (tps < 1) tps = 1;
+    if (tps > g.taps) tps = g.taps;
+    int nw = static_cast<int>((budget - P.NA * a_stage) / (tps * w_tap));
+    while (nw < 2 && tps > 1) { --tps; nw = static_cast<int>((budget - P.NA * a_stage) / (tps * w_tap)); }
+    if (nw > 6) nw = 6;
+    if (nw < 2) {
+      snprintf(err, errn, "tc_run_conv(%s): no room for the weight ring", L.name.c_str());
+      return 1;
+    }
+    P.TPS = tps; P.NW = nw;
+    w_region = static_cast<size_t>(tps) * nw * w_tap;
+  }
+  const size_t smem = 128 + P.NA * a_stage + w_region + (2 * P.NA + 16 + 4) * 8 + 16;
   if (smem > 227 * 1024) {
     snprintf(err, errn, "tc_run_conv(%s): shared memory budget exceeded (%zu bytes)", L.name.c_str(), smem);
     return 1;
@@ -133,7 +154,7 @@ inline int tc_run_conv(vcd_plan* p, const Layer& L, bool dgrad, const void* in, 
     return 1;
   }
   const int grid = P.total_tiles < p->num_sms ? P.total_tiles : p->num_sms;
-  tc::conv_kernel<<<grid, tc::kThreads, smem, stream>>>(tmA, P);
+  tc::conv_kernel<<<grid, tc::kConvThreads, smem, stream>>>(tmA, P);
   launches.fetch_add(1, std::memory_order_relaxed);
   const cudaError_t ce = cudaGetLastError();
   if (ce != cudaSuccess) {
@@ -144,51 +165,59 @@ inline int tc_run_conv(vcd_plan* p, const Layer& L, bool dgrad, const void* in, 
 }
 
 inline int tc_run_wgrad(vcd_plan* p, const Layer& L, const void* in, const void* dout, float* dwp, int B, int Lin,
-                        int Lq, int Lout, cudaStream_t stream, std::atomic<uint64_t>& launches, char* err, size_t errn) {
-  const ConvGeo& g = L.fwd;
-  (void)Lq; (void)Lout;
+                        int Ld, cudaStream_t stream, std::atomic<uint64_t>& launches, char* err, size_t errn) {
+  const ConvGeo& g = L.wgr;
   tc::WgradParams P{};
   P.dwp = dwp;
   P.taps = g.taps; P.K = g.K; P.N = g.N; P.step = g.step; P.off0 = g.off0;
   P.minshift = g.step < 0 ? (g.taps - 1) * g.step : 0;
-  P.B = B; P.L = Lin;
-  P.pair = g.K == 32;
-  if (g.K % 128 == 0) { P.M = 128; P.mch = 16; P.n_mtiles = g.K / 128; }
-  else if (g.K == 64) { P.M = 64; P.mch = 8; P.n_mtiles = 1; }
-  else { P.M = 64; P.mch = 4; P.n_mtiles = 1; }
+  P.B = B; P.L = Ld;
+  if (g.K % 128 == 0) { P.G = 1; P.mch = 16; P.n_mtiles = g.K / 128; }
+  else if (g.K == 64) { P.G = 2; P.mch = 8; P.n_mtiles = 1; }
+  else { P.G = 4; P.mch = 4; P.n_mtiles = 1; }
   P.NT = g.N < 256 ? g.N : 256;
   P.n_ntiles = g.N / P.NT;
-  P.n_slots = P.pair ? (g.taps + 1) / 2 : g.taps;
-  const int cap = P.M == 128 ? 512 / P.NT : 2 * (512 / P.NT);
+  P.n_slots = (g.taps + P.G - 1) / P.G;
+  const int cap = 512 / P.NT;
   P.TG = cap < P.n_slots ? cap : P.n_slots;
   P.n_tgroups = (P.n_slots + P.TG - 1) / P.TG;
-  uint32_t need = static_cast<uint32_t>(P.M == 128 ? P.TG * P.NT : ((P.TG + 1) / 2) * P.NT), cols = 32;
+  uint32_t need = static_cast<uint32_t>(P.TG * P.NT), cols = 32;
   while (cols < need) cols <<= 1;
   P.tmem_cols = cols;
-  P.TK = 64;
   const int astep = g.step < 0 ? -g.step : g.step;
-  P.RI = (P.TK + (g.taps - 1) * astep + 7) / 8 * 8;
-  const size_t stage = static_cast<size_t>(P.mch) * P.RI * 16 * (P.pair ? 2 : 1) + static_cast<size_t>(P.NT / 8) * P.TK * 16;
+  const int halo = (g.taps - 1) * astep;
+  auto stage_bytes = [&](int tk) {
+    const int ri = (tk + halo + 7) / 8 * 8;
+    return static_cast<size_t>(P.mch) * ri * 16 * P.G + static_cast<size_t>(P.NT / 8) * tk * 16;
+  };
+  P.TK = (128 + halo <= 256 && 3 * stage_bytes(128) <= 200 * 1024) ? 128 : 64;
+  P.RI = (P.TK + halo + 7) / 8 * 8;
+  const size_t stage = stage_bytes(P.TK);
   int NS = static_cast<int>((200 * 1024) / stage);
-  P.NS = NS > 4 ? 4 : (NS < 2 ? 2 : NS);
+  P.NS = NS > 6 ? 6 : (NS < 2 ? 2 : NS);
   const size_t smem = 128 + P.NS * stage + (2 * P.NS + 1) * 8 + 16;
   if (smem > 227 * 1024) {
     snprintf(err, errn, "tc_run_wgrad(%s): shared memory budget exceeded (%zu bytes)", L.name.c_str(), smem);
     return 1;
   }
-  const long long base_ctas = 1LL * P.n_mtiles * P.n_ntiles * P.n_tgroups * B;
-  const int max_slabs = (Lin + P.TK - 1) / P.TK;
-  long long want = (2LL * p->num_sms + base_ctas - 1) / base_ctas;
+  // splits of the (batch, time) contraction: enough CTAs for ~1/3 of the SMs per layer (independent layers run
+  // concurrently on side streams), never more than one split per 8 time blocks
+  static const int target_ctas = tc_env_int("VCD_WGRAD_CTAS", 48);
+  const long long base_ctas = 1LL * P.n_mtiles * P.n_ntiles * P.n_tgroups;
+  P.kb_per_item = (Ld + P.TK - 1) / P.TK;
+  const long long total_kb = 1LL * B * P.kb_per_item;
+  long long want = (target_ctas + base_ctas - 1) / base_ctas;
+  const long long max_splits = (total_kb + 7) / 8;
+  if (want > max_splits) want = max_splits;
   if (want < 1) want = 1;
-  if (want > max_slabs) want = max_slabs;
-  P.slab_rows = static_cast<int>(((Lin + want - 1) / want + P.TK - 1) / P.TK) * P.TK;
-  P.slabs_per_item = (Lin + P.slab_rows - 1) / P.slab_rows;
+  P.kb_per_split = static_cast<int>((total_kb + want - 1) / want);
+  P.n_splits = static_cast<int>((total_kb + P.kb_per_split - 1) / P.kb_per_split);
   CUtensorMap tmIn, tmD;
-  if (!tc_make_act_map(&tmIn, in, B, g.K, Lin, P.RI, P.mch) || !tc_make_act_map(&tmD, dout, B, g.N, Lin, P.TK, P.NT / 8)) {
+  if (!tc_make_act_map(&tmIn, in, B, g.K, Lin, P.RI, P.mch) || !tc_make_act_map(&tmD, dout, B, g.N, Ld, P.TK, P.NT / 8)) {
     snprintf(err, errn, "tc_run_wgrad(%s): cuTensorMapEncodeTiled failed", L.name.c_str());
     return 1;
   }
-  const long long grid = base_ctas * P.slabs_per_item;
+  const long long grid = base_ctas * P.n_splits;
   tc::wgrad_kernel<<<static_cast<unsigned>(grid), tc::kThreads, smem, stream>>>(tmIn, tmD, P);
   launches.fetch_add(1, std::memory_order_relaxed);
   const cudaError_t ce = cudaGetLastError();

@@ -95,7 +95,11 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
       : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
         "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+  // the wait is tied to the loaded registers (in/out operands) instead of a memory clobber, so independent
+  // global loads may be scheduled across it
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                 "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]));
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
@@ -127,43 +131,127 @@ struct Pipe {
 
 // ---------------------------------------------------------------------------------------------------
 // Forward / data-gradient convolution (generalised geometry with is == 1).
+//
+// Warp roles (kConvThreads = 320): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer,
+// warps 2..9 = epilogue (two warps per TMEM lane quadrant, interleaved over 16-column units).
+// Weights: if the whole [taps][K][BN] set of the column tile fits (and every tile of the launch uses the same
+// column tile) it is loaded ONCE per CTA and stays resident; otherwise it streams through a ring whose stages
+// hold several taps of one K block (fewer barrier round trips than one tap per stage).
 // ---------------------------------------------------------------------------------------------------
+constexpr int kConvThreads = 320;
+
 struct ConvParams {
   ConvGeo g;
   Epilogue e;
   const bf16* w;          // packed [N/BN][taps][K/8][BN][8]
   int B, Lin, Lq, Lout;
   int BN, MT, KB, RA;     // column tile, 128-row tiles per CTA tile, K block (channels), rows per A region
-  int NA, NW;             // pipeline depths
+  int NA;                 // activation pipeline depth
+  int w_resident;         // 1: all weights of the column tile live in shared memory for the whole kernel
+  int TPS, NW;            // ring mode: taps per stage, stages
   int n_tiles_n, n_mgroups, total_tiles;
   int minshift;           // min over taps of j*step (<= 0)
   uint32_t tmem_cols;
 };
 
-__global__ void __launch_bounds__(kThreads, 1)
+struct EpiLoads {
+  uint4 mask, rest;
+  float4 r2a, r2b;
+};
+
+__device__ __forceinline__ void unpack8(const uint4& raw, float (&f)[8]) {
+  const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    f[2 * i] = __uint_as_float(w[i] << 16);
+    f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+  }
+}
+
+__device__ __forceinline__ void epi_prefetch(const Epilogue& e, size_t o, bool valid, EpiLoads& L) {
+  if (!valid) return;
+  if (e.mask) L.mask = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(e.mask) + o));
+  if (e.res_t) L.rest = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(e.res_t) + o));
+  if (e.res2) {
+    L.r2a = __ldg(reinterpret_cast<const float4*>(e.res2 + o));
+    L.r2b = __ldg(reinterpret_cast<const float4*>(e.res2 + o) + 1);
+  }
+}
+
+__device__ __forceinline__ void epi_finish(const Epilogue& e, const ConvGeo& g, int b, int ro, int ch0, size_t o,
+                                           const EpiLoads& L, float (&v)[8]) {
+  if (e.bias) {
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(e.bias + ch0));
+    const float4 b1 = __ldg(reinterpret_cast<const float4*>(e.bias + ch0) + 1);
+    v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+    v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+  }
+  if (e.bias2) {
+    const float* bp = e.bias2 + static_cast<size_t>(b) * g.creal + ch0;
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(bp));
+    const float4 b1 = __ldg(reinterpret_cast<const float4*>(bp) + 1);
+    v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+    v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+  }
+  if (e.mask) {
+    float m[8];
+    unpack8(L.mask, m);
+#pragma unroll
+    for (int n = 0; n < 8; ++n) v[n] *= (m[n] > 0.f ? 1.f : e.mask_slope);
+  }
+#pragma unroll
+  for (int n = 0; n < 8; ++n) v[n] *= e.scale;
+  if (e.res_t) {
+    float t[8];
+    unpack8(L.rest, t);
+#pragma unroll
+    for (int n = 0; n < 8; ++n) v[n] += (t[n] > 0.f ? t[n] : t[n] * e.res_inv);
+  }
+  if (e.res2) {
+    v[0] += L.r2a.x; v[1] += L.r2a.y; v[2] += L.r2a.z; v[3] += L.r2a.w;
+    v[4] += L.r2b.x; v[5] += L.r2b.y; v[6] += L.r2b.z; v[7] += L.r2b.w;
+  }
+  if (e.out_raw) store8<float>(e.out_raw + o, v);
+  if (e.out_t) {
+    float a[8];
+#pragma unroll
+    for (int n = 0; n < 8; ++n) a[n] = lrelu(v[n] * e.tscale, e.act_slope);
+    if (e.zu > 0) {
+      const int q = (ro + e.zp) / e.zu, r = (ro + e.zp) - q * e.zu;
+      store8<bf16>(reinterpret_cast<bf16*>(e.out_t) + blk_off(b, r * g.creal + ch0, q, e.zu * g.creal, e.zLq), a);
+    } else {
+      store8<bf16>(reinterpret_cast<bf16*>(e.out_t) + o, a);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kConvThreads, 1)
 conv_kernel(const __grid_constant__ CUtensorMap tmA, const ConvParams P) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   const uint32_t a_region_bytes = static_cast<uint32_t>(P.KB / 8) * P.RA * 16;
   const uint32_t a_stage_bytes = a_region_bytes * P.MT;
-  const uint32_t w_stage_bytes = static_cast<uint32_t>(P.KB / 8) * P.BN * 16;
+  const uint32_t w_tap_bytes = static_cast<uint32_t>(P.KB / 8) * P.BN * 16;   // one tap of one K block
+  const int kblocks = P.g.K / P.KB;
+  const int kk_per_block = P.KB / 16;
+  const uint32_t w_region_bytes = P.w_resident ? w_tap_bytes * P.g.taps * kblocks : w_tap_bytes * P.TPS * P.NW;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
   uint8_t* a_smem = smem;
   uint8_t* w_smem = a_smem + static_cast<size_t>(P.NA) * a_stage_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(w_smem + static_cast<size_t>(P.NW) * w_stage_bytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(w_smem + w_region_bytes);
   uint64_t* fullA = bars;
   uint64_t* emptyA = fullA + P.NA;
-  uint64_t* fullW = emptyA + P.NA;
-  uint64_t* emptyW = fullW + P.NW;
-  uint64_t* acc_full = emptyW + P.NW;
+  uint64_t* fullW = emptyA + P.NA;      // ring mode: NW entries; resident mode: entry 0 = "weights loaded"
+  uint64_t* emptyW = fullW + 8;
+  uint64_t* acc_full = emptyW + 8;
   uint64_t* acc_empty = acc_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < P.NA; ++i) { mbar_init(&fullA[i], 1); mbar_init(&emptyA[i], 1); }
-    for (int i = 0; i < P.NW; ++i) { mbar_init(&fullW[i], 1); mbar_init(&emptyW[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+    for (int i = 0; i < 8; ++i) { mbar_init(&fullW[i], 1); mbar_init(&emptyW[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 8); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, P.tmem_cols);
@@ -172,12 +260,15 @@ conv_kernel(const __grid_constant__ CUtensorMap tmA, const ConvParams P) {
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int kblocks = P.g.K / P.KB;
-  const int kk_per_block = P.KB / 16;
-
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
+      if (P.w_resident) {  // whole weight set of column tile 0 (n_tiles_n == 1), one bulk copy per 64 KB
+        const uint32_t total = w_region_bytes;
+        mbar_expect_tx(&fullW[0], total);
+        for (uint32_t off = 0; off < total; off += 65536u)
+          bulk_load(w_smem + off, reinterpret_cast<const uint8_t*>(P.w) + off, min(65536u, total - off), &fullW[0]);
+      }
       Pipe pa, pw;
       for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
         const int nt = tile % P.n_tiles_n;
@@ -192,12 +283,19 @@ conv_kernel(const __grid_constant__ CUtensorMap tmA, const ConvParams P) {
             tma_load_4d(&tmA, &fullA[pa.stage], a_smem + static_cast<size_t>(pa.stage) * a_stage_bytes + mt * a_region_bytes,
                         0, row0 + mt * 128, kb * (P.KB / 8), b);
           pa.advance(P.NA);
-          for (int j = 0; j < P.g.taps; ++j) {
-            mbar_wait(&emptyW[pw.stage], pw.phase ^ 1);
-            mbar_expect_tx(&fullW[pw.stage], w_stage_bytes);
-            const bf16* src = P.w + ((static_cast<size_t>(nt) * P.g.taps + j) * (P.g.K / 8) + static_cast<size_t>(kb) * (P.KB / 8)) * P.BN * 8;
-            bulk_load(w_smem + static_cast<size_t>(pw.stage) * w_stage_bytes, src, w_stage_bytes, &fullW[pw.stage]);
-            pw.advance(P.NW);
+          if (!P.w_resident) {
+            for (int j0 = 0; j0 < P.g.taps; j0 += P.TPS) {
+              const int nj = min(P.TPS, P.g.taps - j0);
+              mbar_wait(&emptyW[pw.stage], pw.phase ^ 1);
+              mbar_expect_tx(&fullW[pw.stage], nj * w_tap_bytes);
+              uint8_t* dst = w_smem + static_cast<size_t>(pw.stage) * P.TPS * w_tap_bytes;
+              for (int jj = 0; jj < nj; ++jj) {
+                const bf16* src = P.w + ((static_cast<size_t>(nt) * P.g.taps + j0 + jj) * (P.g.K / 8) +
+                                         static_cast<size_t>(kb) * (P.KB / 8)) * P.BN * 8;
+                bulk_load(dst + jj * w_tap_bytes, src, w_tap_bytes, &fullW[pw.stage]);
+              }
+              pw.advance(P.NW);
+            }
           }
         }
       }
@@ -207,31 +305,55 @@ conv_kernel(const __grid_constant__ CUtensorMap tmA, const ConvParams P) {
     if (lane == 0) {
       const uint32_t idesc = make_idesc(128, P.BN, 0, 0);
       const uint32_t a_lbo = static_cast<uint32_t>(P.RA) * 16, w_lbo = static_cast<uint32_t>(P.BN) * 16;
+      // descriptor arithmetic in 16-byte units on the low word (start-address field)
+      const uint32_t a_region16 = a_region_bytes >> 4, a_kk16 = (2 * a_lbo) >> 4, w_kk16 = (2 * w_lbo) >> 4;
+      const uint32_t w_tap16 = w_tap_bytes >> 4;
+      const uint64_t a_desc0 = make_desc(0, a_lbo, 128), w_desc0 = make_desc(0, w_lbo, 128);
       Pipe pa, pw;
       int it = 0;
+      if (P.w_resident) {
+        mbar_wait(&fullW[0], 0);
+        tc_fence_after();
+      }
       for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++it) {
         const int buf = it & 1;
         mbar_wait(&acc_empty[buf], ((it >> 1) & 1) ^ 1);
         tc_fence_after();
+        const uint32_t d_tile = tmem_base + static_cast<uint32_t>(buf * P.MT * P.BN);
         for (int kb = 0; kb < kblocks; ++kb) {
           mbar_wait(&fullA[pa.stage], pa.phase);
           tc_fence_after();
-          const uint32_t a_base = smem_u32(a_smem + static_cast<size_t>(pa.stage) * a_stage_bytes);
-          for (int j = 0; j < P.g.taps; ++j) {
-            mbar_wait(&fullW[pw.stage], pw.phase);
-            tc_fence_after();
-            const uint32_t w_base = smem_u32(w_smem + static_cast<size_t>(pw.stage) * w_stage_bytes);
-            const uint32_t shift_bytes = static_cast<uint32_t>(j * P.g.step - P.minshift) * 16;
-            for (int mt = 0; mt < P.MT; ++mt) {
-              const uint32_t d_tmem = tmem_base + static_cast<uint32_t>((buf * P.MT + mt) * P.BN);
-              for (int kk = 0; kk < kk_per_block; ++kk) {
-                const uint64_t ad = make_desc(a_base + mt * a_region_bytes + kk * 2 * a_lbo + shift_bytes, a_lbo, 128);
-                const uint64_t bd = make_desc(w_base + kk * 2 * w_lbo, w_lbo, 128);
-                umma_bf16(d_tmem, ad, bd, idesc, (kb | j | kk) != 0 ? 1u : 0u);
+          const uint64_t a_stage_desc = a_desc0 + (smem_u32(a_smem + static_cast<size_t>(pa.stage) * a_stage_bytes) >> 4);
+          int j = 0;
+          while (j < P.g.taps) {
+            int nj;
+            uint64_t w_desc;
+            if (P.w_resident) {
+              nj = P.g.taps;
+              w_desc = w_desc0 + ((smem_u32(w_smem) >> 4) + static_cast<uint32_t>(kb) * w_tap16);
+            } else {
+              nj = min(P.TPS, P.g.taps - j);
+              mbar_wait(&fullW[pw.stage], pw.phase);
+              tc_fence_after();
+              w_desc = w_desc0 + (smem_u32(w_smem + static_cast<size_t>(pw.stage) * P.TPS * w_tap_bytes) >> 4);
+            }
+            // resident layout is [tap][K/8][BN][8]: consecutive taps are kblocks*w_tap16 apart
+            const uint32_t tap_stride16 = P.w_resident ? w_tap16 * kblocks : w_tap16;
+            for (int jj = 0; jj < nj; ++jj, ++j) {
+              const uint64_t a_tap = a_stage_desc + static_cast<uint32_t>(j * P.g.step - P.minshift);
+              const uint64_t w_tap = w_desc + jj * tap_stride16;
+              for (int mt = 0; mt < P.MT; ++mt) {
+                const uint32_t d_tmem = d_tile + static_cast<uint32_t>(mt * P.BN);
+                const uint64_t a_mt = a_tap + mt * a_region16;
+#pragma unroll 4
+                for (int kk = 0; kk < kk_per_block; ++kk)
+                  umma_bf16(d_tmem, a_mt + kk * a_kk16, w_tap + kk * w_kk16, idesc, (kb | j | kk) != 0 ? 1u : 0u);
               }
             }
-            umma_commit(&emptyW[pw.stage]);
-            pw.advance(P.NW);
+            if (!P.w_resident) {
+              umma_commit(&emptyW[pw.stage]);
+              pw.advance(P.NW);
+            }
           }
           umma_commit(&emptyA[pa.stage]);
           pa.advance(P.NA);
@@ -242,8 +364,11 @@ conv_kernel(const __grid_constant__ CUtensorMap tmA, const ConvParams P) {
   } else {
     // ===================== epilogue warps =====================
     const int quad = warp & 3;               // TMEM lane quadrant this warp may access
+    const int half = (warp - 2) >> 2;        // two warps per quadrant interleave over 16-column units
     const int row_in_tile = quad * 32 + lane;
     const Epilogue& e = P.e;
+    const int units_per_mt = P.BN / 16;
+    const int n_units = P.MT * units_per_mt;
     int it = 0;
     for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++it) {
       const int nt = tile % P.n_tiles_n;
@@ -251,62 +376,54 @@ conv_kernel(const __grid_constant__ CUtensorMap tmA, const ConvParams P) {
       const int mg = rest % P.n_mgroups;
       const int b = rest / P.n_mgroups;
       const int buf = it & 1;
+      const int r_phase = (nt * P.BN) / P.g.creal;          // scatter phase of this column tile (os > 1)
+      const int ch_tile = nt * P.BN - r_phase * P.g.creal;  // first output channel of the tile
+
+      auto unit_coords = [&](int u, int& ro, bool& valid, size_t& o0, uint32_t& taddr) {
+        const int mt = u / units_per_mt, c16 = u - mt * units_per_mt;
+        const int q = (mg * P.MT + mt) * 128 + row_in_tile;
+        ro = q * P.g.os + r_phase - P.g.p;
+        valid = q < P.Lq && ro >= 0 && ro < P.Lout;
+        o0 = blk_off(b, ch_tile + c16 * 16, valid ? ro : 0, P.g.creal, P.Lout);
+        taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>((buf * P.MT + mt) * P.BN + c16 * 16);
+      };
+
+      // software pipeline: global operands of unit u+2 are requested before unit u is finished
+      EpiLoads cur[2], nxt[2];
+      int ro_c = 0, ro_n = 0;
+      bool v_c = false, v_n = false;
+      size_t o_c = 0, o_n = 0;
+      uint32_t t_c = 0, t_n = 0;
+      const size_t chunk_stride = static_cast<size_t>(P.Lout) * 8;  // next 8-channel group of the same row
+      int u = half;
+      if (u < n_units) {
+        unit_coords(u, ro_c, v_c, o_c, t_c);
+        epi_prefetch(e, o_c, v_c, cur[0]);
+        epi_prefetch(e, o_c + chunk_stride, v_c, cur[1]);
+      }
       mbar_wait(&acc_full[buf], (it >> 1) & 1);
       tc_fence_after();
-      for (int mt = 0; mt < P.MT; ++mt) {
-        const int q = (mg * P.MT + mt) * 128 + row_in_tile;
-        const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>((buf * P.MT + mt) * P.BN);
-        for (int c16 = 0; c16 < P.BN / 16; ++c16) {
-          float acc[16];
-          tmem_ld16(t_row + c16 * 16, acc);
+      for (; u < n_units; u += 2) {
+        const int un = u + 2;
+        if (un < n_units) {
+          unit_coords(un, ro_n, v_n, o_n, t_n);
+          epi_prefetch(e, o_n, v_n, nxt[0]);
+          epi_prefetch(e, o_n + chunk_stride, v_n, nxt[1]);
+        }
+        float acc[16];
+        tmem_ld16(t_c, acc);
+        if (v_c) {
+          const int c16 = u % units_per_mt;
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
-            const int n0 = nt * P.BN + c16 * 16 + h * 8;
-            const int r = n0 / P.g.creal;
-            const int ch0 = n0 - r * P.g.creal;
-            const int ro = q * P.g.os + r - P.g.p;
-            if (q >= P.Lq || ro < 0 || ro >= P.Lout) continue;
-            const size_t o = blk_off(b, ch0, ro, P.g.creal, P.Lout);
             float v[8];
 #pragma unroll
             for (int n = 0; n < 8; ++n) v[n] = acc[h * 8 + n];
-            if (e.bias) {
-#pragma unroll
-              for (int n = 0; n < 8; ++n) v[n] += __ldg(e.bias + ch0 + n);
-            }
-            if (e.bias2) {
-#pragma unroll
-              for (int n = 0; n < 8; ++n) v[n] += __ldg(e.bias2 + static_cast<size_t>(b) * P.g.creal + ch0 + n);
-            }
-            if (e.mask) {
-              float m[8];
-              load8<bf16>(reinterpret_cast<const bf16*>(e.mask) + o, m);
-#pragma unroll
-              for (int n = 0; n < 8; ++n) v[n] *= (m[n] > 0.f ? 1.f : e.mask_slope);
-            }
-#pragma unroll
-            for (int n = 0; n < 8; ++n) v[n] *= e.scale;
-            if (e.res) {
-              float t[8];
-              load8<float>(e.res + o, t);
-#pragma unroll
-              for (int n = 0; n < 8; ++n) v[n] += t[n];
-            }
-            if (e.res2) {
-              float t[8];
-              load8<float>(e.res2 + o, t);
-#pragma unroll
-              for (int n = 0; n < 8; ++n) v[n] += t[n];
-            }
-            if (e.out_raw) store8<float>(e.out_raw + o, v);
-            if (e.out_t) {
-              float a[8];
-#pragma unroll
-              for (int n = 0; n < 8; ++n) a[n] = lrelu(v[n] * e.tscale, e.act_slope);
-              store8<bf16>(reinterpret_cast<bf16*>(e.out_t) + o, a);
-            }
+            epi_finish(e, P.g, b, ro_c, ch_tile + c16 * 16 + h * 8, o_c + h * chunk_stride, cur[h], v);
           }
         }
+        cur[0] = nxt[0]; cur[1] = nxt[1];
+        ro_c = ro_n; v_c = v_n; o_c = o_n; t_c = t_n;
       }
       tc_fence_before();
       __syncwarp();
@@ -321,26 +438,27 @@ conv_kernel(const __grid_constant__ CUtensorMap tmA, const ConvParams P) {
 
 // ---------------------------------------------------------------------------------------------------
 // Weight gradient:  dWp[j][c][n] += sum_t in[b][t + off0 + j*step][c] * dout[b][t][n]     (is = os = 1)
-// GEMM view: D[M = c][N = n] per tap, contraction over time.  Both operands are read MN-major straight from
-// the blocked layout (time rows are the 16-byte-strided K direction: LBO = 128 B, SBO = channel-group stride),
-// a tap is again a +16*shift byte offset on the A descriptor.  One CTA = (channel tile, column tile, tap group,
-// time slab); partial sums of different slabs are combined with fp32 atomics (dWp zeroed by the caller).
-//   M == 128 : accumulator of tap tl at TMEM columns tl*NT, all 128 lanes.
-//   M == 64  : two accumulators share NT columns (lanes +0 / +16 of every 32-lane quadrant).
-//   pair     : K_conv == 32 -- rows 0..31 of a 64-row accumulator are tap 2*tl, rows 32..63 tap 2*tl+1 (the
-//              A tile holds a second copy of the 4 channel groups displaced by `step` rows).
+// GEMM view: D[M][N = n] with the contraction over time.  Both operands are read MN-major straight from the
+// blocked layout (time rows are the 16-byte-strided K direction: LBO = 128 B, SBO = channel-group stride);
+// a tap is again a +16*shift byte offset on the A descriptor.
+// M is always 128: for K_conv >= 128 it is a 128-channel tile of one tap; for K_conv = 64 / 32 the A tile holds
+// G = 2 / 4 copies of the channel groups, copy g displaced by g*step rows, so ONE MMA covers G consecutive taps
+// (rows g*K .. g*K+K-1 of the accumulator belong to tap slot*G + g).
+// One CTA = (channel tile, column tile, slot group, split of the flattened (batch, time block) range); a single
+// split stores its result directly, several splits combine with fp32 atomics (dWp zeroed by the caller).  Few,
+// long CTAs per layer are preferred: the host runs the weight-gradient kernels of independent layers
+// concurrently on side streams.
 // ---------------------------------------------------------------------------------------------------
 struct WgradParams {
   float* dwp;             // [taps][K][N] fp32
   int taps, K, N, step, off0, minshift;
-  int B, L;
-  int M, mch, n_mtiles;   // instruction M (128 | 64), channel groups per A tile, channel tiles
+  int B, L;               // L = rows of dout per batch item (the contraction length)
+  int G, mch, n_mtiles;   // tap copies per MMA, channel groups per copy, channel tiles
   int NT, n_ntiles;       // column tile (<= 256)
-  int pair;               // 1: K == 32 tap pairing
-  int TG, n_tgroups;      // accumulator slots (taps, or tap pairs) per CTA and number of groups
-  int n_slots;            // total slots = pair ? ceil(taps/2) : taps
+  int TG, n_tgroups;      // accumulator slots per CTA and number of slot groups
+  int n_slots;            // total slots = ceil(taps / G)
   int TK, RI;             // time rows per pipeline stage, rows of the A tile (TK + halo)
-  int slab_rows, slabs_per_item;
+  int kb_per_item, n_splits, kb_per_split;  // the flattened (batch, time block) range is cut into n_splits
   int NS;
   uint32_t tmem_cols;
 };
@@ -350,7 +468,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ C
   extern __shared__ __align__(128) uint8_t smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t in_copy_bytes = static_cast<uint32_t>(P.mch) * P.RI * 16;
-  const uint32_t in_bytes = in_copy_bytes * (P.pair ? 2 : 1);
+  const uint32_t in_bytes = in_copy_bytes * P.G;
   const uint32_t d_bytes = static_cast<uint32_t>(P.NT / 8) * P.TK * 16;
   const uint32_t stage_bytes = in_bytes + d_bytes;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
@@ -373,14 +491,13 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ C
 
   // CTA coordinates
   int id = blockIdx.x;
-  const int slab = id % P.slabs_per_item; id /= P.slabs_per_item;
-  const int b = id % P.B; id /= P.B;
+  const int split = id % P.n_splits; id /= P.n_splits;
   const int tg = id % P.n_tgroups; id /= P.n_tgroups;
   const int ntile = id % P.n_ntiles; id /= P.n_ntiles;
   const int mtile = id;
-  const int t_begin = slab * P.slab_rows;
-  const int t_end = min(P.L, t_begin + P.slab_rows);
-  const int kblocks = (t_end - t_begin + P.TK - 1) / P.TK;
+  const int f_begin = split * P.kb_per_split;
+  const int f_end = min(P.B * P.kb_per_item, f_begin + P.kb_per_split);
+  const int kblocks = f_end - f_begin;
   const int slot0 = tg * P.TG;
   const int nslots = min(P.TG, P.n_slots - slot0);
 
@@ -388,37 +505,37 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ C
     if (lane == 0) {
       Pipe ps;
       for (int kb = 0; kb < kblocks; ++kb) {
-        const int t0 = t_begin + kb * P.TK;
+        const int f = f_begin + kb;
+        const int b = f / P.kb_per_item;
+        const int t0 = (f - b * P.kb_per_item) * P.TK;
         mbar_wait(&empty[ps.stage], ps.phase ^ 1);
         mbar_expect_tx(&full[ps.stage], stage_bytes);
         uint8_t* st = smem + static_cast<size_t>(ps.stage) * stage_bytes;
-        tma_load_4d(&tmIn, &full[ps.stage], st, 0, t0 + P.off0 + P.minshift, mtile * P.mch, b);
-        if (P.pair) tma_load_4d(&tmIn, &full[ps.stage], st + in_copy_bytes, 0, t0 + P.off0 + P.minshift + P.step, mtile * P.mch, b);
+        for (int g = 0; g < P.G; ++g)
+          tma_load_4d(&tmIn, &full[ps.stage], st + g * in_copy_bytes, 0, t0 + P.off0 + P.minshift + g * P.step, mtile * P.mch, b);
         tma_load_4d(&tmD, &full[ps.stage], st + in_bytes, 0, t0, ntile * (P.NT / 8), b);
         ps.advance(P.NS);
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      const uint32_t idesc = make_idesc(P.M, P.NT, 1, 1);
-      const uint32_t a_sbo = static_cast<uint32_t>(P.RI) * 16, b_sbo = static_cast<uint32_t>(P.TK) * 16;
+      const uint32_t idesc = make_idesc(128, P.NT, 1, 1);
+      const uint64_t a_desc0 = make_desc(0, 128, static_cast<uint32_t>(P.RI) * 16);
+      const uint64_t b_desc0 = make_desc(0, 128, static_cast<uint32_t>(P.TK) * 16);
+      const int kks = P.TK / 16;
       Pipe ps;
       for (int kb = 0; kb < kblocks; ++kb) {
         mbar_wait(&full[ps.stage], ps.phase);
         tc_fence_after();
         const uint32_t a_base = smem_u32(smem + static_cast<size_t>(ps.stage) * stage_bytes);
-        const uint32_t b_base = a_base + in_bytes;
+        const uint64_t a_stage = a_desc0 + (a_base >> 4);
+        const uint64_t b_stage = b_desc0 + ((a_base + in_bytes) >> 4);
         for (int tl = 0; tl < nslots; ++tl) {
-          const int j = (slot0 + tl) * (P.pair ? 2 : 1);
-          const uint32_t shift_bytes = static_cast<uint32_t>(j * P.step - P.minshift) * 16;
-          uint32_t d_tmem;
-          if (P.M == 128) d_tmem = tmem_base + static_cast<uint32_t>(tl * P.NT);
-          else d_tmem = tmem_base + static_cast<uint32_t>((tl >> 1) * P.NT) + (static_cast<uint32_t>((tl & 1) * 16) << 16);
-          for (int kk = 0; kk < P.TK / 16; ++kk) {
-            const uint64_t ad = make_desc(a_base + shift_bytes + kk * 256, 128, a_sbo);
-            const uint64_t bd = make_desc(b_base + kk * 256, 128, b_sbo);
-            umma_bf16(d_tmem, ad, bd, idesc, (kb | kk) != 0 ? 1u : 0u);
-          }
+          const uint64_t a_slot = a_stage + static_cast<uint32_t>((slot0 + tl) * P.G * P.step - P.minshift);
+          const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(tl * P.NT);
+#pragma unroll 4
+          for (int kk = 0; kk < kks; ++kk)
+            umma_bf16(d_tmem, a_slot + kk * 16, b_stage + kk * 16, idesc, (kb | kk) != 0 ? 1u : 0u);
         }
         umma_commit(&empty[ps.stage]);
         ps.advance(P.NS);
@@ -427,37 +544,27 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ C
     }
   } else {
     const int quad = warp & 3;
+    const int row = quad * 32 + lane;
     mbar_wait(acc_full, 0);
     tc_fence_after();
+    const int rows_per_tap = 128 / P.G;
+    const int g = row / rows_per_tap;
     for (int tl = 0; tl < nslots; ++tl) {
-      int j, c;            // tap and conv-K channel handled by this thread for this slot (j < 0: nothing)
-      uint32_t col0;
-      bool active = true;
-      if (P.M == 128) {
-        j = slot0 + tl;
-        c = mtile * 128 + quad * 32 + lane;
-        col0 = static_cast<uint32_t>(tl * P.NT);
-      } else {
-        // lanes 16..31 of a quadrant hold the odd slot of the column block
-        if ((tl & 1) != (lane >> 4)) active = false;
-        const int row = quad * 16 + (lane & 15);
-        col0 = static_cast<uint32_t>((tl >> 1) * P.NT);
-        if (P.pair) {
-          j = (slot0 + tl) * 2 + (row >> 5);
-          c = row & 31;
-        } else {
-          j = slot0 + tl;
-          c = mtile * 64 + row;
-        }
-      }
-      if (j >= P.taps) active = false;
+      const int j = (slot0 + tl) * P.G + g;
+      const int c = P.G == 1 ? mtile * 128 + row : row - g * rows_per_tap;
+      const bool active = j < P.taps;
       for (int c16 = 0; c16 < P.NT / 16; ++c16) {
         float acc[16];
-        tmem_ld16(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + col0 + c16 * 16, acc);
+        tmem_ld16(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(tl * P.NT + c16 * 16), acc);
         if (active) {
           float* dst = P.dwp + (static_cast<size_t>(j) * P.K + c) * P.N + ntile * P.NT + c16 * 16;
+          if (P.n_splits == 1) {
 #pragma unroll
-          for (int n = 0; n < 16; ++n) atomicAdd(dst + n, acc[n]);
+            for (int n = 0; n < 16; n += 4) *reinterpret_cast<float4*>(dst + n) = make_float4(acc[n], acc[n + 1], acc[n + 2], acc[n + 3]);
+          } else {
+#pragma unroll
+            for (int n = 0; n < 16; ++n) atomicAdd(dst + n, acc[n]);
+          }
         }
       }
     }

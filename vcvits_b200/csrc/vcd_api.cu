@@ -59,7 +59,7 @@ static int fail(const char* fmt, ...) {
 namespace {
 enum : int { PC_TC_CONV = 0, PC_TC_WGRAD, PC_FFMA_CONV, PC_FFMA_WGRAD, PC_POST, PC_FOLD, PC_MISC, PC_COUNT };
 const char* kProfNames[PC_COUNT] = {"tc_conv(fwd+dgrad)", "tc_wgrad", "ffma_conv", "ffma_wgrad", "conv_post", "weight_norm_fold", "misc"};
-struct ProfRec { int cls; cudaEvent_t a, b; double flops, bytes; };
+struct ProfRec { int cls; cudaEvent_t a, b; double flops, bytes; std::string tag; };
 bool g_prof_on = false;
 std::vector<ProfRec> g_prof;
 std::vector<cudaEvent_t> g_prof_pool;
@@ -71,9 +71,9 @@ cudaEvent_t prof_event() {
 }
 struct ProfScope {
   cudaStream_t s; bool on;
-  ProfScope(int cls, double flops, double bytes, cudaStream_t stream) : s(stream), on(g_prof_on) {
+  ProfScope(int cls, double flops, double bytes, cudaStream_t stream, const char* tag = "") : s(stream), on(g_prof_on) {
     if (!on) return;
-    ProfRec r{cls, prof_event(), prof_event(), flops, bytes};
+    ProfRec r{cls, prof_event(), prof_event(), flops, bytes, tag};
     cudaEventRecord(r.a, s);
     g_prof.push_back(r);
   }
@@ -97,6 +97,21 @@ extern "C" int vcd_profile_read(int reset, double* ms, uint64_t* launches, doubl
     for (const ProfRec& r : g_prof) { g_prof_pool.push_back(r.a); g_prof_pool.push_back(r.b); }
     g_prof.clear();
   }
+  return 0;
+}
+
+// Writes one CSV line per recorded launch (class, tag, ms, gflop) to `path`; does not reset.
+extern "C" int vcd_profile_dump(const char* path) {
+  cudaDeviceSynchronize();
+  FILE* f = fopen(path, "w");
+  if (!f) return fail("vcd_profile_dump: cannot open %s", path);
+  fprintf(f, "class,tag,ms,gflop\n");
+  for (const ProfRec& r : g_prof) {
+    float t = 0.f;
+    cudaEventElapsedTime(&t, r.a, r.b);
+    fprintf(f, "%s,%s,%.6f,%.4f\n", kProfNames[r.cls], r.tag.c_str(), t, r.flops / 1e9);
+  }
+  fclose(f);
   return 0;
 }
 
@@ -146,6 +161,7 @@ static int add_conv(vcd_plan* p, const std::string& name, int cin, int cout, int
   }
   L.fwd = ConvGeo{k, cin, cout, 1, -L.pad, dil, 1, 0, cout};
   L.dgr = ConvGeo{k, cout, cin, 1, -L.pad, dil, 1, 0, cin};
+  L.wgr = L.fwd;
   L.map_fwd = WeightMap{SRC_CONV_FWD, cin, cout, k, 1};
   L.map_dgr = WeightMap{SRC_CONV_DGRAD, cin, cout, k, 1};
   p->layers.push_back(L);
@@ -165,8 +181,11 @@ static int add_convt(vcd_plan* p, const std::string& name, int cin, int cout, in
   const int m = (k + u - 1) / u;
   // forward, scatter form: Z[q][(r,co)] = sum_{s<m} x[q-s] W[:,co,s*u+r]  ->  y[q*u + r - pad][co]
   L.fwd = ConvGeo{m, cin, u * cout, 1, 0, -1, u, L.pad, cout};
-  // data gradient: dx[i][ci] = sum_j sum_co dy[i*u - pad + j][co] W[ci][co][j]
-  L.dgr = ConvGeo{k, cout, cin, u, -L.pad, 1, 1, 0, cin};
+  // data gradient on the phase-packed ("Z") output gradient DY[q][(r,co)] = dy[q*u + r - pad][co]:
+  //   dx[i][ci] = sum_{s<m} sum_{(r,co)} DY[i+s][(r,co)] W[ci][co][s*u+r]      -- a plain m-tap convolution
+  L.dgr = ConvGeo{m, u * cout, cin, 1, 0, 1, 1, 0, cin};
+  // weight gradient: same taps as fwd, DY taken as an ordinary [u*cout]-channel tensor
+  L.wgr = ConvGeo{m, cin, u * cout, 1, 0, -1, 1, 0, u * cout};
   L.map_fwd = WeightMap{SRC_CONVT_FWD, cin, cout, k, u};
   L.map_dgr = WeightMap{SRC_CONVT_DGRAD, cin, cout, k, u};
   p->layers.push_back(L);
@@ -379,6 +398,8 @@ extern "C" int vcd_plan_create(const vcd_config* cfg, vcd_plan** out_plan) {
     sj.nblocks = blk;
     TRY(upload_jobs(uj, &sj.d_jobs));
   }
+  for (int i = 0; i < vcd_plan::kMaxAux; ++i) CU_TRY(cudaStreamCreateWithFlags(&p->aux[i], cudaStreamNonBlocking));
+  for (int i = 0; i < vcd_plan::kMaxEvents; ++i) CU_TRY(cudaEventCreateWithFlags(&p->events[i], cudaEventDisableTiming));
   TRY(tc_plan_init(p));
   *out_plan = p;
   return 0;
@@ -390,6 +411,8 @@ extern "C" void vcd_plan_destroy(vcd_plan* p) {
   cudaFree(p->d_params); cudaFree(p->d_dparams); cudaFree(p->d_norm_jobs);
   cudaFree(p->d_pack_jobs[0]); cudaFree(p->d_pack_jobs[1]);
   for (auto& s : p->segments) cudaFree(s.d_jobs);
+  for (int i = 0; i < vcd_plan::kMaxAux; ++i) if (p->aux[i]) cudaStreamDestroy(p->aux[i]);
+  for (int i = 0; i < vcd_plan::kMaxEvents; ++i) if (p->events[i]) cudaEventDestroy(p->events[i]);
   delete p;
 }
 
@@ -419,20 +442,32 @@ extern "C" int vcd_segment_params(const vcd_plan* p, int seg, int* idx, int cap)
 // ---------------------------------------------------------------------------------------------------
 // workspace layout
 // ---------------------------------------------------------------------------------------------------
+// Only ACTIVATED tensors (storage type T) are kept between layers; fp32 is used for the running branch
+// sums, the per-batch conditioning bias and the boundary tensors.  With save_for_backward the activations of
+// every layer stay resident (they are the wgrad operands and the leaky_relu masks of the backward pass);
+// without it every stage recycles one scratch set per ResBlock branch.
 namespace {
 struct StageWs {
-  size_t u_raw = 0, ua = 0;
+  size_t ua = 0;
   std::vector<std::vector<size_t>> ma, xa;  // [branch][pair]
 };
 struct WsLayout {
   size_t xin = 0, cb = 0, dcb = 0;
   std::vector<size_t> a;
   std::vector<StageWs> st;
-  size_t xr[2] = {0, 0}, sum[2] = {0, 0};
-  size_t Gr[2] = {0, 0}, Gt[2] = {0, 0}, dm = 0, bsum[2] = {0, 0}, du = 0, Gi_r[2] = {0, 0}, Gi_t[2] = {0, 0};
+  size_t sum[2] = {0, 0};                   // fp32 running sums over ResBlock branches (fwd) / branch gradients (bwd)
+  size_t Gi[2] = {0, 0};                    // T: gradient w.r.t. a stage output (ping-pong across stages)
+  std::vector<std::vector<size_t>> Gt, dm;  // T [branch][pair]: residual-stream gradient / mid gradient
+  size_t duz = 0;                           // T: phase-packed gradient w.r.t. the upsample output
   size_t d0 = 0, dxb = 0;
   size_t total = 0;
 };
+
+size_t stage_elems(const vcd_plan* p, int i, int B, int T) {
+  size_t L = T;
+  for (int s = 0; s <= i; ++s) L *= p->stages[s].u;
+  return static_cast<size_t>(B) * p->stages[i].cout * L;
+}
 
 WsLayout make_layout(const vcd_plan* p, int mode, int B, int T, bool save) {
   WsLayout w;
@@ -451,43 +486,51 @@ WsLayout make_layout(const vcd_plan* p, int mode, int B, int T, bool save) {
   w.dcb = alloc(4 * B * C0);
   w.a.resize(S + 1);
   w.a[0] = alloc(es * B * C0 * T);
-  size_t L = T, emax = 0;
+  size_t emax = 0, zmax = 0, L = T;
   std::vector<size_t> E(S);
   for (int i = 0; i < S; ++i) {
+    const Layer& U = p->layers[p->stages[i].up_layer];
+    zmax = std::max(zmax, static_cast<size_t>(B) * U.wgr.N * (L + U.fwd.taps - 1));
     L *= p->stages[i].u;
-    E[i] = static_cast<size_t>(B) * p->stages[i].cout * L;
+    E[i] = stage_elems(p, i, B, T);
     emax = std::max(emax, E[i]);
     w.a[i + 1] = alloc(es * E[i]);
   }
   w.st.resize(S);
-  size_t shared_ua = 0, shared_ma = 0, shared_xa[2] = {0, 0};
+  std::vector<size_t> sh_ma(NB, 0), sh_xa0(NB, 0), sh_xa1(NB, 0);
+  size_t sh_ua = 0;
   if (!save) {
-    shared_ua = alloc(es * emax);
-    shared_ma = alloc(es * emax);
-    shared_xa[0] = alloc(es * emax);
-    shared_xa[1] = alloc(es * emax);
+    sh_ua = alloc(es * emax);
+    for (int j = 0; j < NB; ++j) {
+      if (p->cfg.resblock == 1) sh_ma[j] = alloc(es * emax);
+      sh_xa0[j] = alloc(es * emax);
+      sh_xa1[j] = alloc(es * emax);
+    }
   }
-  const size_t u_raw = alloc(4 * emax);
   for (int i = 0; i < S; ++i) {
     StageWs& s = w.st[i];
-    s.u_raw = u_raw;
-    s.ua = save ? alloc(es * E[i]) : shared_ua;
+    s.ua = save ? alloc(es * E[i]) : sh_ua;
     s.ma.assign(NB, std::vector<size_t>(npairs, 0));
     s.xa.assign(NB, std::vector<size_t>(npairs, 0));
     for (int j = 0; j < NB; ++j)
       for (int q = 0; q < npairs; ++q) {
-        if (p->cfg.resblock == 1) s.ma[j][q] = save ? alloc(es * E[i]) : shared_ma;
-        if (q < npairs - 1) s.xa[j][q] = save ? alloc(es * E[i]) : shared_xa[q & 1];
+        if (p->cfg.resblock == 1) s.ma[j][q] = save ? alloc(es * E[i]) : sh_ma[j];
+        if (q < npairs - 1) s.xa[j][q] = save ? alloc(es * E[i]) : ((q & 1) ? sh_xa1[j] : sh_xa0[j]);
       }
   }
-  for (int i = 0; i < 2; ++i) { w.xr[i] = alloc(4 * emax); w.sum[i] = alloc(4 * emax); }
+  w.sum[0] = alloc(4 * emax);
+  w.sum[1] = alloc(4 * emax);
   if (save) {
-    // backward scratch: the fp32 forward scratch (u_raw, xr, sum) is dead by then and is reused
-    w.Gr[0] = w.xr[0]; w.Gr[1] = w.xr[1]; w.bsum[0] = w.sum[0]; w.bsum[1] = w.sum[1];
-    w.Gi_r[0] = u_raw; w.Gi_r[1] = alloc(4 * emax);
-    w.Gt[0] = alloc(es * emax); w.Gt[1] = alloc(es * emax);
-    w.dm = alloc(es * emax); w.du = alloc(es * emax);
-    w.Gi_t[0] = alloc(es * emax); w.Gi_t[1] = alloc(es * emax);
+    w.Gi[0] = alloc(es * emax);
+    w.Gi[1] = alloc(es * emax);
+    w.Gt.assign(NB, std::vector<size_t>(npairs, 0));
+    w.dm.assign(NB, std::vector<size_t>(npairs, 0));
+    for (int j = 0; j < NB; ++j)
+      for (int q = 0; q < npairs; ++q) {
+        if (q > 0) w.Gt[j][q] = alloc(es * emax);
+        if (p->cfg.resblock == 1) w.dm[j][q] = alloc(es * emax);
+      }
+    w.duz = alloc(es * zmax);
     w.d0 = alloc(es * B * C0 * T);
     w.dxb = alloc(4 * static_cast<size_t>(B) * p->cfg.initial_channel * T);
   }
@@ -539,73 +582,93 @@ namespace {
 struct Ctx {
   vcd_plan* p;
   int mode, B;
-  cudaStream_t stream;
+  cudaStream_t main;
   char* ws;
+  bool serial;  // profiling: everything on the caller's stream so per-launch event times are isolated
+
+  // stream j of the branch set (0 = caller's stream) / weight-gradient side streams
+  cudaStream_t branch(int j) const { return (serial || j == 0) ? main : p->aux[j - 1]; }
+  cudaStream_t side(int i) const { return serial ? main : p->aux[VCD_MAX_KERNELS - 1 + (i & 3)]; }
+  cudaEvent_t record(cudaStream_t s) const {
+    cudaEvent_t e = p->events[p->next_event];
+    p->next_event = (p->next_event + 1) % vcd_plan::kMaxEvents;
+    cudaEventRecord(e, s);
+    return e;
+  }
+  void wait(cudaStream_t s, cudaEvent_t e) const { cudaStreamWaitEvent(s, e, 0); }
+  void order(cudaStream_t from, cudaStream_t to) const {
+    if (from != to) wait(to, record(from));
+  }
 };
 
 template <typename T>
-int launch_gconv_simt(const Ctx& c, const void* in, const float* w, const ConvGeo& g, const Epilogue& e,
-                      int Lin, int Lq, int Lout, double flops) {
-  ProfScope ps__(PC_FFMA_CONV, flops, 0, c.stream);
+int launch_gconv_simt(const Ctx& c, cudaStream_t st, const void* in, const float* w, const ConvGeo& g, const Epilogue& e,
+                      int Lin, int Lq, int Lout, double flops, const char* tag) {
+  ProfScope ps__(PC_FFMA_CONV, flops, 0, st, tag);
   if (Lq <= 128) {
     dim3 grid((Lq + 127) / 128, g.N / 8, c.B);
-    gconv_simt_kernel<T, 1><<<grid, 128, 0, c.stream>>>(static_cast<const T*>(in), w, g, e, Lin, Lq, Lout);
+    gconv_simt_kernel<T, 1><<<grid, 128, 0, st>>>(static_cast<const T*>(in), w, g, e, Lin, Lq, Lout);
   } else {
     dim3 grid((Lq + 255) / 256, g.N / 8, c.B);
-    gconv_simt_kernel<T, 2><<<grid, 128, 0, c.stream>>>(static_cast<const T*>(in), w, g, e, Lin, Lq, Lout);
+    gconv_simt_kernel<T, 2><<<grid, 128, 0, st>>>(static_cast<const T*>(in), w, g, e, Lin, Lq, Lout);
   }
   LAUNCH_CHECK("gconv_simt_kernel");
   return 0;
 }
 
-// One convolution (forward or data-gradient direction) of layer L.
-int run_conv(const Ctx& c, const Layer& L, bool dgrad, const void* in, int Lin, int Lq, int Lout, Epilogue e) {
-  const ConvGeo& g = dgrad ? L.dgr : L.fwd;
-  // algorithmic FLOPs: 2*Cin*Cout*k per forward-input position (ConvT) / output position (Conv)
-  const int lpos = L.kind == LK_CONVT ? (dgrad ? Lout : Lin) : Lout;
-  const double flops = 2.0 * L.cin * L.cout * L.k * static_cast<double>(c.B) * lpos;
-  if (c.mode == VCD_MODE_BF16 && (dgrad ? L.tc_ok_dgr : L.tc_ok_fwd)) {
-    ProfScope ps__(PC_TC_CONV, flops, 0, c.stream);
-    return tc_run_conv(c.p, L, dgrad, in, c.B, Lin, Lq, Lout, e, c.stream, g_launches, g_err, sizeof(g_err));
-  }
-  const float* w = c.p->d_f32 + (dgrad ? L.f32_dgr : L.f32_fwd);
-  if (c.mode == VCD_MODE_FP32) return launch_gconv_simt<float>(c, in, w, g, e, Lin, Lq, Lout, flops);
-  return launch_gconv_simt<bf16>(c, in, w, g, e, Lin, Lq, Lout, flops);
+// Algorithmic FLOPs of one pass over layer L: 2*Cin*Cout*k per forward-input position
+// (ConvTranspose1d) or per output position (Conv1d).
+double layer_flops(const Layer& L, int B, int Lfwd_in) {
+  return 2.0 * L.cin * L.cout * L.k * static_cast<double>(B) * Lfwd_in;
 }
 
-// Weight gradient (+ bias gradient) of layer L: in = layer input, dout = gradient w.r.t. the layer output.
-int run_wgrad(const Ctx& c, const Layer& L, const void* in, const void* dout, int Lin, int Lq, int Lout) {
-  const ConvGeo& g = L.fwd;
+// One convolution (forward or data-gradient direction) of layer L on stream st.
+int run_conv(const Ctx& c, cudaStream_t st, const Layer& L, bool dgrad, const void* in, int Lin, int Lq, int Lout,
+             Epilogue e, double flops) {
+  const ConvGeo& g = dgrad ? L.dgr : L.fwd;
+  if (c.mode == VCD_MODE_BF16 && (dgrad ? L.tc_ok_dgr : L.tc_ok_fwd)) {
+    ProfScope ps__(PC_TC_CONV, flops, 0, st, (L.name + (dgrad ? ":dgrad" : ":fwd")).c_str());
+    return tc_run_conv(c.p, L, dgrad, in, c.B, Lin, Lq, Lout, e, st, g_launches, g_err, sizeof(g_err));
+  }
+  const float* w = c.p->d_f32 + (dgrad ? L.f32_dgr : L.f32_fwd);
+  const std::string tag = L.name + (dgrad ? ":dgrad" : ":fwd");
+  if (c.mode == VCD_MODE_FP32) return launch_gconv_simt<float>(c, st, in, w, g, e, Lin, Lq, Lout, flops, tag.c_str());
+  return launch_gconv_simt<bf16>(c, st, in, w, g, e, Lin, Lq, Lout, flops, tag.c_str());
+}
+
+// Weight gradient (+ bias gradient) of layer L: in = layer input (length Lin), dout = gradient w.r.t. the layer
+// output in the layer's wgr view (length Ld; for ConvTranspose1d the phase-packed tensor).
+int run_wgrad(const Ctx& c, cudaStream_t st, const Layer& L, const void* in, const void* dout, int Lin, int Ld, double flops) {
+  const ConvGeo& g = L.wgr;
   float* dwp = c.p->d_gscratch + L.dwp;
-  const double flops = 2.0 * L.cin * L.cout * L.k * static_cast<double>(c.B) * (L.kind == LK_CONVT ? Lin : Lout);
   if (c.mode == VCD_MODE_BF16 && L.tc_ok_wgr) {
-    ProfScope ps__(PC_TC_WGRAD, flops, 0, c.stream);
-    TRY(tc_run_wgrad(c.p, L, in, dout, dwp, c.B, Lin, Lq, Lout, c.stream, g_launches, g_err, sizeof(g_err)));
+    ProfScope ps__(PC_TC_WGRAD, flops, 0, st, (L.name + ":wgrad").c_str());
+    TRY(tc_run_wgrad(c.p, L, in, dout, dwp, c.B, Lin, Ld, st, g_launches, g_err, sizeof(g_err)));
   } else {
-    const long long total = 1LL * c.B * Lq;
+    const long long total = 1LL * c.B * Ld;
     const int blocks_x = g.taps * (g.K / 8) * (g.N / 8);
     long long splits = std::max<long long>(1, std::min<long long>((total + 2047) / 2048,
                                                                     std::max(1, 4 * c.p->num_sms * 8 / blocks_x)));
     const int rows_per_split = static_cast<int>((total + splits - 1) / splits);
     splits = (total + rows_per_split - 1) / rows_per_split;
     dim3 grid(blocks_x, static_cast<unsigned>(splits));
-    ProfScope ps__(PC_FFMA_WGRAD, flops, 0, c.stream);
+    ProfScope ps__(PC_FFMA_WGRAD, flops, 0, st, (L.name + ":wgrad").c_str());
     if (c.mode == VCD_MODE_FP32)
-      gconv_wgrad_simt_kernel<float><<<grid, 256, 0, c.stream>>>(static_cast<const float*>(in),
-          static_cast<const float*>(dout), dwp, g, c.B, Lin, Lq, Lout, rows_per_split);
+      gconv_wgrad_simt_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(in),
+          static_cast<const float*>(dout), dwp, g, c.B, Lin, Ld, Ld, rows_per_split);
     else
-      gconv_wgrad_simt_kernel<bf16><<<grid, 256, 0, c.stream>>>(static_cast<const bf16*>(in),
-          static_cast<const bf16*>(dout), dwp, g, c.B, Lin, Lq, Lout, rows_per_split);
+      gconv_wgrad_simt_kernel<bf16><<<grid, 256, 0, st>>>(static_cast<const bf16*>(in),
+          static_cast<const bf16*>(dout), dwp, g, c.B, Lin, Ld, Ld, rows_per_split);
     LAUNCH_CHECK("gconv_wgrad_simt_kernel");
   }
   if (L.dbias >= 0) {
-    const int splits = std::max(1, std::min(64, Lout / 2048));
-    dim3 grid(L.cout / 8, c.B, splits);
-    ProfScope ps__(PC_MISC, 0, esize(c.mode) * static_cast<double>(c.B) * L.cout * Lout, c.stream);
+    const int splits = std::max(1, std::min(64, Ld / 2048));
+    dim3 grid(g.N / 8, c.B, splits);
+    ProfScope ps__(PC_MISC, 0, esize(c.mode) * static_cast<double>(c.B) * g.N * Ld, st);
     if (c.mode == VCD_MODE_FP32)
-      colsum_kernel<float><<<grid, 256, 0, c.stream>>>(static_cast<const float*>(dout), c.p->d_gscratch + L.dbias, L.cout, Lout, 0);
+      colsum_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(dout), c.p->d_gscratch + L.dbias, g.N, Ld, 0, L.cout);
     else
-      colsum_kernel<bf16><<<grid, 256, 0, c.stream>>>(static_cast<const bf16*>(dout), c.p->d_gscratch + L.dbias, L.cout, Lout, 0);
+      colsum_kernel<bf16><<<grid, 256, 0, st>>>(static_cast<const bf16*>(dout), c.p->d_gscratch + L.dbias, g.N, Ld, 0, L.cout);
     LAUNCH_CHECK("colsum_kernel");
   }
   return 0;
@@ -613,7 +676,7 @@ int run_wgrad(const Ctx& c, const Layer& L, const void* in, const void* dout, in
 
 Epilogue epi() {
   Epilogue e{};
-  e.mask_slope = 1.f; e.scale = 1.f; e.tscale = 1.f; e.act_slope = 1.f;
+  e.mask_slope = 1.f; e.scale = 1.f; e.res_inv = 1.f; e.tscale = 1.f; e.act_slope = 1.f;
   return e;
 }
 
@@ -628,6 +691,10 @@ int check_common(vcd_plan* p, int mode, int B, int T, void* ws, size_t ws_bytes,
   return 0;
 }
 
+constexpr float kSlope = 0.1f;          // LRELU_SLOPE, vits/model/modules.py:16
+constexpr float kInvSlope = 10.f;       // exact inverse used to recover the residual stream from lrelu(x)
+constexpr float kFinalSlope = 0.01f;    // F.leaky_relu default before conv_post (upstream Generator)
+
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------------
@@ -641,8 +708,8 @@ extern "C" int vcd_forward(vcd_plan* p, int mode, const float* x, int64_t xs_b, 
   if (!x || !y) return fail("vcd_forward: null x or y");
   if (gvec && !p->cfg.gin_channels) return fail("vcd_forward: g given but the plan has gin_channels = 0");
   const WsLayout w = make_layout(p, mode, B, T, save);
-  Ctx c{p, mode, B, static_cast<cudaStream_t>(stream_), static_cast<char*>(ws)};
-  cudaStream_t stream = c.stream;
+  Ctx c{p, mode, B, static_cast<cudaStream_t>(stream_), static_cast<char*>(ws), g_prof_on};
+  cudaStream_t stream = c.main;
   const bool f32 = mode == VCD_MODE_FP32;
   const int S = static_cast<int>(p->stages.size()), NB = p->cfg.num_kernels;
   const int npairs = p->cfg.resblock == 1 ? 3 : 2;
@@ -651,12 +718,14 @@ extern "C" int vcd_forward(vcd_plan* p, int mode, const float* x, int64_t xs_b, 
   auto PF = [&](size_t off) { return reinterpret_cast<float*>(c.ws + off); };
 
   {  // latent -> blocked layout
+    ProfScope ps__(PC_MISC, 0, 0, stream);
     dim3 grid((T + 127) / 128, Cin0 / 8, B);
     if (f32) ncl_to_blocked_kernel<float><<<grid, 128, 0, stream>>>(x, xs_b, xs_c, xs_t, static_cast<float*>(P(w.xin)), Cin0, T);
     else ncl_to_blocked_kernel<bf16><<<grid, 128, 0, stream>>>(x, xs_b, xs_c, xs_t, static_cast<bf16*>(P(w.xin)), Cin0, T);
     LAUNCH_CHECK("ncl_to_blocked_kernel");
   }
   if (gvec) {
+    ProfScope ps__(PC_MISC, 0, 0, stream);
     dim3 grid((C0 + 127) / 128, B);
     cond_fwd_kernel<<<grid, 128, 0, stream>>>(p->h_params[p->p_cond_w], p->h_params[p->p_cond_b], gvec, PF(w.cb), C0,
                                               p->cfg.gin_channels);
@@ -668,26 +737,28 @@ extern "C" int vcd_forward(vcd_plan* p, int mode, const float* x, int64_t xs_b, 
     e.bias = p->h_params[L.p_b];
     e.bias2 = gvec ? PF(w.cb) : nullptr;
     e.out_t = P(w.a[0]);
-    e.act_slope = 0.1f;
-    TRY(run_conv(c, L, false, P(w.xin), T, T, T, e));
+    e.act_slope = kSlope;
+    TRY(run_conv(c, stream, L, false, P(w.xin), T, T, T, e, layer_flops(L, B, T)));
   }
   int Lcur = T;
   for (int i = 0; i < S; ++i) {
     const StageDesc& sd = p->stages[i];
     const StageWs& sw = w.st[i];
     const Layer& U = p->layers[sd.up_layer];
-    {
+    {  // x = ups[i](lrelu(x)) ; stored as ua = lrelu(x, 0.1)
       Epilogue e = epi();
       e.bias = p->h_params[U.p_b];
-      e.out_raw = PF(sw.u_raw);
       e.out_t = P(sw.ua);
-      e.act_slope = 0.1f;
-      TRY(run_conv(c, U, false, P(w.a[i]), Lcur, Lcur + U.fwd.taps - 1, Lcur * sd.u, e));
+      e.act_slope = kSlope;
+      TRY(run_conv(c, stream, U, false, P(w.a[i]), Lcur, Lcur + U.fwd.taps - 1, Lcur * sd.u, e, layer_flops(U, B, Lcur)));
     }
     Lcur *= sd.u;
+    // ResBlock branches run concurrently; the running sum over branches chains their last convolutions
+    for (int j = 1; j < NB; ++j) c.order(stream, c.branch(j));
+    cudaEvent_t prev_last = nullptr;
     for (int j = 0; j < NB; ++j) {
+      cudaStream_t sj = c.branch(j);
       const void* xin_t = P(sw.ua);
-      const float* xres = PF(sw.u_raw);
       for (int q = 0; q < npairs; ++q) {
         const bool last = q == npairs - 1;
         const void* conv_in = xin_t;
@@ -696,33 +767,37 @@ extern "C" int vcd_forward(vcd_plan* p, int mode, const float* x, int64_t xs_b, 
           Epilogue e = epi();
           e.bias = p->h_params[L1.p_b];
           e.out_t = P(sw.ma[j][q]);
-          e.act_slope = 0.1f;
-          TRY(run_conv(c, L1, false, xin_t, Lcur, Lcur, Lcur, e));
+          e.act_slope = kSlope;
+          TRY(run_conv(c, sj, L1, false, xin_t, Lcur, Lcur, Lcur, e, layer_flops(L1, B, Lcur)));
           conv_in = P(sw.ma[j][q]);
         }
         const Layer& L2 = p->layers[sd.convs[j][q].back()];
         Epilogue e = epi();
         e.bias = p->h_params[L2.p_b];
-        e.res = xres;
+        e.res_t = xin_t;  // x recovered from lrelu(x)
+        e.res_inv = kInvSlope;
         if (!last) {
-          e.out_raw = PF(w.xr[q & 1]);
           e.out_t = P(sw.xa[j][q]);
-          e.act_slope = 0.1f;
-          xres = PF(w.xr[q & 1]);
+          e.act_slope = kSlope;
           xin_t = P(sw.xa[j][q]);
         } else {
-          e.res2 = j > 0 ? PF(w.sum[(j - 1) & 1]) : nullptr;
+          if (j > 0) {
+            e.res2 = PF(w.sum[(j - 1) & 1]);
+            if (sj != c.branch(j - 1)) c.wait(sj, prev_last);
+          }
           if (j < NB - 1) {
             e.out_raw = PF(w.sum[j & 1]);
           } else {  // mean over branches + the next leaky_relu, fused
             e.out_t = P(w.a[i + 1]);
             e.tscale = 1.f / NB;
-            e.act_slope = (i == S - 1) ? 0.01f : 0.1f;
+            e.act_slope = (i == S - 1) ? kFinalSlope : kSlope;
           }
         }
-        TRY(run_conv(c, L2, false, conv_in, Lcur, Lcur, Lcur, e));
+        TRY(run_conv(c, sj, L2, false, conv_in, Lcur, Lcur, Lcur, e, layer_flops(L2, B, Lcur)));
+        if (last && !c.serial) prev_last = c.record(sj);
       }
     }
+    if (!c.serial && c.branch(NB - 1) != stream) c.wait(stream, prev_last);
   }
   {  // conv_post + tanh
     const int C = p->stages[S - 1].cout;
@@ -745,9 +820,10 @@ extern "C" int vcd_backward(vcd_plan* p, int mode, const float* dy, const float*
   TRY(check_common(p, mode, B, T, ws, ws_bytes, true));
   if (!dy || !y || !dparams) return fail("vcd_backward: null dy, y or dparams");
   const WsLayout w = make_layout(p, mode, B, T, true);
-  Ctx c{p, mode, B, static_cast<cudaStream_t>(stream_), static_cast<char*>(ws)};
-  cudaStream_t stream = c.stream;
+  Ctx c{p, mode, B, static_cast<cudaStream_t>(stream_), static_cast<char*>(ws), g_prof_on};
+  cudaStream_t stream = c.main;
   const bool f32 = mode == VCD_MODE_FP32;
+  const size_t es = esize(mode);
   const int S = static_cast<int>(p->stages.size()), NB = p->cfg.num_kernels;
   const int npairs = p->cfg.resblock == 1 ? 3 : 2;
   const int C0 = p->cfg.upsample_initial_channel, Cin0 = p->cfg.initial_channel;
@@ -769,43 +845,40 @@ extern "C" int vcd_backward(vcd_plan* p, int mode, const float* dy, const float*
   Ls[0] = T;
   for (int i = 0; i < S; ++i) Ls[i + 1] = Ls[i] * p->stages[i].u;
 
-  auto begin_segment = [&](int seg) -> int {
+  for (int seg = 0; seg <= S; ++seg) {
+    if (!(segment_mask & (1u << seg))) continue;
     const SegmentJobs& sj = p->segments[seg];
     if (sj.scratch_end > sj.scratch_begin)
       CU_TRY(cudaMemsetAsync(p->d_gscratch + sj.scratch_begin, 0, (sj.scratch_end - sj.scratch_begin) * sizeof(float), stream));
-    return 0;
-  };
-  auto end_segment = [&](int seg) -> int {
-    const SegmentJobs& sj = p->segments[seg];
-    if (sj.nblocks) {
-      ProfScope ps__(PC_FOLD, 0, 8.0 * (sj.scratch_end - sj.scratch_begin), stream);
-      wn_unfold_kernel<<<sj.nblocks, 256, 0, stream>>>(sj.d_jobs, sj.njobs, p->d_params, p->d_dparams, p->d_norms, p->d_gscratch);
-      LAUNCH_CHECK("wn_unfold_kernel");
-    }
-    return 0;
-  };
+    int side_rr = 0;
+    bool side_used[4] = {false, false, false, false};
+    // weight-gradient kernels run on side streams: they only need their two operands, never feed the
+    // data-gradient chain, and are joined before the segment's weight-norm backward
+    auto side_after = [&](cudaEvent_t ready) {
+      const int k = side_rr++ & 3;
+      cudaStream_t s = c.side(k);
+      if (!c.serial) { c.wait(s, ready); side_used[k] = true; }
+      return s;
+    };
 
-  for (int seg = 0; seg <= S; ++seg) {
-    if (!(segment_mask & (1u << seg))) continue;
-    TRY(begin_segment(seg));
-    if (seg == 0) {  // conv_post + tanh backward -> G_init of the last stage
+    if (seg == 0) {  // conv_post + tanh backward -> gradient w.r.t. the last stage output
       const int C = p->stages[S - 1].cout, L = Ls[S];
       const int splits = std::max(1, std::min(64, L / 2048));
       dim3 gw(C / 8, B, splits);
       dim3 gd((L + 127) / 128, C / 8, B);
       const float* wpost = p->h_params[p->p_post_w];
       const int slot = (S - 1) & 1;
-      ProfScope ps__(PC_POST, 4.0 * C * 7 * B * L, static_cast<double>(B) * L * (C * (3 * esize(mode) + 4) + 16), stream);
+      ProfScope ps__(PC_POST, 4.0 * C * 7 * B * L, static_cast<double>(B) * L * (C * 3 * es + 16), stream);
       if (f32) {
         conv_post_wgrad_kernel<float><<<gw, 256, 0, stream>>>(dy, y, static_cast<const float*>(P(w.a[S])), p->d_gscratch + p->post_dw, C, L);
         LAUNCH_CHECK("conv_post_wgrad_kernel");
-        conv_post_dgrad_kernel<float><<<gd, 128, 0, stream>>>(dy, y, wpost, static_cast<const float*>(P(w.a[S])), 0.01f, 1.f / NB,
-                                                               PF(w.Gi_r[slot]), static_cast<float*>(P(w.Gi_t[slot])), C, L);
+        conv_post_dgrad_kernel<float><<<gd, 128, 0, stream>>>(dy, y, wpost, static_cast<const float*>(P(w.a[S])), kFinalSlope, 1.f / NB,
+                                                               nullptr, static_cast<float*>(P(w.Gi[slot])), C, L);
       } else {
         conv_post_wgrad_kernel<bf16><<<gw, 256, 0, stream>>>(dy, y, static_cast<const bf16*>(P(w.a[S])), p->d_gscratch + p->post_dw, C, L);
         LAUNCH_CHECK("conv_post_wgrad_kernel");
-        conv_post_dgrad_kernel<bf16><<<gd, 128, 0, stream>>>(dy, y, wpost, static_cast<const bf16*>(P(w.a[S])), 0.01f, 1.f / NB,
-                                                              PF(w.Gi_r[slot]), static_cast<bf16*>(P(w.Gi_t[slot])), C, L);
+        conv_post_dgrad_kernel<bf16><<<gd, 128, 0, stream>>>(dy, y, wpost, static_cast<const bf16*>(P(w.a[S])), kFinalSlope, 1.f / NB,
+                                                              nullptr, static_cast<bf16*>(P(w.Gi[slot])), C, L);
       }
       LAUNCH_CHECK("conv_post_dgrad_kernel");
     }
@@ -813,74 +886,92 @@ extern "C" int vcd_backward(vcd_plan* p, int mode, const float* dy, const float*
       const int i = S - 1 - seg;
       const StageDesc& sd = p->stages[i];
       const StageWs& sw = w.st[i];
-      const int L = Ls[i + 1];
-      const float* Gi_r = PF(w.Gi_r[i & 1]);
-      const void* Gi_t = P(w.Gi_t[i & 1]);
+      const int L = Ls[i + 1], Lprev = Ls[i];
+      const Layer& U = p->layers[sd.up_layer];
+      const int Lz = Lprev + U.fwd.taps - 1;  // rows of the phase-packed gradient
+      const void* Gi = P(w.Gi[i & 1]);
+      // unwritten edge slots of the phase-packed tensor must read as zero
+      CU_TRY(cudaMemsetAsync(P(w.duz), 0, es * static_cast<size_t>(B) * U.wgr.N * Lz, stream));
+      cudaEvent_t ev0 = c.serial ? nullptr : c.record(stream);
+      for (int j = 1; j < NB; ++j) if (!c.serial) c.wait(c.branch(j), ev0);
+      cudaEvent_t prev_final = nullptr;
       for (int j = 0; j < NB; ++j) {
-        const float* Gr_cur = Gi_r;
-        const void* Gt_cur = Gi_t;
-        int pp = 0;
+        cudaStream_t sjs = c.branch(j);
+        const void* Gt_cur = Gi;
+        cudaEvent_t ev_cur = ev0;
         for (int q = npairs - 1; q >= 0; --q) {
           const void* in_first = q == 0 ? P(sw.ua) : P(sw.xa[j][q - 1]);  // input of the pair's first conv
           const void* d_first = Gt_cur;                                   // gradient w.r.t. that conv's output
+          cudaEvent_t ev_first = ev_cur;
           if (p->cfg.resblock == 1) {
             const Layer& L2 = p->layers[sd.convs[j][q][1]];
-            TRY(run_wgrad(c, L2, P(sw.ma[j][q]), Gt_cur, L, L, L));
+            TRY(run_wgrad(c, side_after(ev_cur), L2, P(sw.ma[j][q]), Gt_cur, L, L, layer_flops(L2, B, L)));
             Epilogue e = epi();
             e.mask = P(sw.ma[j][q]);
-            e.mask_slope = 0.1f;
-            e.out_t = P(w.dm);
-            TRY(run_conv(c, L2, true, Gt_cur, L, L, L, e));
-            d_first = P(w.dm);
+            e.mask_slope = kSlope;
+            e.out_t = P(w.dm[j][q]);
+            TRY(run_conv(c, sjs, L2, true, Gt_cur, L, L, L, e, layer_flops(L2, B, L)));
+            d_first = P(w.dm[j][q]);
+            ev_first = c.serial ? nullptr : c.record(sjs);
           }
           const Layer& L1 = p->layers[sd.convs[j][q][0]];
-          TRY(run_wgrad(c, L1, in_first, d_first, L, L, L));
+          TRY(run_wgrad(c, side_after(ev_first), L1, in_first, d_first, L, L, layer_flops(L1, B, L)));
           Epilogue e = epi();
           e.mask = in_first;
-          e.mask_slope = 0.1f;
-          e.res = Gr_cur;
+          e.mask_slope = kSlope;
+          e.res_t = Gt_cur;  // identity path of `x = xt + x`
           if (q > 0) {
-            e.out_raw = PF(w.Gr[pp]);
-            e.out_t = P(w.Gt[pp]);
-            Gr_cur = PF(w.Gr[pp]);
-            Gt_cur = P(w.Gt[pp]);
-            pp ^= 1;
+            e.out_t = P(w.Gt[j][q]);
+            Gt_cur = P(w.Gt[j][q]);
           } else {
-            e.res2 = j > 0 ? PF(w.bsum[(j - 1) & 1]) : nullptr;
-            if (j < NB - 1) e.out_raw = PF(w.bsum[j & 1]);
-            else e.out_t = P(w.du);
+            if (j > 0) {
+              e.res2 = PF(w.sum[(j - 1) & 1]);
+              if (!c.serial && sjs != c.branch(j - 1)) c.wait(sjs, prev_final);
+            }
+            if (j < NB - 1) {
+              e.out_raw = PF(w.sum[j & 1]);
+            } else {  // sum over branches, written phase-packed for the upsample conv's backward GEMMs
+              e.out_t = P(w.duz);
+              e.zu = sd.u; e.zp = U.pad; e.zLq = Lz;
+            }
           }
-          TRY(run_conv(c, L1, true, d_first, L, L, L, e));
+          TRY(run_conv(c, sjs, L1, true, d_first, L, L, L, e, layer_flops(L1, B, L)));
+          if (!c.serial) {
+            if (q > 0) ev_cur = c.record(sjs);
+            else prev_final = c.record(sjs);
+          }
         }
       }
-      // upsample conv: weight/bias gradients and data gradient (fused with lrelu mask and the 1/NB of the
-      // previous stage's branch mean)
-      const Layer& U = p->layers[sd.up_layer];
-      const int Lprev = Ls[i];
-      TRY(run_wgrad(c, U, P(w.a[i]), P(w.du), Lprev, Lprev + U.fwd.taps - 1, L));
+      if (!c.serial && c.branch(NB - 1) != stream) c.wait(stream, prev_final);
+      // upsample conv: weight/bias gradients (side stream) and data gradient, fused with the lrelu mask and the
+      // 1/NB of the previous stage's branch mean
+      cudaEvent_t ev_du = c.serial ? nullptr : c.record(stream);
+      TRY(run_wgrad(c, side_after(ev_du), U, P(w.a[i]), P(w.duz), Lprev, Lz, layer_flops(U, B, Lprev)));
       Epilogue e = epi();
       e.mask = P(w.a[i]);
-      e.mask_slope = 0.1f;
+      e.mask_slope = kSlope;
       if (i > 0) {
         e.scale = 1.f / NB;
-        e.out_raw = PF(w.Gi_r[(i - 1) & 1]);
-        e.out_t = P(w.Gi_t[(i - 1) & 1]);
+        e.out_t = P(w.Gi[(i - 1) & 1]);
       } else {
         e.out_t = P(w.d0);
       }
-      TRY(run_conv(c, U, true, P(w.du), L, Lprev, Lprev, e));
+      TRY(run_conv(c, stream, U, true, P(w.duz), Lz, Lprev, Lprev, e, layer_flops(U, B, Lprev)));
     } else {  // conv_pre + cond
       const Layer& L = p->layers[p->l_pre];
-      TRY(run_wgrad(c, L, P(w.xin), P(w.d0), T, T, T));
+      cudaEvent_t ev0 = c.serial ? nullptr : c.record(stream);
+      TRY(run_wgrad(c, side_after(ev0), L, P(w.xin), P(w.d0), T, T, layer_flops(L, B, T)));
       CU_TRY(cudaMemsetAsync(PF(w.dcb), 0, sizeof(float) * B * C0, stream));
       {
+        ProfScope ps__(PC_MISC, 0, 0, stream);
         const int splits = std::max(1, std::min(64, T / 2048));
         dim3 grid(C0 / 8, B, splits);
-        if (f32) colsum_kernel<float><<<grid, 256, 0, stream>>>(static_cast<const float*>(P(w.d0)), PF(w.dcb), C0, T, 1);
-        else colsum_kernel<bf16><<<grid, 256, 0, stream>>>(static_cast<const bf16*>(P(w.d0)), PF(w.dcb), C0, T, 1);
+        if (f32) colsum_kernel<float><<<grid, 256, 0, stream>>>(static_cast<const float*>(P(w.d0)), PF(w.dcb), C0, T, 1, C0);
+        else colsum_kernel<bf16><<<grid, 256, 0, stream>>>(static_cast<const bf16*>(P(w.d0)), PF(w.dcb), C0, T, 1, C0);
         LAUNCH_CHECK("colsum_kernel");
       }
       {
+        ProfScope ps__(PC_MISC, 0, 0, stream);
         const int G = p->cfg.gin_channels;
         const bool have_g = gvec != nullptr && G > 0;
         long long n = C0;
@@ -899,13 +990,21 @@ extern "C" int vcd_backward(vcd_plan* p, int mode, const float* dy, const float*
       if (dx) {
         Epilogue e = epi();
         e.out_raw = PF(w.dxb);
-        TRY(run_conv(c, L, true, P(w.d0), T, T, T, e));
+        TRY(run_conv(c, stream, L, true, P(w.d0), T, T, T, e, layer_flops(L, B, T)));
+        ProfScope ps__(PC_MISC, 0, 0, stream);
         dim3 grid((T + 127) / 128, Cin0 / 8, B);
         blocked_to_ncl_kernel<<<grid, 128, 0, stream>>>(PF(w.dxb), dx, Cin0, T);
         LAUNCH_CHECK("blocked_to_ncl_kernel");
       }
     }
-    TRY(end_segment(seg));
+    // join the side streams, then the weight-norm backward of this segment's parameters
+    for (int k = 0; k < 4; ++k)
+      if (side_used[k]) c.order(c.side(k), stream);
+    if (sj.nblocks) {
+      ProfScope ps__(PC_FOLD, 0, 8.0 * (sj.scratch_end - sj.scratch_begin), stream);
+      wn_unfold_kernel<<<sj.nblocks, 256, 0, stream>>>(sj.d_jobs, sj.njobs, p->d_params, p->d_dparams, p->d_norms, p->d_gscratch);
+      LAUNCH_CHECK("wn_unfold_kernel");
+    }
   }
   return 0;
 }
