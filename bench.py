@@ -257,12 +257,15 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
         evs = []
+        host = 0.0
         for _ in range(steps):
             if flush_buf is not None:
                 flush_buf.fill_(1)  # evict L2 (256 MB write > 126 MB L2); outside the timed events
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
+            h0 = time.perf_counter()
             fn()
+            host += time.perf_counter() - h0
             b.record()
             evs.append((a, b))
         torch.cuda.synchronize()
@@ -273,6 +276,7 @@ def run_b200(args):
         t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        timed.host_ms = host / steps * 1e3
         return float(t.item()) / steps
 
     sampler = ClockSampler(local)
@@ -280,6 +284,7 @@ def run_b200(args):
         sampler.start()
     lib.vcd_launch_count(1)
     ms = timed(step_device, args.steps, args.warmup)
+    host_ms = timed.host_ms
     launches_total = lib.vcd_launch_count(1)
     clocks = sampler.stop() if rank == 0 else None
     launches_per_step = launches_total / (args.steps + args.warmup)
@@ -356,6 +361,7 @@ def run_b200(args):
                            "random_init_weights": True},
                 "tflops_algorithmic": flops / (ms * 1e-3) / 1e12,
                 "frac_of_bf16_peak_sustained": flops / (ms * 1e-3) / 1e12 / peaks["bf16_sustained"],
+                "host_enqueue_ms_per_step": host_ms,
                 "gpu_launches": round(launches_per_step * args.steps), "gpu_launches_per_step": launches_per_step,
                 "clocks": clocks, "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu_baseline,
                 "kernel_classes": classes}

@@ -2,7 +2,9 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <map>
 #include <string>
+#include <tuple>
 #include <vector>
 
 #include "../../include/vcd.h"
@@ -43,6 +45,18 @@ struct SegmentJobs {
   int njobs = 0, nblocks = 0;
   long long scratch_begin = 0, scratch_end = 0;  // float range of the gradient scratch to zero
   std::vector<int> params;
+};
+
+// Identity of a captured launch sequence (see run_graphed in vcd_api.cu).
+struct GraphKey {
+  int region;          // 0 = forward core, 1 + s = backward segment s
+  int mode, B, T, save, has_g, has_dx;
+  const void* ws;
+  uint64_t params_version;
+  bool operator<(const GraphKey& o) const {
+    return std::tie(region, mode, B, T, save, has_g, has_dx, ws, params_version) <
+           std::tie(o.region, o.mode, o.B, o.T, o.save, o.has_g, o.has_dx, o.ws, o.params_version);
+  }
 };
 
 struct StageDesc {
@@ -87,6 +101,13 @@ struct vcd_plan {
   // auxiliary streams / events for intra-step concurrency (ResBlock branches, weight-gradient kernels)
   static constexpr int kMaxAux = 12, kMaxEvents = 256;
   cudaStream_t aux[kMaxAux] = {};
+  cudaStream_t own = nullptr;              // stands in for the legacy default stream (not capturable)
+  cudaEvent_t hop_in = nullptr, hop_out = nullptr;
   cudaEvent_t events[kMaxEvents] = {};
   int next_event = 0;
+
+  // CUDA graph cache
+  uint64_t params_version = 0;
+  std::map<vcd::GraphKey, cudaGraphExec_t> graphs;
+  std::map<vcd::GraphKey, uint64_t> graph_kernels;
 };

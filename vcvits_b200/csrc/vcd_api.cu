@@ -399,6 +399,9 @@ extern "C" int vcd_plan_create(const vcd_config* cfg, vcd_plan** out_plan) {
     TRY(upload_jobs(uj, &sj.d_jobs));
   }
   for (int i = 0; i < vcd_plan::kMaxAux; ++i) CU_TRY(cudaStreamCreateWithFlags(&p->aux[i], cudaStreamNonBlocking));
+  CU_TRY(cudaStreamCreateWithFlags(&p->own, cudaStreamNonBlocking));
+  CU_TRY(cudaEventCreateWithFlags(&p->hop_in, cudaEventDisableTiming));
+  CU_TRY(cudaEventCreateWithFlags(&p->hop_out, cudaEventDisableTiming));
   for (int i = 0; i < vcd_plan::kMaxEvents; ++i) CU_TRY(cudaEventCreateWithFlags(&p->events[i], cudaEventDisableTiming));
   TRY(tc_plan_init(p));
   *out_plan = p;
@@ -411,6 +414,10 @@ extern "C" void vcd_plan_destroy(vcd_plan* p) {
   cudaFree(p->d_params); cudaFree(p->d_dparams); cudaFree(p->d_norm_jobs);
   cudaFree(p->d_pack_jobs[0]); cudaFree(p->d_pack_jobs[1]);
   for (auto& s : p->segments) cudaFree(s.d_jobs);
+  for (auto& kv : p->graphs) cudaGraphExecDestroy(kv.second);
+  if (p->own) cudaStreamDestroy(p->own);
+  if (p->hop_in) cudaEventDestroy(p->hop_in);
+  if (p->hop_out) cudaEventDestroy(p->hop_out);
   for (int i = 0; i < vcd_plan::kMaxAux; ++i) if (p->aux[i]) cudaStreamDestroy(p->aux[i]);
   for (int i = 0; i < vcd_plan::kMaxEvents; ++i) if (p->events[i]) cudaEventDestroy(p->events[i]);
   delete p;
@@ -559,6 +566,7 @@ extern "C" int vcd_fold_weights(vcd_plan* p, int mode, const float* const* param
   }
   if (changed) {
     std::copy(params, params + np, p->h_params.begin());
+    ++p->params_version;  // bias pointers are baked into captured kernel parameters
     // pageable->device async copy is staged by the runtime before returning, so h_params may change later
     CU_TRY(cudaMemcpyAsync(p->d_params, p->h_params.data(), np * sizeof(float*), cudaMemcpyHostToDevice, stream));
   }
@@ -691,6 +699,70 @@ int check_common(vcd_plan* p, int mode, int B, int T, void* ws, size_t ws_bytes,
   return 0;
 }
 
+// The legacy default stream cannot be captured into a CUDA graph.  When the caller hands us stream 0 the work
+// runs on a plan-owned non-blocking stream instead, ordered after / before the caller's stream with events.
+struct StreamHop {
+  vcd_plan* p;
+  cudaStream_t user, run;
+  bool hop;
+  StreamHop(vcd_plan* plan, void* stream_) : p(plan), user(static_cast<cudaStream_t>(stream_)) {
+    hop = (user == nullptr || user == cudaStreamLegacy || user == cudaStreamPerThread);
+    run = hop ? p->own : user;
+    if (hop) {
+      cudaEventRecord(p->hop_in, user);
+      cudaStreamWaitEvent(run, p->hop_in, 0);
+    }
+  }
+  ~StreamHop() {
+    if (hop) {
+      cudaEventRecord(p->hop_out, run);
+      cudaStreamWaitEvent(user, p->hop_out, 0);
+    }
+  }
+};
+
+// CUDA-graph cache: the launch sequence of a call region (kernels, memsets, the fork/join pattern of the
+// auxiliary streams, the TMA descriptors baked into kernel parameters) only depends on GraphKey, so it is
+// captured once from the SAME enqueue code and replayed afterwards.  Kernels that touch caller-owned tensors
+// (x, g, y, dy, dx, dg) stay outside the captured regions because those addresses may change per call.
+template <class F>
+int run_graphed(vcd_plan* p, const GraphKey& key, cudaStream_t stream, F&& enqueue) {
+  static const int enabled = tc_env_int("VCD_GRAPHS", 1);
+  if (!enabled || g_prof_on) return enqueue();
+  auto it = p->graphs.find(key);
+  if (it != p->graphs.end()) {
+    CU_TRY(cudaGraphLaunch(it->second, stream));
+    g_launches.fetch_add(p->graph_kernels[key], std::memory_order_relaxed);
+    return 0;
+  }
+  const uint64_t before = g_launches.load();
+  CU_TRY(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+  const int rc = enqueue();
+  cudaGraph_t graph = nullptr;
+  const cudaError_t ce = cudaStreamEndCapture(stream, &graph);
+  if (rc != 0 || ce != cudaSuccess || !graph) {
+    if (graph) cudaGraphDestroy(graph);
+    if (rc != 0) return rc;
+    return fail("CUDA graph capture failed: %s", cudaGetErrorString(ce));
+  }
+  cudaGraphExec_t exec = nullptr;
+  const cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (ie != cudaSuccess) return fail("cudaGraphInstantiate failed: %s", cudaGetErrorString(ie));
+  if (p->graphs.size() >= 64) {  // bounded cache: drop everything (shapes / workspaces keep changing)
+    for (auto& kv : p->graphs) cudaGraphExecDestroy(kv.second);
+  if (p->own) cudaStreamDestroy(p->own);
+  if (p->hop_in) cudaEventDestroy(p->hop_in);
+  if (p->hop_out) cudaEventDestroy(p->hop_out);
+    p->graphs.clear();
+    p->graph_kernels.clear();
+  }
+  p->graphs[key] = exec;
+  p->graph_kernels[key] = g_launches.load() - before;
+  CU_TRY(cudaGraphLaunch(exec, stream));
+  return 0;
+}
+
 constexpr float kSlope = 0.1f;          // LRELU_SLOPE, vits/model/modules.py:16
 constexpr float kInvSlope = 10.f;       // exact inverse used to recover the residual stream from lrelu(x)
 constexpr float kFinalSlope = 0.01f;    // F.leaky_relu default before conv_post (upstream Generator)
@@ -708,7 +780,8 @@ extern "C" int vcd_forward(vcd_plan* p, int mode, const float* x, int64_t xs_b, 
   if (!x || !y) return fail("vcd_forward: null x or y");
   if (gvec && !p->cfg.gin_channels) return fail("vcd_forward: g given but the plan has gin_channels = 0");
   const WsLayout w = make_layout(p, mode, B, T, save);
-  Ctx c{p, mode, B, static_cast<cudaStream_t>(stream_), static_cast<char*>(ws), g_prof_on};
+  StreamHop hop(p, stream_);
+  Ctx c{p, mode, B, hop.run, static_cast<char*>(ws), g_prof_on || tc_env_int("VCD_SERIAL", 0) != 0};
   cudaStream_t stream = c.main;
   const bool f32 = mode == VCD_MODE_FP32;
   const int S = static_cast<int>(p->stages.size()), NB = p->cfg.num_kernels;
@@ -731,6 +804,8 @@ extern "C" int vcd_forward(vcd_plan* p, int mode, const float* x, int64_t xs_b, 
                                               p->cfg.gin_channels);
     LAUNCH_CHECK("cond_fwd_kernel");
   }
+  int Lcur = T;
+  auto core = [&]() -> int {
   {  // conv_pre (+ cond) -> a[0] = lrelu(., 0.1)
     const Layer& L = p->layers[p->l_pre];
     Epilogue e = epi();
@@ -740,7 +815,6 @@ extern "C" int vcd_forward(vcd_plan* p, int mode, const float* x, int64_t xs_b, 
     e.act_slope = kSlope;
     TRY(run_conv(c, stream, L, false, P(w.xin), T, T, T, e, layer_flops(L, B, T)));
   }
-  int Lcur = T;
   for (int i = 0; i < S; ++i) {
     const StageDesc& sd = p->stages[i];
     const StageWs& sw = w.st[i];
@@ -799,6 +873,10 @@ extern "C" int vcd_forward(vcd_plan* p, int mode, const float* x, int64_t xs_b, 
     }
     if (!c.serial && c.branch(NB - 1) != stream) c.wait(stream, prev_last);
   }
+  return 0;
+  };
+  TRY(run_graphed(p, GraphKey{0, mode, B, T, save ? 1 : 0, gvec ? 1 : 0, 0, ws, p->params_version}, stream, core));
+  Lcur = T * p->hop;  // `core` is skipped on a graph replay: do not rely on its side effects
   {  // conv_post + tanh
     const int C = p->stages[S - 1].cout;
     dim3 grid((Lcur + 255) / 256, B);
@@ -820,7 +898,8 @@ extern "C" int vcd_backward(vcd_plan* p, int mode, const float* dy, const float*
   TRY(check_common(p, mode, B, T, ws, ws_bytes, true));
   if (!dy || !y || !dparams) return fail("vcd_backward: null dy, y or dparams");
   const WsLayout w = make_layout(p, mode, B, T, true);
-  Ctx c{p, mode, B, static_cast<cudaStream_t>(stream_), static_cast<char*>(ws), g_prof_on};
+  StreamHop hop(p, stream_);
+  Ctx c{p, mode, B, hop.run, static_cast<char*>(ws), g_prof_on || tc_env_int("VCD_SERIAL", 0) != 0};
   cudaStream_t stream = c.main;
   const bool f32 = mode == VCD_MODE_FP32;
   const size_t es = esize(mode);
@@ -850,17 +929,6 @@ extern "C" int vcd_backward(vcd_plan* p, int mode, const float* dy, const float*
     const SegmentJobs& sj = p->segments[seg];
     if (sj.scratch_end > sj.scratch_begin)
       CU_TRY(cudaMemsetAsync(p->d_gscratch + sj.scratch_begin, 0, (sj.scratch_end - sj.scratch_begin) * sizeof(float), stream));
-    int side_rr = 0;
-    bool side_used[4] = {false, false, false, false};
-    // weight-gradient kernels run on side streams: they only need their two operands, never feed the
-    // data-gradient chain, and are joined before the segment's weight-norm backward
-    auto side_after = [&](cudaEvent_t ready) {
-      const int k = side_rr++ & 3;
-      cudaStream_t s = c.side(k);
-      if (!c.serial) { c.wait(s, ready); side_used[k] = true; }
-      return s;
-    };
-
     if (seg == 0) {  // conv_post + tanh backward -> gradient w.r.t. the last stage output
       const int C = p->stages[S - 1].cout, L = Ls[S];
       const int splits = std::max(1, std::min(64, L / 2048));
@@ -882,6 +950,17 @@ extern "C" int vcd_backward(vcd_plan* p, int mode, const float* dy, const float*
       }
       LAUNCH_CHECK("conv_post_dgrad_kernel");
     }
+    auto core = [&]() -> int {
+    int side_rr = 0;
+    bool side_used[4] = {false, false, false, false};
+    // weight-gradient kernels run on side streams: they only need their two operands, never feed the
+    // data-gradient chain, and are joined before the segment's weight-norm backward
+    auto side_after = [&](cudaEvent_t ready) {
+      const int k = side_rr++ & 3;
+      cudaStream_t s = c.side(k);
+      if (!c.serial) { c.wait(s, ready); side_used[k] = true; }
+      return s;
+    };
     if (seg < S) {
       const int i = S - 1 - seg;
       const StageDesc& sd = p->stages[i];
@@ -957,7 +1036,7 @@ extern "C" int vcd_backward(vcd_plan* p, int mode, const float* dy, const float*
         e.out_t = P(w.d0);
       }
       TRY(run_conv(c, stream, U, true, P(w.duz), Lz, Lprev, Lprev, e, layer_flops(U, B, Lprev)));
-    } else {  // conv_pre + cond
+    } else {  // conv_pre: weight gradient, per-batch column sums (bias / cond gradients), data gradient
       const Layer& L = p->layers[p->l_pre];
       cudaEvent_t ev0 = c.serial ? nullptr : c.record(stream);
       TRY(run_wgrad(c, side_after(ev0), L, P(w.xin), P(w.d0), T, T, layer_flops(L, B, T)));
@@ -970,6 +1049,25 @@ extern "C" int vcd_backward(vcd_plan* p, int mode, const float* dy, const float*
         else colsum_kernel<bf16><<<grid, 256, 0, stream>>>(static_cast<const bf16*>(P(w.d0)), PF(w.dcb), C0, T, 1, C0);
         LAUNCH_CHECK("colsum_kernel");
       }
+      if (dx) {
+        Epilogue e = epi();
+        e.out_raw = PF(w.dxb);
+        TRY(run_conv(c, stream, L, true, P(w.d0), T, T, T, e, layer_flops(L, B, T)));
+      }
+    }
+    // join the side streams, then the weight-norm backward of this segment's parameters
+    for (int k = 0; k < 4; ++k)
+      if (side_used[k]) c.order(c.side(k), stream);
+    if (sj.nblocks) {
+      ProfScope ps__(PC_FOLD, 0, 8.0 * (sj.scratch_end - sj.scratch_begin), stream);
+      wn_unfold_kernel<<<sj.nblocks, 256, 0, stream>>>(sj.d_jobs, sj.njobs, p->d_params, p->d_dparams, p->d_norms, p->d_gscratch);
+      LAUNCH_CHECK("wn_unfold_kernel");
+    }
+    return 0;
+    };
+    TRY(run_graphed(p, GraphKey{1 + seg, mode, B, T, 1, gvec ? 1 : 0, dx ? 1 : 0, ws, p->params_version}, stream, core));
+    if (seg == S) {  // kernels that touch caller-owned tensors: cond / conv_pre.bias gradients, dg, dx
+      const Layer& L = p->layers[p->l_pre];
       {
         ProfScope ps__(PC_MISC, 0, 0, stream);
         const int G = p->cfg.gin_channels;
@@ -988,22 +1086,11 @@ extern "C" int vcd_backward(vcd_plan* p, int mode, const float* dy, const float*
         }
       }
       if (dx) {
-        Epilogue e = epi();
-        e.out_raw = PF(w.dxb);
-        TRY(run_conv(c, stream, L, true, P(w.d0), T, T, T, e, layer_flops(L, B, T)));
         ProfScope ps__(PC_MISC, 0, 0, stream);
         dim3 grid((T + 127) / 128, Cin0 / 8, B);
         blocked_to_ncl_kernel<<<grid, 128, 0, stream>>>(PF(w.dxb), dx, Cin0, T);
         LAUNCH_CHECK("blocked_to_ncl_kernel");
       }
-    }
-    // join the side streams, then the weight-norm backward of this segment's parameters
-    for (int k = 0; k < 4; ++k)
-      if (side_used[k]) c.order(c.side(k), stream);
-    if (sj.nblocks) {
-      ProfScope ps__(PC_FOLD, 0, 8.0 * (sj.scratch_end - sj.scratch_begin), stream);
-      wn_unfold_kernel<<<sj.nblocks, 256, 0, stream>>>(sj.d_jobs, sj.njobs, p->d_params, p->d_dparams, p->d_norms, p->d_gscratch);
-      LAUNCH_CHECK("wn_unfold_kernel");
     }
   }
   return 0;

@@ -100,7 +100,7 @@ class _DecoderFunction(torch.autograd.Function):
         if g is not None:
             gf = g.reshape(B, -1).float().contiguous()
         ws_bytes = lib.vcd_workspace_bytes(plan, mode, B, T, 1 if need_grad else 0)
-        ws = module._workspace(ws_bytes, x.device, cache=not need_grad)
+        ws = module._take_workspace(ws_bytes, x.device) if need_grad else module._workspace(ws_bytes, x.device, cache=True)
         y = torch.empty((B, 1, T * module.hop), dtype=torch.float32, device=x.device)
         _lib.check(lib.vcd_forward(plan, mode, xf.data_ptr(), xf.stride(0), xf.stride(1), xf.stride(2),
                                    gf.data_ptr() if gf is not None else None, y.data_ptr(), ws.data_ptr(),
@@ -120,6 +120,9 @@ class _DecoderFunction(torch.autograd.Function):
     def backward(ctx, dy: torch.Tensor):
         lib = _lib.load()
         module: Generator = ctx.module
+        if ctx.ws is None:
+            raise RuntimeError("vcvits_b200.Generator: backward through the same forward twice is not supported "
+                               "(the activation workspace is recycled after the first backward)")
         y, gf = ctx.saved_tensors
         if not ctx.has_g:
             gf = None
@@ -151,6 +154,7 @@ class _DecoderFunction(torch.autograd.Function):
                                                           group=group, async_op=True))
         for wk in works:
             wk.wait()
+        module._give_workspace(ctx.ws)
         ctx.ws = None
         grads = [v if p.requires_grad else None for v, p in zip(views, module._ordered_params())]
         gx = dx.to(ctx.x_dtype) if dx is not None else None
@@ -222,6 +226,7 @@ class Generator(nn.Module):
         self._plans = {}
         self._fold_key = None
         self._ws_cache = {}
+        self._ws_pool = {}
         self._grad_sync_group = None
         self._names: Optional[List[str]] = None
 
@@ -355,10 +360,24 @@ class Generator(nn.Module):
             self._ws_cache = {device: ws}
         return ws
 
+    def _take_workspace(self, nbytes: int, device: torch.device) -> torch.Tensor:
+        """Training workspaces are pooled so that steady-state steps see the SAME device address (the library
+        replays CUDA graphs keyed on it).  A workspace is out of the pool between forward and backward."""
+        pool = self._ws_pool.setdefault((device, nbytes), [])
+        if pool:
+            return pool.pop()
+        return torch.empty(nbytes, dtype=torch.uint8, device=device)
+
+    def _give_workspace(self, ws: torch.Tensor) -> None:
+        pool = self._ws_pool.setdefault((ws.device, ws.numel()), [])
+        if len(pool) < 4:
+            pool.append(ws)
+
     def _apply(self, fn, *args, **kwargs):
         out = super()._apply(fn, *args, **kwargs)
         self._fold_key = None
         self._ws_cache = {}
+        self._ws_pool = {}
         return out
 
     # ------------------------------------------------------------------ forward
@@ -415,6 +434,7 @@ class Generator(nn.Module):
         state = dict(self.__dict__)
         state["_plans"] = {}        # library handles are per process / per device; rebuilt lazily
         state["_ws_cache"] = {}
+        state["_ws_pool"] = {}
         state["_fold_key"] = None
         state["_grad_sync_group"] = None
         return state
