@@ -136,6 +136,9 @@ const char* vcd_profile_class_name(int class_id);
 int vcd_profile_read(int reset, double* ms, uint64_t* launches, double* flops, double* bytes);
 int vcd_profile_dump(const char* csv_path); /* one line per recorded launch: class, layer tag, ms, GFLOP */
 
+/* Debug only: 64 in-kernel %globaltimer stamps of the kernel selected with the VCD_KTRACE environment variable. */
+int vcd_debug_read_trace(vcd_plan* plan, unsigned long long* out64);
+
 /* Per-layer timing / debugging: name of the arithmetic path ("simt-fp32", "tcgen05-bf16", ...) used by
  * layer `index` of the forward schedule in `mode`; NULL past the end. */
 const char* vcd_layer_path(const vcd_plan* plan, int mode, int index);

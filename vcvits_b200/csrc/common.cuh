@@ -91,9 +91,26 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
+// Every (batch item, channel group) row array carries kPadL zero rows before row 0 and kPadR zero rows after
+// row L-1.  The pads ARE the convolution's zero padding: a tile with its dilation halo is then one contiguous
+// run of 16-byte rows per channel group, fetched with a single 1-D bulk copy (cp.async.bulk) -- no per-row TMA
+// requests, no out-of-bounds handling, and taps never bleed across batch items.  kPadR also absorbs the
+// overhang of the last 128-row tile / time block of an item.  Pads are (re)zeroed by pad_zero_kernel.
+constexpr int kPadL = 32;
+constexpr int kPadR = 160;
+__host__ __device__ __forceinline__ int padded_len(int L) { return L + kPadL + kPadR; }
+
+// Element offset of row t (may be in [-kPadL, L + kPadR)) of channel group cg of batch item b.
+__host__ __device__ __forceinline__ size_t blk_row(int b, int cg, int t, int C, int L) {
+  return ((static_cast<size_t>(b) * (C >> 3) + cg) * padded_len(L) + (t + kPadL)) * 8;
+}
 // Element offset of (b, c, t) in a blocked channels-last tensor with C channels and length L.
 __host__ __device__ __forceinline__ size_t blk_off(int b, int c, int t, int C, int L) {
-  return ((static_cast<size_t>(b) * (C >> 3) + (c >> 3)) * L + t) * 8 + (c & 7);
+  return blk_row(b, c >> 3, t, C, L) + (c & 7);
+}
+// Elements of a blocked tensor (including pads).
+__host__ __device__ __forceinline__ size_t blk_elems(int B, int C, int L) {
+  return static_cast<size_t>(B) * C * padded_len(L);
 }
 
 // ---- generalised convolution geometry (shared by SIMT and tensor-core kernels) ----------------------

@@ -106,8 +106,13 @@ struct vcd_plan {
   cudaEvent_t events[kMaxEvents] = {};
   int next_event = 0;
 
+  unsigned long long* d_trace = nullptr;   // VCD_KTRACE debug buffer
+
   // CUDA graph cache
   uint64_t params_version = 0;
   std::map<vcd::GraphKey, cudaGraphExec_t> graphs;
   std::map<vcd::GraphKey, uint64_t> graph_kernels;
+
+  // device copies of the pad-zeroing job tables, keyed by (mode, B, T, save, phase, backward)
+  std::map<std::tuple<int, int, int, int, int, int>, void*> pad_tables;
 };

@@ -30,7 +30,8 @@ gconv_simt_kernel(const T* __restrict__ in, const float* __restrict__ w, ConvGeo
 #pragma unroll
     for (int n = 0; n < 8; ++n) acc[i][n] = 0.f;
 
-  const T* in_b = in + static_cast<size_t>(b) * kch * Lin * 8;
+  const T* in_b = in + blk_row(b, 0, 0, g.K, Lin);
+  const size_t cg_stride = static_cast<size_t>(padded_len(Lin)) * 8;
   for (int j = 0; j < g.taps; ++j) {
     int row[ROWS];
     bool ok[ROWS];
@@ -49,7 +50,7 @@ gconv_simt_kernel(const T* __restrict__ in, const float* __restrict__ w, ConvGeo
 #pragma unroll
       for (int i = 0; i < ROWS; ++i) {
         if (ok[i]) {
-          load8<T>(in_b + (static_cast<size_t>(cc) * Lin + row[i]) * 8, xin[i]);
+          load8<T>(in_b + cc * cg_stride + static_cast<size_t>(row[i]) * 8, xin[i]);
         } else {
 #pragma unroll
           for (int c = 0; c < 8; ++c) xin[i][c] = 0.f;
@@ -171,7 +172,7 @@ colsum_kernel(const T* __restrict__ d, float* __restrict__ out, int C, int L, in
   float acc[8];
 #pragma unroll
   for (int n = 0; n < 8; ++n) acc[n] = 0.f;
-  const T* base = d + (static_cast<size_t>(b) * (C >> 3) + cg) * L * 8;
+  const T* base = d + blk_row(b, cg, 0, C, L);
   for (int t = t0 + threadIdx.x; t < t1; t += 256) {
     float v[8];
     load8<T>(base + static_cast<size_t>(t) * 8, v);
@@ -192,6 +193,37 @@ colsum_kernel(const T* __restrict__ d, float* __restrict__ out, int C, int L, in
     for (int wv = 0; wv < 8; ++wv) s += red[wv][threadIdx.x];
     atomicAdd(out + (per_batch ? static_cast<size_t>(b) * cmod : 0) + (cg * 8 + threadIdx.x) % cmod, s);
   }
+}
+
+// -------------------------------------------------------------------------------------------------
+// Zero the pad rows of a list of blocked tensors (see kPadL / kPadR in common.cuh).
+// grid = (total row arrays over all tensors), block = 64; one CTA per (tensor, batch item, channel group).
+// -------------------------------------------------------------------------------------------------
+struct PadJob {
+  long long off;      // byte offset of the tensor in the workspace
+  int arrays;         // B * C/8
+  int L;
+  int esize;          // 2 | 4
+  int first_block;
+};
+
+__global__ void __launch_bounds__(64)
+pad_zero_kernel(const PadJob* __restrict__ jobs, int njobs, char* __restrict__ ws) {
+  int lo = 0, hi = njobs - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (jobs[mid].first_block <= static_cast<int>(blockIdx.x)) lo = mid; else hi = mid - 1;
+  }
+  const PadJob jb = jobs[lo];
+  const int arr = blockIdx.x - jb.first_block;
+  const size_t row_bytes = 8 * jb.esize;
+  char* base = ws + jb.off + static_cast<size_t>(arr) * padded_len(jb.L) * row_bytes;
+  const int vec_per_row = static_cast<int>(row_bytes / 16);
+  uint4* left = reinterpret_cast<uint4*>(base);
+  uint4* right = reinterpret_cast<uint4*>(base + static_cast<size_t>(kPadL + jb.L) * row_bytes);
+  const uint4 z = make_uint4(0, 0, 0, 0);
+  for (int i = threadIdx.x; i < kPadL * vec_per_row; i += 64) left[i] = z;
+  for (int i = threadIdx.x; i < kPadR * vec_per_row; i += 64) right[i] = z;
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -283,7 +315,7 @@ conv_post_fwd_kernel(const T* __restrict__ a, const float* __restrict__ w, float
   if (t >= L) return;
   float acc = 0.f;
   for (int cg = 0; cg < (C >> 3); ++cg) {
-    const T* base = a + (static_cast<size_t>(b) * (C >> 3) + cg) * L * 8;
+    const T* base = a + blk_row(b, cg, 0, C, L);
 #pragma unroll
     for (int j = 0; j < 7; ++j) {
       const int r = t + j - 3;
@@ -348,7 +380,7 @@ conv_post_wgrad_kernel(const float* __restrict__ dy, const float* __restrict__ y
   for (int c = 0; c < 8; ++c)
 #pragma unroll
     for (int j = 0; j < 7; ++j) acc[c][j] = 0.f;
-  const T* base = a + (static_cast<size_t>(b) * (C >> 3) + cg) * L * 8;
+  const T* base = a + blk_row(b, cg, 0, C, L);
   for (int r = r0 + threadIdx.x; r < r1; r += 256) {
     float v[8];
     load8<T>(base + static_cast<size_t>(r) * 8, v);

@@ -1,6 +1,5 @@
 // Host side of the tcgen05 kernels: layer eligibility, tile configuration, TMA descriptors, launches.
 #pragma once
-#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include <atomic>
@@ -31,7 +30,11 @@ inline bool tc_geo_ok(const ConvGeo& g) {
   if (g.K > 64 && g.K % 64) return false;
   if (!tc_col_tile(g.creal)) return false;
   const int halo = (g.taps - 1) * (g.step < 0 ? -g.step : g.step);
-  if (128 + halo > 256) return false;               // TMA box limit on the row dimension
+  const int left = g.off0 + (g.step < 0 ? (g.taps - 1) * g.step : 0);       // most negative row offset
+  const int right = g.off0 + (g.step > 0 ? (g.taps - 1) * g.step : 0);     // most positive row offset
+  if (-left > kPadL) return false;                  // halo must fit the zero pads of the row-padded layout
+  if (127 + right + 8 > kPadR) return false;
+  (void)halo;
   return true;
 }
 
@@ -44,29 +47,15 @@ inline void tc_layer_eligibility(Layer& L) {
   {
     const ConvGeo& g = L.wgr;
     const int halo = (g.taps - 1) * (g.step < 0 ? -g.step : g.step);
+    const int left = g.off0 + (g.step < 0 ? (g.taps - 1) * g.step : 0);
+    const int right = g.off0 + (g.step > 0 ? (g.taps - 1) * g.step : 0);
     const bool shape_ok = g.is == 1 && g.os == 1 && g.p == 0 && g.creal == g.N && g.N % 16 == 0 &&
-                          (g.N <= 256 || g.N % 256 == 0) && 64 + halo <= 256;
+                          (g.N <= 256 || g.N % 256 == 0) && -left <= kPadL && 127 + right + 8 <= kPadR && halo <= 120;
     const bool k_ok = (g.K % 128 == 0) || (en_m64 && (g.K == 64 || g.K == 32));
     L.tc_ok_wgr = en_wgr && shape_ok && k_ok;
   }
   L.nt_fwd = L.tc_ok_fwd ? tc_col_tile(L.fwd.creal) : 8;
   L.nt_dgr = L.tc_ok_dgr ? tc_col_tile(L.dgr.creal) : 8;
-}
-
-typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-inline PFN_encodeTiled tc_encode_fn() {
-  static PFN_encodeTiled fn = nullptr;
-  if (!fn) {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
-        qres == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<PFN_encodeTiled>(p);
-  }
-  return fn;
 }
 
 inline int tc_plan_init(vcd_plan* p) {
@@ -77,18 +66,11 @@ inline int tc_plan_init(vcd_plan* p) {
   if (e != cudaSuccess) return 1;
   e = cudaFuncSetAttribute(tc::wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   if (e != cudaSuccess) return 1;
-  return tc_encode_fn() ? 0 : 1;
-}
-
-// bf16 blocked activation [B][C/8][L][8] viewed as a 4-D tensor (8, L, C/8, B); box = (8, rows, kchunks, 1).
-inline bool tc_make_act_map(CUtensorMap* map, const void* base, int B, int C, int L, int box_rows, int box_chunks) {
-  const cuuint64_t dims[4] = {8, static_cast<cuuint64_t>(L), static_cast<cuuint64_t>(C / 8), static_cast<cuuint64_t>(B)};
-  const cuuint64_t strides[3] = {16, static_cast<cuuint64_t>(L) * 16, static_cast<cuuint64_t>(C / 8) * L * 16};
-  const cuuint32_t box[4] = {8, static_cast<cuuint32_t>(box_rows), static_cast<cuuint32_t>(box_chunks), 1};
-  const cuuint32_t estr[4] = {1, 1, 1, 1};
-  return tc_encode_fn()(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+  if (getenv("VCD_KTRACE")) {
+    if (cudaMalloc(&p->d_trace, 64 * sizeof(unsigned long long)) != cudaSuccess) return 1;
+    cudaMemset(p->d_trace, 0, 64 * sizeof(unsigned long long));
+  }
+  return 0;
 }
 
 inline int tc_run_conv(vcd_plan* p, const Layer& L, bool dgrad, const void* in, int B, int Lin, int Lq, int Lout,
@@ -106,18 +88,38 @@ inline int tc_run_conv(vcd_plan* p, const Layer& L, bool dgrad, const void* in, 
   P.minshift = g.step < 0 ? (g.taps - 1) * g.step : 0;
   P.n_tiles_n = g.N / P.BN;
   const int mtiles = (Lq + 127) / 128;
-  int MT = 1;
-  for (int cand : {4, 2}) {
-    if (2 * cand * P.BN > 512 || cand > mtiles) continue;
+  // Rows per CTA tile (MT x 128) from a small cost model (clocks per CTA): the weight stream of a tile is paid once
+  // per MT*128 rows, so larger MT trades CTA-level parallelism for less L2->SM traffic per MMA.
+  //   t_mma  = MT * taps * K/16 * BN/2          (128 x BN x 16 UMMA = BN/2 clk)
+  //   t_load = bytes(A + streamed W) / 27 B/clk  (measured per-SM bulk-copy rate with ~160 KB in flight)
+  //   t_epi  = MT * BN/16 units * 450 clk        (8 epilogue warps)
+  const double w_tile_bytes = 2.0 * g.taps * g.K * P.BN;
+  const bool can_reside = (P.n_tiles_n == 1 && w_tile_bytes <= 100 * 1024);
+  int MT = 1, bufs = 2;
+  double best = 1e30;
+  for (int cand : {1, 2, 4}) {
+    if (cand * P.BN > 512 || cand > mtiles) continue;
+    const int cb = 2 * cand * P.BN <= 512 ? 2 : 1;
     const long long tiles = 1LL * ((mtiles + cand - 1) / cand) * P.n_tiles_n * B;
-    if (tiles >= p->num_sms) { MT = cand; break; }
+    const double waves = static_cast<double>((tiles + p->num_sms - 1) / p->num_sms);
+    const double t_mma = 1.0 * cand * g.taps * (g.K / 16) * (P.BN / 2);
+    const double a_bytes = 2.0 * cand * P.RA * g.K;
+    const double t_load = (a_bytes + (can_reside ? 0.0 : w_tile_bytes)) / 27.0;
+    const double t_epi = cand * (P.BN / 16) * 450.0;
+    const double body = t_mma > t_load ? t_mma : t_load;
+    const double per_tile = cb == 2 ? (body > t_epi ? body : t_epi) : body + t_epi;
+    const double total = waves * per_tile + (cb == 2 ? t_epi : 0.0) + (can_reside ? w_tile_bytes / 27.0 : 0.0);
+    if (total < best) { best = total; MT = cand; bufs = cb; }
   }
   P.MT = MT;
+  P.acc_bufs = bufs;
   P.n_mgroups = (mtiles + MT - 1) / MT;
   P.total_tiles = P.n_mgroups * P.n_tiles_n * B;
   uint32_t cols = 32;
-  while (cols < static_cast<uint32_t>(2 * MT * P.BN)) cols <<= 1;
+  while (cols < static_cast<uint32_t>(bufs * MT * P.BN)) cols <<= 1;
   P.tmem_cols = cols;
+  // keep two activation stages within ~96 KB so the weight ring keeps most of the shared memory
+  while (P.KB > 16 && 2 * static_cast<size_t>(MT) * (P.KB / 8) * P.RA * 16 > 96 * 1024) P.KB /= 2;
   const size_t a_stage = static_cast<size_t>(MT) * (P.KB / 8) * P.RA * 16;
   const size_t w_tap = static_cast<size_t>(P.KB / 8) * P.BN * 16;
   const size_t w_all = w_tap * g.taps * (g.K / P.KB);
@@ -143,18 +145,23 @@ inline int tc_run_conv(vcd_plan* p, const Layer& L, bool dgrad, const void* in, 
     P.TPS = tps; P.NW = nw;
     w_region = static_cast<size_t>(tps) * nw * w_tap;
   }
-  const size_t smem = 128 + P.NA * a_stage + w_region + (2 * P.NA + 16 + 4) * 8 + 16;
+  const size_t smem = 128 + P.NA * a_stage + w_region + (2 * P.NA + 16 + 4) * 8 + 16 + 2 * 128 * 4;
   if (smem > 227 * 1024) {
     snprintf(err, errn, "tc_run_conv(%s): shared memory budget exceeded (%zu bytes)", L.name.c_str(), smem);
     return 1;
   }
-  CUtensorMap tmA;
-  if (!tc_make_act_map(&tmA, in, B, g.K, Lin, P.RA, P.KB / 8)) {
-    snprintf(err, errn, "tc_run_conv(%s): cuTensorMapEncodeTiled failed", L.name.c_str());
-    return 1;
+  P.in = static_cast<const bf16*>(in);
+  P.trace = nullptr;
+  {
+    static const char* want = getenv("VCD_KTRACE");  // e.g. "resblocks.5.convs1.0:fwd"
+    if (want && p->d_trace && (L.name + (dgrad ? ":dgrad" : ":fwd")) == want) {
+      P.trace = p->d_trace;
+      fprintf(stderr, "[ktrace] %s%s bufs=%d BN=%d MT=%d KB=%d RA=%d NA=%d resident=%d TPS=%d NW=%d tiles=%d taps=%d K=%d\n", L.name.c_str(),
+              dgrad ? ":dgrad" : ":fwd", P.acc_bufs, P.BN, P.MT, P.KB, P.RA, P.NA, P.w_resident, P.TPS, P.NW, P.total_tiles, g.taps, g.K);
+    }
   }
   const int grid = P.total_tiles < p->num_sms ? P.total_tiles : p->num_sms;
-  tc::conv_kernel<<<grid, tc::kConvThreads, smem, stream>>>(tmA, P);
+  tc::conv_kernel<<<grid, tc::kConvThreads, smem, stream>>>(P);
   launches.fetch_add(1, std::memory_order_relaxed);
   const cudaError_t ce = cudaGetLastError();
   if (ce != cudaSuccess) {
@@ -212,13 +219,11 @@ inline int tc_run_wgrad(vcd_plan* p, const Layer& L, const void* in, const void*
   if (want < 1) want = 1;
   P.kb_per_split = static_cast<int>((total_kb + want - 1) / want);
   P.n_splits = static_cast<int>((total_kb + P.kb_per_split - 1) / P.kb_per_split);
-  CUtensorMap tmIn, tmD;
-  if (!tc_make_act_map(&tmIn, in, B, g.K, Lin, P.RI, P.mch) || !tc_make_act_map(&tmD, dout, B, g.N, Ld, P.TK, P.NT / 8)) {
-    snprintf(err, errn, "tc_run_wgrad(%s): cuTensorMapEncodeTiled failed", L.name.c_str());
-    return 1;
-  }
+  P.in = static_cast<const bf16*>(in);
+  P.dout = static_cast<const bf16*>(dout);
+  P.Lin = Lin;
   const long long grid = base_ctas * P.n_splits;
-  tc::wgrad_kernel<<<static_cast<unsigned>(grid), tc::kThreads, smem, stream>>>(tmIn, tmD, P);
+  tc::wgrad_kernel<<<static_cast<unsigned>(grid), tc::kThreads, smem, stream>>>(P);
   launches.fetch_add(1, std::memory_order_relaxed);
   const cudaError_t ce = cudaGetLastError();
   if (ce != cudaSuccess) {

@@ -1,5 +1,7 @@
 // tcgen05 / TMEM / TMA implicit-GEMM kernels for sm_100a (bf16 operands, fp32 accumulation in TMEM).
 //
+// Operands reach shared memory through the TMA bulk-copy engine (cp.async.bulk, SASS UBLKCP) completing on
+// mbarriers: in the row-padded blocked layout every (channel group, row range) of a tile is one contiguous run.
 // Shared-memory operand layout (no swizzle, 8x(16 B) core matrices, see common.cuh):
 //     A tile  : [K_blk/8][RA rows][8]   -- K-major operand, row r of channel group c at (c*RA + r)*16 B.
 //               A dilated tap is the SAME tile read through a descriptor whose start address is advanced by
@@ -10,8 +12,6 @@
 // The kernel is persistent: each CTA walks a static tile list; TMEM accumulators are double-buffered so the
 // epilogue of tile i overlaps the MMAs of tile i+1.
 #pragma once
-#include <cuda.h>
-
 #include "common.cuh"
 
 namespace vcd {
@@ -54,12 +54,6 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-__device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2, int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-      : "memory");
-}
 __device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(smem_u32(bar))
@@ -121,6 +115,16 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, 
          (static_cast<uint32_t>(M >> 4) << 24);
 }
 
+// One elected lane of a CONVERGED warp.  The producer / MMA warps keep their control flow warp-uniform and
+// predicate only the issuing instruction with this: descriptors, addresses and loop state then live in
+// uniform registers (a divergent `if (lane == 0)` region forces an R2UR + per-lane ELECT loop around every
+// UTCHMMA / UBLKCP -- measured ~150 clk per MMA issue and ~500 clk per bulk copy on B200).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
 struct Pipe {
   int stage = 0;
   uint32_t phase = 0;
@@ -143,6 +147,7 @@ constexpr int kConvThreads = 320;
 struct ConvParams {
   ConvGeo g;
   Epilogue e;
+  const bf16* in;         // blocked, row-padded activation [B][K/8][Lin + pads][8]
   const bf16* w;          // packed [N/BN][taps][K/8][BN][8]
   int B, Lin, Lq, Lout;
   int BN, MT, KB, RA;     // column tile, 128-row tiles per CTA tile, K block (channels), rows per A region
@@ -151,8 +156,18 @@ struct ConvParams {
   int TPS, NW;            // ring mode: taps per stage, stages
   int n_tiles_n, n_mgroups, total_tiles;
   int minshift;           // min over taps of j*step (<= 0)
+  int acc_bufs;           // 2: accumulators double-buffered (epilogue overlaps the next tile's MMAs); 1: MT*BN > 256
   uint32_t tmem_cols;
+  unsigned long long* trace;  // debug: %globaltimer stamps of CTA 0 (null = off)
 };
+
+__device__ __forceinline__ void ktrace(unsigned long long* buf, int slot) {
+  if (buf != nullptr && blockIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    buf[slot] = t;
+  }
+}
 
 struct EpiLoads {
   uint4 mask, rest;
@@ -178,18 +193,13 @@ __device__ __forceinline__ void epi_prefetch(const Epilogue& e, size_t o, bool v
   }
 }
 
+// bias8: the 8 bias values (bias + per-batch bias) of this channel group, staged in shared memory per tile -- a
+// global bias load here would put a full memory latency on the critical path of every 16-column unit.
 __device__ __forceinline__ void epi_finish(const Epilogue& e, const ConvGeo& g, int b, int ro, int ch0, size_t o,
-                                           const EpiLoads& L, float (&v)[8]) {
-  if (e.bias) {
-    const float4 b0 = __ldg(reinterpret_cast<const float4*>(e.bias + ch0));
-    const float4 b1 = __ldg(reinterpret_cast<const float4*>(e.bias + ch0) + 1);
-    v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-    v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-  }
-  if (e.bias2) {
-    const float* bp = e.bias2 + static_cast<size_t>(b) * g.creal + ch0;
-    const float4 b0 = __ldg(reinterpret_cast<const float4*>(bp));
-    const float4 b1 = __ldg(reinterpret_cast<const float4*>(bp) + 1);
+                                           const EpiLoads& L, const float* bias8, float (&v)[8]) {
+  {
+    const float4 b0 = *reinterpret_cast<const float4*>(bias8);
+    const float4 b1 = *reinterpret_cast<const float4*>(bias8 + 4);
     v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
     v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
   }
@@ -226,9 +236,12 @@ __device__ __forceinline__ void epi_finish(const Epilogue& e, const ConvGeo& g, 
 }
 
 __global__ void __launch_bounds__(kConvThreads, 1)
-conv_kernel(const __grid_constant__ CUtensorMap tmA, const ConvParams P) {
+conv_kernel(const ConvParams P) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // shfl-broadcast warp index: provably warp-uniform, so role branches are uniform and the compiler may use the
+  // uniform datapath (UR registers) for descriptor / address arithmetic inside them
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) ktrace(P.trace, 0);
 
   const uint32_t a_region_bytes = static_cast<uint32_t>(P.KB / 8) * P.RA * 16;
   const uint32_t a_stage_bytes = a_region_bytes * P.MT;
@@ -247,6 +260,7 @@ conv_kernel(const __grid_constant__ CUtensorMap tmA, const ConvParams P) {
   uint64_t* acc_full = emptyW + 8;
   uint64_t* acc_empty = acc_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  float* bias_s = reinterpret_cast<float*>(tmem_slot + 4);   // [2][128]: per-tile bias (+ per-batch bias), double-buffered
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < P.NA; ++i) { mbar_init(&fullA[i], 1); mbar_init(&emptyA[i], 1); }
@@ -259,108 +273,137 @@ conv_kernel(const __grid_constant__ CUtensorMap tmA, const ConvParams P) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) ktrace(P.trace, 1);
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
-      if (P.w_resident) {  // whole weight set of column tile 0 (n_tiles_n == 1), one bulk copy per 64 KB
-        const uint32_t total = w_region_bytes;
+    // ===================== bulk-copy (TMA) producer: converged warp, elected lane issues =====================
+    // An A region is (KB/8) channel groups x RA rows; in the row-padded global layout each channel group's rows
+    // are one contiguous run, so the region is KB/8 1-D bulk copies.
+    if (P.w_resident) {  // whole weight set of column tile 0 (n_tiles_n == 1)
+      const uint32_t total = w_region_bytes;
+      if (elect_one()) {
         mbar_expect_tx(&fullW[0], total);
         for (uint32_t off = 0; off < total; off += 65536u)
           bulk_load(w_smem + off, reinterpret_cast<const uint8_t*>(P.w) + off, min(65536u, total - off), &fullW[0]);
       }
-      Pipe pa, pw;
-      for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
-        const int nt = tile % P.n_tiles_n;
-        const int rest = tile / P.n_tiles_n;
-        const int mg = rest % P.n_mgroups;
-        const int b = rest / P.n_mgroups;
-        const int row0 = mg * 128 * P.MT + P.g.off0 + P.minshift;
-        for (int kb = 0; kb < kblocks; ++kb) {
-          mbar_wait(&emptyA[pa.stage], pa.phase ^ 1);
-          mbar_expect_tx(&fullA[pa.stage], a_stage_bytes);
-          for (int mt = 0; mt < P.MT; ++mt)
-            tma_load_4d(&tmA, &fullA[pa.stage], a_smem + static_cast<size_t>(pa.stage) * a_stage_bytes + mt * a_region_bytes,
-                        0, row0 + mt * 128, kb * (P.KB / 8), b);
-          pa.advance(P.NA);
-          if (!P.w_resident) {
-            for (int j0 = 0; j0 < P.g.taps; j0 += P.TPS) {
-              const int nj = min(P.TPS, P.g.taps - j0);
-              mbar_wait(&emptyW[pw.stage], pw.phase ^ 1);
+      __syncwarp();
+    }
+    const int cgs = P.KB / 8;
+    const uint32_t cg_bytes = static_cast<uint32_t>(P.RA) * 16;
+    const size_t cg_stride_g = static_cast<size_t>(padded_len(P.Lin)) * 8;   // elements between channel groups
+    Pipe pa, pw;
+    for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+      const int nt = tile % P.n_tiles_n;
+      const int rest = tile / P.n_tiles_n;
+      const int mg = rest % P.n_mgroups;
+      const int b = rest / P.n_mgroups;
+      const int row0 = mg * 128 * P.MT + P.g.off0 + P.minshift;
+      // 128-row tiles that start beyond the last output row are not loaded (their accumulators are never stored)
+      int mt_live = P.MT;
+      while (mt_live > 1 && (mg * P.MT + mt_live - 1) * 128 >= P.Lq) --mt_live;
+      for (int kb = 0; kb < kblocks; ++kb) {
+        mbar_wait(&emptyA[pa.stage], pa.phase ^ 1);
+        uint8_t* stage = a_smem + static_cast<size_t>(pa.stage) * a_stage_bytes;
+        const bf16* src0 = P.in + blk_row(b, kb * cgs, row0, P.g.K, P.Lin);
+        if (elect_one()) {
+          mbar_expect_tx(&fullA[pa.stage], mt_live * cgs * cg_bytes);
+          for (int mt = 0; mt < mt_live; ++mt)
+            for (int cg = 0; cg < cgs; ++cg)
+              bulk_load(stage + mt * a_region_bytes + cg * cg_bytes, src0 + cg * cg_stride_g + static_cast<size_t>(mt) * 128 * 8,
+                        cg_bytes, &fullA[pa.stage]);
+        }
+        __syncwarp();
+        if (tile == static_cast<int>(blockIdx.x) && kb == 0 && lane == 0) ktrace(P.trace, 2);
+        pa.advance(P.NA);
+        if (!P.w_resident) {
+          for (int j0 = 0; j0 < P.g.taps; j0 += P.TPS) {
+            const int nj = min(P.TPS, P.g.taps - j0);
+            mbar_wait(&emptyW[pw.stage], pw.phase ^ 1);
+            uint8_t* dst = w_smem + static_cast<size_t>(pw.stage) * P.TPS * w_tap_bytes;
+            const bf16* src = P.w + ((static_cast<size_t>(nt) * P.g.taps + j0) * (P.g.K / 8) +
+                                     static_cast<size_t>(kb) * (P.KB / 8)) * P.BN * 8;
+            const size_t tap_stride_g = static_cast<size_t>(P.g.K / 8) * P.BN * 8;
+            if (elect_one()) {
               mbar_expect_tx(&fullW[pw.stage], nj * w_tap_bytes);
-              uint8_t* dst = w_smem + static_cast<size_t>(pw.stage) * P.TPS * w_tap_bytes;
-              for (int jj = 0; jj < nj; ++jj) {
-                const bf16* src = P.w + ((static_cast<size_t>(nt) * P.g.taps + j0 + jj) * (P.g.K / 8) +
-                                         static_cast<size_t>(kb) * (P.KB / 8)) * P.BN * 8;
-                bulk_load(dst + jj * w_tap_bytes, src, w_tap_bytes, &fullW[pw.stage]);
+              if (kblocks == 1) {  // taps are contiguous in the packed weights: one copy per stage
+                bulk_load(dst, src, nj * w_tap_bytes, &fullW[pw.stage]);
+              } else {
+                for (int jj = 0; jj < nj; ++jj)
+                  bulk_load(dst + jj * w_tap_bytes, src + jj * tap_stride_g, w_tap_bytes, &fullW[pw.stage]);
               }
-              pw.advance(P.NW);
             }
+            __syncwarp();
+            pw.advance(P.NW);
           }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (one thread) =====================
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc(128, P.BN, 0, 0);
-      const uint32_t a_lbo = static_cast<uint32_t>(P.RA) * 16, w_lbo = static_cast<uint32_t>(P.BN) * 16;
-      // descriptor arithmetic in 16-byte units on the low word (start-address field)
-      const uint32_t a_region16 = a_region_bytes >> 4, a_kk16 = (2 * a_lbo) >> 4, w_kk16 = (2 * w_lbo) >> 4;
-      const uint32_t w_tap16 = w_tap_bytes >> 4;
-      const uint64_t a_desc0 = make_desc(0, a_lbo, 128), w_desc0 = make_desc(0, w_lbo, 128);
-      Pipe pa, pw;
-      int it = 0;
-      if (P.w_resident) {
-        mbar_wait(&fullW[0], 0);
+    // ===================== MMA issuer: converged warp, elected lane issues =====================
+    const uint32_t idesc = make_idesc(128, P.BN, 0, 0);
+    const uint32_t a_lbo = static_cast<uint32_t>(P.RA) * 16, w_lbo = static_cast<uint32_t>(P.BN) * 16;
+    // descriptor arithmetic in 16-byte units on the low word (start-address field)
+    const uint32_t a_region16 = a_region_bytes >> 4, a_kk16 = (2 * a_lbo) >> 4, w_kk16 = (2 * w_lbo) >> 4;
+    const uint32_t w_tap16 = w_tap_bytes >> 4;
+    const uint64_t a_desc0 = make_desc(0, a_lbo, 128), w_desc0 = make_desc(0, w_lbo, 128);
+    Pipe pa, pw;
+    int it = 0;
+    if (P.w_resident) {
+      mbar_wait(&fullW[0], 0);
+      tc_fence_after();
+      if (lane == 0) ktrace(P.trace, 3);
+    }
+    for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++it) {
+      const int buf = P.acc_bufs == 2 ? (it & 1) : 0;
+      const int use = P.acc_bufs == 2 ? (it >> 1) : it;      // how many times this buffer was used before
+      mbar_wait(&acc_empty[buf], (use & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t d_tile = tmem_base + static_cast<uint32_t>(buf * P.MT * P.BN);
+      for (int kb = 0; kb < kblocks; ++kb) {
+        mbar_wait(&fullA[pa.stage], pa.phase);
         tc_fence_after();
-      }
-      for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++it) {
-        const int buf = it & 1;
-        mbar_wait(&acc_empty[buf], ((it >> 1) & 1) ^ 1);
-        tc_fence_after();
-        const uint32_t d_tile = tmem_base + static_cast<uint32_t>(buf * P.MT * P.BN);
-        for (int kb = 0; kb < kblocks; ++kb) {
-          mbar_wait(&fullA[pa.stage], pa.phase);
-          tc_fence_after();
-          const uint64_t a_stage_desc = a_desc0 + (smem_u32(a_smem + static_cast<size_t>(pa.stage) * a_stage_bytes) >> 4);
-          int j = 0;
-          while (j < P.g.taps) {
-            int nj;
-            uint64_t w_desc;
-            if (P.w_resident) {
-              nj = P.g.taps;
-              w_desc = w_desc0 + ((smem_u32(w_smem) >> 4) + static_cast<uint32_t>(kb) * w_tap16);
-            } else {
-              nj = min(P.TPS, P.g.taps - j);
-              mbar_wait(&fullW[pw.stage], pw.phase);
-              tc_fence_after();
-              w_desc = w_desc0 + (smem_u32(w_smem + static_cast<size_t>(pw.stage) * P.TPS * w_tap_bytes) >> 4);
-            }
-            // resident layout is [tap][K/8][BN][8]: consecutive taps are kblocks*w_tap16 apart
-            const uint32_t tap_stride16 = P.w_resident ? w_tap16 * kblocks : w_tap16;
-            for (int jj = 0; jj < nj; ++jj, ++j) {
-              const uint64_t a_tap = a_stage_desc + static_cast<uint32_t>(j * P.g.step - P.minshift);
-              const uint64_t w_tap = w_desc + jj * tap_stride16;
-              for (int mt = 0; mt < P.MT; ++mt) {
-                const uint32_t d_tmem = d_tile + static_cast<uint32_t>(mt * P.BN);
-                const uint64_t a_mt = a_tap + mt * a_region16;
-#pragma unroll 4
-                for (int kk = 0; kk < kk_per_block; ++kk)
-                  umma_bf16(d_tmem, a_mt + kk * a_kk16, w_tap + kk * w_kk16, idesc, (kb | j | kk) != 0 ? 1u : 0u);
+        if (it == 0 && kb == 0 && lane == 0) ktrace(P.trace, 4);
+        const uint64_t a_stage_desc = a_desc0 + (smem_u32(a_smem + static_cast<size_t>(pa.stage) * a_stage_bytes) >> 4);
+        int j = 0;
+        while (j < P.g.taps) {
+          int nj;
+          uint64_t w_desc;
+          if (P.w_resident) {
+            nj = P.g.taps;
+            w_desc = w_desc0 + ((smem_u32(w_smem) >> 4) + static_cast<uint32_t>(kb) * w_tap16);
+          } else {
+            nj = min(P.TPS, P.g.taps - j);
+            mbar_wait(&fullW[pw.stage], pw.phase);
+            tc_fence_after();
+            w_desc = w_desc0 + (smem_u32(w_smem + static_cast<size_t>(pw.stage) * P.TPS * w_tap_bytes) >> 4);
+          }
+          // resident layout is [tap][K/8][BN][8]: consecutive taps are kblocks*w_tap16 apart
+          const uint32_t tap_stride16 = P.w_resident ? w_tap16 * kblocks : w_tap16;
+          for (int jj = 0; jj < nj; ++jj, ++j) {
+            const uint64_t a_tap = a_stage_desc + static_cast<uint32_t>(j * P.g.step - P.minshift);
+            const uint64_t w_tap = w_desc + jj * tap_stride16;
+            for (int mt = 0; mt < P.MT; ++mt) {
+              const uint32_t d_tmem = d_tile + static_cast<uint32_t>(mt * P.BN);
+              const uint64_t a_mt = a_tap + mt * a_region16;
+              for (int kk = 0; kk < kk_per_block; ++kk) {
+                const uint64_t ad = a_mt + kk * a_kk16, bd = w_tap + kk * w_kk16;
+                const uint32_t accum = (kb | j | kk) != 0 ? 1u : 0u;
+                if (elect_one()) umma_bf16(d_tmem, ad, bd, idesc, accum);
               }
             }
-            if (!P.w_resident) {
-              umma_commit(&emptyW[pw.stage]);
-              pw.advance(P.NW);
-            }
           }
-          umma_commit(&emptyA[pa.stage]);
-          pa.advance(P.NA);
+          if (!P.w_resident) {
+            if (elect_one()) umma_commit(&emptyW[pw.stage]);
+            pw.advance(P.NW);
+          }
         }
-        umma_commit(&acc_full[buf]);
+        if (elect_one()) umma_commit(&emptyA[pa.stage]);
+        pa.advance(P.NA);
       }
+      if (elect_one()) umma_commit(&acc_full[buf]);
+      if (it < 4 && lane == 0) ktrace(P.trace, 8 + it);       // MMAs of tile `it` issued
     }
+    if (lane == 0) ktrace(P.trace, 5);
   } else {
     // ===================== epilogue warps =====================
     const int quad = warp & 3;               // TMEM lane quadrant this warp may access
@@ -375,65 +418,84 @@ conv_kernel(const __grid_constant__ CUtensorMap tmA, const ConvParams P) {
       const int rest = tile / P.n_tiles_n;
       const int mg = rest % P.n_mgroups;
       const int b = rest / P.n_mgroups;
-      const int buf = it & 1;
+      const int buf = P.acc_bufs == 2 ? (it & 1) : 0;
+      const int use = P.acc_bufs == 2 ? (it >> 1) : it;
       const int r_phase = (nt * P.BN) / P.g.creal;          // scatter phase of this column tile (os > 1)
       const int ch_tile = nt * P.BN - r_phase * P.g.creal;  // first output channel of the tile
 
-      auto unit_coords = [&](int u, int& ro, bool& valid, size_t& o0, uint32_t& taddr) {
+      {  // stage this tile's bias vector (named barrier 1 = the 256 epilogue threads)
+        const int et = static_cast<int>(threadIdx.x) - 64;
+        if (et < P.BN) {
+          float bv = e.bias ? __ldg(e.bias + ch_tile + et) : 0.f;
+          if (e.bias2) bv += __ldg(e.bias2 + static_cast<size_t>(b) * P.g.creal + ch_tile + et);
+          bias_s[(it & 1) * 128 + et] = bv;
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+      }
+      // per-thread row state of each 128-row tile (computed once per tile, not per unit)
+      const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(buf * P.MT * P.BN);
+      const size_t chunk_stride = static_cast<size_t>(padded_len(P.Lout)) * 8;  // next 8-channel group, same row
+      const int q_first = mg * P.MT * 128 + row_in_tile;
+      auto unit_coords = [&](int u, int& ro, bool& valid, size_t& o0, uint32_t& taddr, int& ch) {
         const int mt = u / units_per_mt, c16 = u - mt * units_per_mt;
-        const int q = (mg * P.MT + mt) * 128 + row_in_tile;
+        const int q = q_first + mt * 128;
         ro = q * P.g.os + r_phase - P.g.p;
         valid = q < P.Lq && ro >= 0 && ro < P.Lout;
-        o0 = blk_off(b, ch_tile + c16 * 16, valid ? ro : 0, P.g.creal, P.Lout);
-        taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>((buf * P.MT + mt) * P.BN + c16 * 16);
+        ch = ch_tile + c16 * 16;
+        o0 = blk_row(b, ch >> 3, valid ? ro : 0, P.g.creal, P.Lout);
+        taddr = t_lane + static_cast<uint32_t>(mt * P.BN + c16 * 16);
       };
 
       // software pipeline: global operands of unit u+2 are requested before unit u is finished
       EpiLoads cur[2], nxt[2];
-      int ro_c = 0, ro_n = 0;
+      int ro_c = 0, ro_n = 0, ch_c = 0, ch_n = 0;
       bool v_c = false, v_n = false;
       size_t o_c = 0, o_n = 0;
       uint32_t t_c = 0, t_n = 0;
-      const size_t chunk_stride = static_cast<size_t>(P.Lout) * 8;  // next 8-channel group of the same row
       int u = half;
       if (u < n_units) {
-        unit_coords(u, ro_c, v_c, o_c, t_c);
+        unit_coords(u, ro_c, v_c, o_c, t_c, ch_c);
         epi_prefetch(e, o_c, v_c, cur[0]);
         epi_prefetch(e, o_c + chunk_stride, v_c, cur[1]);
       }
-      mbar_wait(&acc_full[buf], (it >> 1) & 1);
+      mbar_wait(&acc_full[buf], use & 1);
       tc_fence_after();
+      if (warp == 2 && lane == 0 && it < 4) ktrace(P.trace, 12 + it);   // accumulators of tile `it` complete
       for (; u < n_units; u += 2) {
         const int un = u + 2;
         if (un < n_units) {
-          unit_coords(un, ro_n, v_n, o_n, t_n);
+          unit_coords(un, ro_n, v_n, o_n, t_n, ch_n);
           epi_prefetch(e, o_n, v_n, nxt[0]);
           epi_prefetch(e, o_n + chunk_stride, v_n, nxt[1]);
         }
         float acc[16];
+        if (warp == 2 && lane == 0 && it == 0 && u < 6) ktrace(P.trace, 20 + u * 2);       // debug: unit start
         tmem_ld16(t_c, acc);
+        if (warp == 2 && lane == 0 && it == 0 && u < 6) ktrace(P.trace, 21 + u * 2);       // debug: TMEM load done
         if (v_c) {
-          const int c16 = u % units_per_mt;
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             float v[8];
 #pragma unroll
             for (int n = 0; n < 8; ++n) v[n] = acc[h * 8 + n];
-            epi_finish(e, P.g, b, ro_c, ch_tile + c16 * 16 + h * 8, o_c + h * chunk_stride, cur[h], v);
+            epi_finish(e, P.g, b, ro_c, ch_c + h * 8, o_c + h * chunk_stride, cur[h],
+                       bias_s + (it & 1) * 128 + (ch_c - ch_tile) + h * 8, v);
           }
         }
         cur[0] = nxt[0]; cur[1] = nxt[1];
-        ro_c = ro_n; v_c = v_n; o_c = o_n; t_c = t_n;
+        ro_c = ro_n; v_c = v_n; o_c = o_n; t_c = t_n; ch_c = ch_n;
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[buf]);
+      if (warp == 2 && lane == 0 && it < 4) ktrace(P.trace, 16 + it);   // epilogue of tile `it` done
     }
   }
 
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, P.tmem_cols);
+  if (threadIdx.x == 0) ktrace(P.trace, 6);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -450,6 +512,9 @@ conv_kernel(const __grid_constant__ CUtensorMap tmA, const ConvParams P) {
 // concurrently on side streams.
 // ---------------------------------------------------------------------------------------------------
 struct WgradParams {
+  const bf16* in;         // blocked, row-padded [B][K/8][Lin + pads][8]
+  const bf16* dout;       // blocked, row-padded [B][N/8][L + pads][8]
+  int Lin;
   float* dwp;             // [taps][K][N] fp32
   int taps, K, N, step, off0, minshift;
   int B, L;               // L = rows of dout per batch item (the contraction length)
@@ -464,9 +529,11 @@ struct WgradParams {
 };
 
 __global__ void __launch_bounds__(kThreads, 1)
-wgrad_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ CUtensorMap tmD, const WgradParams P) {
+wgrad_kernel(const WgradParams P) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // shfl-broadcast warp index: provably warp-uniform, so role branches are uniform and the compiler may use the
+  // uniform datapath (UR registers) for descriptor / address arithmetic inside them
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const uint32_t in_copy_bytes = static_cast<uint32_t>(P.mch) * P.RI * 16;
   const uint32_t in_bytes = in_copy_bytes * P.G;
   const uint32_t d_bytes = static_cast<uint32_t>(P.NT / 8) * P.TK * 16;
@@ -502,46 +569,58 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ C
   const int nslots = min(P.TG, P.n_slots - slot0);
 
   if (warp == 0) {
-    if (lane == 0) {
-      Pipe ps;
-      for (int kb = 0; kb < kblocks; ++kb) {
-        const int f = f_begin + kb;
-        const int b = f / P.kb_per_item;
-        const int t0 = (f - b * P.kb_per_item) * P.TK;
-        mbar_wait(&empty[ps.stage], ps.phase ^ 1);
+    // bulk-copy producer: one contiguous run of rows per channel group (row-padded layout); converged warp,
+    // elected lane issues
+    const int n_d = P.NT / 8;
+    const uint32_t in_cg_bytes = static_cast<uint32_t>(P.RI) * 16, d_cg_bytes = static_cast<uint32_t>(P.TK) * 16;
+    const size_t in_cg_stride = static_cast<size_t>(padded_len(P.Lin)) * 8, d_cg_stride = static_cast<size_t>(padded_len(P.L)) * 8;
+    Pipe ps;
+    for (int kb = 0; kb < kblocks; ++kb) {
+      const int f = f_begin + kb;
+      const int b = f / P.kb_per_item;
+      const int t0 = (f - b * P.kb_per_item) * P.TK;
+      mbar_wait(&empty[ps.stage], ps.phase ^ 1);
+      uint8_t* st = smem + static_cast<size_t>(ps.stage) * stage_bytes;
+      const bf16* in0 = P.in + blk_row(b, mtile * P.mch, t0 + P.off0 + P.minshift, P.K, P.Lin);
+      const bf16* d0 = P.dout + blk_row(b, ntile * n_d, t0, P.N, P.L);
+      if (elect_one()) {
         mbar_expect_tx(&full[ps.stage], stage_bytes);
-        uint8_t* st = smem + static_cast<size_t>(ps.stage) * stage_bytes;
         for (int g = 0; g < P.G; ++g)
-          tma_load_4d(&tmIn, &full[ps.stage], st + g * in_copy_bytes, 0, t0 + P.off0 + P.minshift + g * P.step, mtile * P.mch, b);
-        tma_load_4d(&tmD, &full[ps.stage], st + in_bytes, 0, t0, ntile * (P.NT / 8), b);
-        ps.advance(P.NS);
+          for (int cg = 0; cg < P.mch; ++cg)
+            bulk_load(st + (g * P.mch + cg) * in_cg_bytes, in0 + cg * in_cg_stride + static_cast<ptrdiff_t>(g) * P.step * 8,
+                      in_cg_bytes, &full[ps.stage]);
+        for (int cg = 0; cg < n_d; ++cg)
+          bulk_load(st + in_bytes + cg * d_cg_bytes, d0 + cg * d_cg_stride, d_cg_bytes, &full[ps.stage]);
       }
+      __syncwarp();
+      ps.advance(P.NS);
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc(128, P.NT, 1, 1);
-      const uint64_t a_desc0 = make_desc(0, 128, static_cast<uint32_t>(P.RI) * 16);
-      const uint64_t b_desc0 = make_desc(0, 128, static_cast<uint32_t>(P.TK) * 16);
-      const int kks = P.TK / 16;
-      Pipe ps;
-      for (int kb = 0; kb < kblocks; ++kb) {
-        mbar_wait(&full[ps.stage], ps.phase);
-        tc_fence_after();
-        const uint32_t a_base = smem_u32(smem + static_cast<size_t>(ps.stage) * stage_bytes);
-        const uint64_t a_stage = a_desc0 + (a_base >> 4);
-        const uint64_t b_stage = b_desc0 + ((a_base + in_bytes) >> 4);
-        for (int tl = 0; tl < nslots; ++tl) {
-          const uint64_t a_slot = a_stage + static_cast<uint32_t>((slot0 + tl) * P.G * P.step - P.minshift);
-          const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(tl * P.NT);
-#pragma unroll 4
-          for (int kk = 0; kk < kks; ++kk)
-            umma_bf16(d_tmem, a_slot + kk * 16, b_stage + kk * 16, idesc, (kb | kk) != 0 ? 1u : 0u);
+    // MMA issuer: converged warp, elected lane issues
+    const uint32_t idesc = make_idesc(128, P.NT, 1, 1);
+    const uint64_t a_desc0 = make_desc(0, 128, static_cast<uint32_t>(P.RI) * 16);
+    const uint64_t b_desc0 = make_desc(0, 128, static_cast<uint32_t>(P.TK) * 16);
+    const int kks = P.TK / 16;
+    Pipe ps;
+    for (int kb = 0; kb < kblocks; ++kb) {
+      mbar_wait(&full[ps.stage], ps.phase);
+      tc_fence_after();
+      const uint32_t a_base = smem_u32(smem + static_cast<size_t>(ps.stage) * stage_bytes);
+      const uint64_t a_stage = a_desc0 + (a_base >> 4);
+      const uint64_t b_stage = b_desc0 + ((a_base + in_bytes) >> 4);
+      for (int tl = 0; tl < nslots; ++tl) {
+        const uint64_t a_slot = a_stage + static_cast<uint32_t>((slot0 + tl) * P.G * P.step - P.minshift);
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(tl * P.NT);
+        for (int kk = 0; kk < kks; ++kk) {
+          const uint64_t ad = a_slot + kk * 16, bd = b_stage + kk * 16;
+          const uint32_t accum = (kb | kk) != 0 ? 1u : 0u;
+          if (elect_one()) umma_bf16(d_tmem, ad, bd, idesc, accum);
         }
-        umma_commit(&empty[ps.stage]);
-        ps.advance(P.NS);
       }
-      umma_commit(acc_full);
+      if (elect_one()) umma_commit(&empty[ps.stage]);
+      ps.advance(P.NS);
     }
+    if (elect_one()) umma_commit(acc_full);
   } else {
     const int quad = warp & 3;
     const int row = quad * 32 + lane;

@@ -415,6 +415,7 @@ extern "C" void vcd_plan_destroy(vcd_plan* p) {
   cudaFree(p->d_pack_jobs[0]); cudaFree(p->d_pack_jobs[1]);
   for (auto& s : p->segments) cudaFree(s.d_jobs);
   for (auto& kv : p->graphs) cudaGraphExecDestroy(kv.second);
+  for (auto& kv : p->pad_tables) cudaFree(kv.second);
   if (p->own) cudaStreamDestroy(p->own);
   if (p->hop_in) cudaEventDestroy(p->hop_in);
   if (p->hop_out) cudaEventDestroy(p->hop_out);
@@ -468,13 +469,9 @@ struct WsLayout {
   size_t duz = 0;                           // T: phase-packed gradient w.r.t. the upsample output
   size_t d0 = 0, dxb = 0;
   size_t total = 0;
+  // pad-row zeroing jobs: forward phase 0 = boundary tensors, phase 1+i = stage i; backward phase = segment
+  std::vector<std::vector<PadJob>> pad_fwd, pad_bwd;
 };
-
-size_t stage_elems(const vcd_plan* p, int i, int B, int T) {
-  size_t L = T;
-  for (int s = 0; s <= i; ++s) L *= p->stages[s].u;
-  return static_cast<size_t>(B) * p->stages[i].cout * L;
-}
 
 WsLayout make_layout(const vcd_plan* p, int mode, int B, int T, bool save) {
   WsLayout w;
@@ -487,19 +484,31 @@ WsLayout make_layout(const vcd_plan* p, int mode, int B, int T, bool save) {
   };
   const int S = static_cast<int>(p->stages.size()), NB = p->cfg.num_kernels;
   const int npairs = p->cfg.resblock == 1 ? 3 : 2;
-  const size_t C0 = p->cfg.upsample_initial_channel;
-  w.xin = alloc(es * B * p->cfg.initial_channel * T);
-  w.cb = alloc(4 * B * C0);
-  w.dcb = alloc(4 * B * C0);
+  const int C0 = p->cfg.upsample_initial_channel, Cin0 = p->cfg.initial_channel;
+  auto pad = [&](std::vector<PadJob>& v, size_t off, int C, int L) {
+    if (!off && &v != &w.pad_fwd[0]) return;  // unallocated slot
+    PadJob j{static_cast<long long>(off), B * (C / 8), L, static_cast<int>(es), 0};
+    j.first_block = v.empty() ? 0 : v.back().first_block + v.back().arrays;
+    v.push_back(j);
+  };
+  w.pad_fwd.resize(S + 1);
+  w.pad_bwd.resize(S + 1);
+  w.xin = alloc(es * blk_elems(B, Cin0, T));
+  w.cb = alloc(4 * static_cast<size_t>(B) * C0);
+  w.dcb = alloc(4 * static_cast<size_t>(B) * C0);
   w.a.resize(S + 1);
-  w.a[0] = alloc(es * B * C0 * T);
-  size_t emax = 0, zmax = 0, L = T;
+  w.a[0] = alloc(es * blk_elems(B, C0, T));
+  pad(w.pad_fwd[0], w.xin, Cin0, T);
+  pad(w.pad_fwd[0], w.a[0], C0, T);
+  size_t emax = 0, zmax = 0;
   std::vector<size_t> E(S);
+  std::vector<int> Ls(S + 1);
+  Ls[0] = T;
   for (int i = 0; i < S; ++i) {
     const Layer& U = p->layers[p->stages[i].up_layer];
-    zmax = std::max(zmax, static_cast<size_t>(B) * U.wgr.N * (L + U.fwd.taps - 1));
-    L *= p->stages[i].u;
-    E[i] = stage_elems(p, i, B, T);
+    zmax = std::max(zmax, blk_elems(B, U.wgr.N, Ls[i] + U.fwd.taps - 1));
+    Ls[i + 1] = Ls[i] * p->stages[i].u;
+    E[i] = blk_elems(B, p->stages[i].cout, Ls[i + 1]);
     emax = std::max(emax, E[i]);
     w.a[i + 1] = alloc(es * E[i]);
   }
@@ -516,14 +525,24 @@ WsLayout make_layout(const vcd_plan* p, int mode, int B, int T, bool save) {
   }
   for (int i = 0; i < S; ++i) {
     StageWs& s = w.st[i];
+    const int C = p->stages[i].cout, L = Ls[i + 1];
+    std::vector<PadJob>& pj = w.pad_fwd[i + 1];
     s.ua = save ? alloc(es * E[i]) : sh_ua;
+    pad(pj, s.ua, C, L);
     s.ma.assign(NB, std::vector<size_t>(npairs, 0));
     s.xa.assign(NB, std::vector<size_t>(npairs, 0));
     for (int j = 0; j < NB; ++j)
       for (int q = 0; q < npairs; ++q) {
-        if (p->cfg.resblock == 1) s.ma[j][q] = save ? alloc(es * E[i]) : sh_ma[j];
-        if (q < npairs - 1) s.xa[j][q] = save ? alloc(es * E[i]) : ((q & 1) ? sh_xa1[j] : sh_xa0[j]);
+        if (p->cfg.resblock == 1) {
+          s.ma[j][q] = save ? alloc(es * E[i]) : sh_ma[j];
+          if (save || q == 0) pad(pj, s.ma[j][q], C, L);
+        }
+        if (q < npairs - 1) {
+          s.xa[j][q] = save ? alloc(es * E[i]) : ((q & 1) ? sh_xa1[j] : sh_xa0[j]);
+          if (save || q < 2) pad(pj, s.xa[j][q], C, L);
+        }
       }
+    pad(pj, w.a[i + 1], C, L);
   }
   w.sum[0] = alloc(4 * emax);
   w.sum[1] = alloc(4 * emax);
@@ -538,11 +557,56 @@ WsLayout make_layout(const vcd_plan* p, int mode, int B, int T, bool save) {
         if (p->cfg.resblock == 1) w.dm[j][q] = alloc(es * emax);
       }
     w.duz = alloc(es * zmax);
-    w.d0 = alloc(es * B * C0 * T);
-    w.dxb = alloc(4 * static_cast<size_t>(B) * p->cfg.initial_channel * T);
+    w.d0 = alloc(es * blk_elems(B, C0, T));
+    w.dxb = alloc(4 * blk_elems(B, Cin0, T));
+    // backward pads: segment s works on stage i = S-1-s and produces the stage gradient consumed by segment s+1
+    pad(w.pad_fwd[S], w.Gi[(S - 1) & 1], p->stages[S - 1].cout, Ls[S]);  // written by conv_post's backward
+    pad(w.pad_fwd[0], w.d0, C0, T);
+    for (int seg = 0; seg < S; ++seg) {
+      const int i = S - 1 - seg;
+      const int C = p->stages[i].cout, L = Ls[i + 1];
+      for (int j = 0; j < NB; ++j)
+        for (int q = 0; q < npairs; ++q) {
+          if (q > 0) pad(w.pad_bwd[seg], w.Gt[j][q], C, L);
+          if (p->cfg.resblock == 1) pad(w.pad_bwd[seg], w.dm[j][q], C, L);
+        }
+      if (i > 0) pad(w.pad_bwd[seg], w.Gi[(i - 1) & 1], p->stages[i - 1].cout, Ls[i]);
+    }
   }
   w.total = top;
   return w;
+}
+
+// Pad-zeroing job tables are uploaded once per layout (outside any stream capture) and cached in the plan.
+int ensure_pad_tables(vcd_plan* p, const WsLayout& w, int mode, int B, int T, bool save) {
+  for (int bwd = 0; bwd < 2; ++bwd) {
+    const auto& phases = bwd ? w.pad_bwd : w.pad_fwd;
+    for (size_t ph = 0; ph < phases.size(); ++ph) {
+      const std::vector<PadJob>& jobs = phases[ph];
+      if (jobs.empty()) continue;
+      const auto key = std::make_tuple(mode, B, T, save ? 1 : 0, static_cast<int>(ph), bwd);
+      if (p->pad_tables.count(key)) continue;
+      PadJob* d = nullptr;
+      CU_TRY(cudaMalloc(&d, jobs.size() * sizeof(PadJob)));
+      CU_TRY(cudaMemcpy(d, jobs.data(), jobs.size() * sizeof(PadJob), cudaMemcpyHostToDevice));
+      p->pad_tables.emplace(key, static_cast<void*>(d));
+    }
+  }
+  return 0;
+}
+
+// Launch the pad-zeroing kernel for one phase.
+int launch_pads(vcd_plan* p, const std::vector<PadJob>& jobs, int mode, int B, int T, bool save, int phase, bool bwd,
+                char* ws, cudaStream_t stream) {
+  if (jobs.empty()) return 0;
+  const auto key = std::make_tuple(mode, B, T, save ? 1 : 0, phase, bwd ? 1 : 0);
+  auto it = p->pad_tables.find(key);
+  if (it == p->pad_tables.end()) return fail("internal: pad table missing");
+  const int blocks = jobs.back().first_block + jobs.back().arrays;
+  ProfScope ps__(PC_MISC, 0, 0, stream);
+  pad_zero_kernel<<<blocks, 64, 0, stream>>>(static_cast<const PadJob*>(it->second), static_cast<int>(jobs.size()), ws);
+  LAUNCH_CHECK("pad_zero_kernel");
+  return 0;
 }
 }  // namespace
 
@@ -751,6 +815,7 @@ int run_graphed(vcd_plan* p, const GraphKey& key, cudaStream_t stream, F&& enque
   if (ie != cudaSuccess) return fail("cudaGraphInstantiate failed: %s", cudaGetErrorString(ie));
   if (p->graphs.size() >= 64) {  // bounded cache: drop everything (shapes / workspaces keep changing)
     for (auto& kv : p->graphs) cudaGraphExecDestroy(kv.second);
+  for (auto& kv : p->pad_tables) cudaFree(kv.second);
   if (p->own) cudaStreamDestroy(p->own);
   if (p->hop_in) cudaEventDestroy(p->hop_in);
   if (p->hop_out) cudaEventDestroy(p->hop_out);
@@ -780,6 +845,7 @@ extern "C" int vcd_forward(vcd_plan* p, int mode, const float* x, int64_t xs_b, 
   if (!x || !y) return fail("vcd_forward: null x or y");
   if (gvec && !p->cfg.gin_channels) return fail("vcd_forward: g given but the plan has gin_channels = 0");
   const WsLayout w = make_layout(p, mode, B, T, save);
+  TRY(ensure_pad_tables(p, w, mode, B, T, save));
   StreamHop hop(p, stream_);
   Ctx c{p, mode, B, hop.run, static_cast<char*>(ws), g_prof_on || tc_env_int("VCD_SERIAL", 0) != 0};
   cudaStream_t stream = c.main;
@@ -806,6 +872,7 @@ extern "C" int vcd_forward(vcd_plan* p, int mode, const float* x, int64_t xs_b, 
   }
   int Lcur = T;
   auto core = [&]() -> int {
+  TRY(launch_pads(p, w.pad_fwd[0], mode, B, T, save, 0, false, c.ws, stream));
   {  // conv_pre (+ cond) -> a[0] = lrelu(., 0.1)
     const Layer& L = p->layers[p->l_pre];
     Epilogue e = epi();
@@ -819,6 +886,7 @@ extern "C" int vcd_forward(vcd_plan* p, int mode, const float* x, int64_t xs_b, 
     const StageDesc& sd = p->stages[i];
     const StageWs& sw = w.st[i];
     const Layer& U = p->layers[sd.up_layer];
+    TRY(launch_pads(p, w.pad_fwd[i + 1], mode, B, T, save, i + 1, false, c.ws, stream));
     {  // x = ups[i](lrelu(x)) ; stored as ua = lrelu(x, 0.1)
       Epilogue e = epi();
       e.bias = p->h_params[U.p_b];
@@ -898,6 +966,7 @@ extern "C" int vcd_backward(vcd_plan* p, int mode, const float* dy, const float*
   TRY(check_common(p, mode, B, T, ws, ws_bytes, true));
   if (!dy || !y || !dparams) return fail("vcd_backward: null dy, y or dparams");
   const WsLayout w = make_layout(p, mode, B, T, true);
+  TRY(ensure_pad_tables(p, w, mode, B, T, true));
   StreamHop hop(p, stream_);
   Ctx c{p, mode, B, hop.run, static_cast<char*>(ws), g_prof_on || tc_env_int("VCD_SERIAL", 0) != 0};
   cudaStream_t stream = c.main;
@@ -969,8 +1038,9 @@ extern "C" int vcd_backward(vcd_plan* p, int mode, const float* dy, const float*
       const Layer& U = p->layers[sd.up_layer];
       const int Lz = Lprev + U.fwd.taps - 1;  // rows of the phase-packed gradient
       const void* Gi = P(w.Gi[i & 1]);
-      // unwritten edge slots of the phase-packed tensor must read as zero
-      CU_TRY(cudaMemsetAsync(P(w.duz), 0, es * static_cast<size_t>(B) * U.wgr.N * Lz, stream));
+      // unwritten edge slots (and the pad rows) of the phase-packed tensor must read as zero
+      CU_TRY(cudaMemsetAsync(P(w.duz), 0, es * blk_elems(B, U.wgr.N, Lz), stream));
+      TRY(launch_pads(p, w.pad_bwd[seg], mode, B, T, true, seg, true, c.ws, stream));
       cudaEvent_t ev0 = c.serial ? nullptr : c.record(stream);
       for (int j = 1; j < NB; ++j) if (!c.serial) c.wait(c.branch(j), ev0);
       cudaEvent_t prev_final = nullptr;
@@ -1128,6 +1198,14 @@ extern "C" int vcd_synthesize_host(vcd_plan* p, int mode, const float* x_host, c
   TRY(vcd_forward(p, mode, xd, static_cast<int64_t>(Cin) * T, T, 1, g_host ? gd : nullptr, yd, ws, core, B, T, 0, stream_));
   CU_TRY(cudaMemcpyAsync(y_host, yd, sizeof(float) * static_cast<size_t>(B) * T * p->hop, cudaMemcpyDeviceToHost, stream));
   CU_TRY(cudaStreamSynchronize(stream));
+  return 0;
+}
+
+// Debug: copy the 64 %globaltimer stamps written by a VCD_KTRACE-selected kernel (see tc_kernels.cuh).
+extern "C" int vcd_debug_read_trace(vcd_plan* p, unsigned long long* out64) {
+  if (!p || !p->d_trace) return fail("tracing is off (set VCD_KTRACE=<layer>:<fwd|dgrad>)");
+  CU_TRY(cudaDeviceSynchronize());
+  CU_TRY(cudaMemcpy(out64, p->d_trace, 64 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
   return 0;
 }
 
