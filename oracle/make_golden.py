@@ -145,7 +145,31 @@ def golden_base_probe():
     print("base probe absmax", float(y.abs().max()), "checksum", checksum)
 
 
+def golden_mel():
+    """Reference mel_spectrogram_torch (vits/mel_processing.py:115-142) run with a librosa stub."""
+    import torchaudio
+    lib = types.ModuleType("librosa")
+    util = types.ModuleType("librosa.util")
+    filt = types.ModuleType("librosa.filters")
+    util.normalize = util.pad_center = util.tiny = None
+    def mel(sr, n_fft, n_mels, fmin, fmax):
+        return torchaudio.functional.melscale_fbanks(n_fft // 2 + 1, float(fmin), float(fmax if fmax else sr / 2), n_mels, sr,
+                                                     norm="slaney", mel_scale="slaney").T.contiguous().numpy()
+    filt.mel = mel
+    lib.util, lib.filters = util, filt
+    sys.modules["librosa"], sys.modules["librosa.util"], sys.modules["librosa.filters"] = lib, util, filt
+    from vits import mel_processing as ref_mel
+    torch.manual_seed(5)
+    t = torch.arange(16384) / 48000.0
+    y = 0.3 * torch.sin(2 * torch.pi * 440 * t) + 0.05 * torch.randn(2, 16384)
+    y = y.clamp(-1, 1)
+    m = ref_mel.mel_spectrogram_torch(y, 2048, 256, 48000, 512, 2048, 0.0, None)
+    np.savez_compressed(os.path.join(OUT, "mel_probe.npz"), y=y.numpy(), logmel=m.numpy())
+    print("mel probe", tuple(m.shape))
+
+
 if __name__ == "__main__":
+    golden_mel()
     golden_resblocks()
     golden_generator("generator_tiny", O.TINY_CFG, 2, 12, gain=1.5)
     golden_generator("generator_tiny2", O.TINY2_CFG, 2, 12, gain=1.5)

@@ -22,6 +22,7 @@ import torch
 from torch import nn
 
 from . import _lib
+from .dist import SegmentReducer
 
 __all__ = ["Generator", "LRELU_SLOPE"]
 
@@ -137,8 +138,7 @@ class _DecoderFunction(torch.autograd.Function):
         flat = torch.empty(module._flat_numel, dtype=torch.float32, device=dev)
         views = module._grad_views(flat)
         ptrs = (C.c_void_p * len(views))(*[v.data_ptr() for v in views])
-        group = module._grad_sync_group
-        works = []
+        reducer = SegmentReducer(flat, module._segment_ranges, module._grad_sync_group)
         for seg in range(module._num_segments):
             _lib.check(lib.vcd_backward(plan, module._mode, dy.data_ptr(), y.data_ptr(),
                                         gf.data_ptr() if gf is not None else None,
@@ -146,14 +146,10 @@ class _DecoderFunction(torch.autograd.Function):
                                         dg.data_ptr() if dg is not None else None,
                                         ptrs, ctx.ws.data_ptr(), ctx.ws_bytes, B, T, 1 << seg, stream),
                        "vcd_backward")
-            if group is not None:
-                # gradients of this segment are final: all-reduce them on NCCL's stream while the next
-                # segment's kernels run (replaces the DDP reducer implied by train.py:99-100)
-                lo, hi = module._segment_ranges[seg]
-                works.append(torch.distributed.all_reduce(flat[lo:hi], op=torch.distributed.ReduceOp.AVG,
-                                                          group=group, async_op=True))
-        for wk in works:
-            wk.wait()
+            # gradients of this segment are final: all-reduce them on NCCL's stream while the next segment's
+            # kernels run (replaces the DDP reducer implied by train.py:99-100)
+            reducer.segment_done(seg)
+        reducer.finish()
         module._give_workspace(ctx.ws)
         ctx.ws = None
         grads = [v if p.requires_grad else None for v, p in zip(views, module._ordered_params())]
