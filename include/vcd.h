@@ -136,6 +136,9 @@ const char* vcd_profile_class_name(int class_id);
 int vcd_profile_read(int reset, double* ms, uint64_t* launches, double* flops, double* bytes);
 int vcd_profile_dump(const char* csv_path); /* one line per recorded launch: class, layer tag, ms, GFLOP */
 
+/* Debug only (VCD_PHASES=1): print the device time of the fold, the forward core and every backward segment. */
+int vcd_phase_dump(int reset);
+
 /* Debug only: 64 in-kernel %globaltimer stamps of the kernel selected with the VCD_KTRACE environment variable. */
 int vcd_debug_read_trace(vcd_plan* plan, unsigned long long* out64);
 

@@ -25,4 +25,8 @@ for _ in range(a.steps):
         m._fold_key = None
         m(x.requires_grad_(True), g.requires_grad_(True)).backward(dy)
 torch.cuda.synchronize()
+from vcvits_b200 import _lib
+import os
+if os.environ.get("VCD_PHASES"):
+    _lib.load().vcd_phase_dump(1)
 print("done")

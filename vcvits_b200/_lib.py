@@ -105,6 +105,7 @@ _SIGNATURES = {
     "vcd_profile_read": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.POINTER(C.c_double),
                                    C.POINTER(C.c_double)]),
     "vcd_profile_dump": (C.c_int, [C.c_char_p]),
+    "vcd_phase_dump": (C.c_int, [C.c_int]),
     "vcd_debug_read_trace": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
     "vcd_layer_path": (C.c_char_p, [C.c_void_p, C.c_int, C.c_int]),
 }

@@ -50,7 +50,7 @@ inline void tc_layer_eligibility(Layer& L) {
     const int left = g.off0 + (g.step < 0 ? (g.taps - 1) * g.step : 0);
     const int right = g.off0 + (g.step > 0 ? (g.taps - 1) * g.step : 0);
     const bool shape_ok = g.is == 1 && g.os == 1 && g.p == 0 && g.creal == g.N && g.N % 16 == 0 &&
-                          (g.N <= 256 || g.N % 256 == 0) && -left <= kPadL && 127 + right + 8 <= kPadR && halo <= 120;
+                          (g.N <= 128 || g.N % 128 == 0) && -left <= kPadL && 127 + right + 8 <= kPadR && halo <= 120;
     const bool k_ok = (g.K % 128 == 0) || (en_m64 && (g.K == 64 || g.K == 32));
     L.tc_ok_wgr = en_wgr && shape_ok && k_ok;
   }
@@ -58,11 +58,35 @@ inline void tc_layer_eligibility(Layer& L) {
   L.nt_dgr = L.tc_ok_dgr ? tc_col_tile(L.dgr.creal) : 8;
 }
 
+// Epilogue-specialised instantiations of the convolution kernel.  P == nullptr: only raise the dynamic shared
+// memory limit of instantiation `f` (plan creation); otherwise launch it.
+template <int F>
+inline cudaError_t tc_conv_launch_one(const tc::ConvParams* P, int grid, size_t smem, cudaStream_t stream) {
+  if (!P) return cudaFuncSetAttribute(tc::conv_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  tc::conv_kernel<F><<<grid, tc::kConvThreads, smem, stream>>>(*P);
+  return cudaGetLastError();
+}
+inline cudaError_t tc_conv_dispatch(int f, const tc::ConvParams* P, int grid, size_t smem, cudaStream_t stream, void*) {
+  switch (f) {
+    case 0: return tc_conv_launch_one<0>(P, grid, smem, stream);
+    case 1: return tc_conv_launch_one<1>(P, grid, smem, stream);
+    case 2: return tc_conv_launch_one<2>(P, grid, smem, stream);
+    case 3: return tc_conv_launch_one<3>(P, grid, smem, stream);
+    case 6: return tc_conv_launch_one<6>(P, grid, smem, stream);
+    case 7: return tc_conv_launch_one<7>(P, grid, smem, stream);
+    case 8: return tc_conv_launch_one<8>(P, grid, smem, stream);
+    case 14: return tc_conv_launch_one<14>(P, grid, smem, stream);
+    case 15: return tc_conv_launch_one<15>(P, grid, smem, stream);
+    default: return P ? cudaErrorInvalidValue : cudaSuccess;
+  }
+}
+
 inline int tc_plan_init(vcd_plan* p) {
   // restrict the tensor-core path to a layer range (debug bisect)
   const int lo = tc_env_int("VCD_TC_MINLAYER", 0), hi = tc_env_int("VCD_TC_MAXLAYER", 1 << 30);
   (void)lo; (void)hi; (void)p;
-  cudaError_t e = cudaFuncSetAttribute(tc::conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  cudaError_t e = cudaSuccess;
+  for (int f = 0; f < 16 && e == cudaSuccess; ++f) e = tc_conv_dispatch(f, nullptr, 0, 0, 0, nullptr);
   if (e != cudaSuccess) return 1;
   e = cudaFuncSetAttribute(tc::wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   if (e != cudaSuccess) return 1;
@@ -161,9 +185,19 @@ inline int tc_run_conv(vcd_plan* p, const Layer& L, bool dgrad, const void* in, 
     }
   }
   const int grid = P.total_tiles < p->num_sms ? P.total_tiles : p->num_sms;
-  tc::conv_kernel<<<grid, tc::kConvThreads, smem, stream>>>(P);
+  // epilogue feature set -> instantiation (a superset is always valid: unused operands are null-checked or zero)
+  int f = (e.mask ? tc::EPI_MASK : 0) | (e.res_t ? tc::EPI_RES : 0) | (e.res2 ? tc::EPI_RES2 : 0) | (e.out_raw ? tc::EPI_RAW : 0);
+  if (f & (tc::EPI_RES2 | tc::EPI_RAW)) {
+    if (f & tc::EPI_RES) f |= tc::EPI_RES2 | tc::EPI_RAW;      // running-sum variants: {RES,RES2,RAW} (+MASK)
+  }
+  if (f == (tc::EPI_RAW | tc::EPI_RES2)) f = tc::EPI_RES | tc::EPI_RES2 | tc::EPI_RAW;
+  const bool known = f == 0 || f == 1 || f == 2 || f == 3 || f == 6 || f == 7 || f == 8 || f == 14 || f == 15;
+  if (!known) f = 15;
+  if (!e.mask && e.scale != 1.f) { snprintf(err, errn, "tc_run_conv(%s): scale without mask is not supported", L.name.c_str()); return 1; }
+  if ((f & tc::EPI_MASK) && !e.mask) { snprintf(err, errn, "tc_run_conv(%s): internal epilogue mismatch", L.name.c_str()); return 1; }
+  if ((f & tc::EPI_RES) && !e.res_t) { snprintf(err, errn, "tc_run_conv(%s): internal epilogue mismatch", L.name.c_str()); return 1; }
+  const cudaError_t ce = tc_conv_dispatch(f, &P, grid, smem, stream, nullptr);
   launches.fetch_add(1, std::memory_order_relaxed);
-  const cudaError_t ce = cudaGetLastError();
   if (ce != cudaSuccess) {
     snprintf(err, errn, "launch of tc::conv_kernel(%s) failed: %s", L.name.c_str(), cudaGetErrorString(ce));
     return 1;
@@ -179,30 +213,47 @@ inline int tc_run_wgrad(vcd_plan* p, const Layer& L, const void* in, const void*
   P.taps = g.taps; P.K = g.K; P.N = g.N; P.step = g.step; P.off0 = g.off0;
   P.minshift = g.step < 0 ? (g.taps - 1) * g.step : 0;
   P.B = B; P.L = Ld;
-  if (g.K % 128 == 0) { P.G = 1; P.mch = 16; P.n_mtiles = g.K / 128; }
-  else if (g.K == 64) { P.G = 2; P.mch = 8; P.n_mtiles = 1; }
-  else { P.G = 4; P.mch = 4; P.n_mtiles = 1; }
-  P.NT = g.N < 256 ? g.N : 256;
+  P.NT = g.N <= 128 ? g.N : 128;
   P.n_ntiles = g.N / P.NT;
-  P.n_slots = (g.taps + P.G - 1) / P.G;
-  const int cap = 512 / P.NT;
-  P.TG = cap < P.n_slots ? cap : P.n_slots;
-  P.n_tgroups = (P.n_slots + P.TG - 1) / P.TG;
-  uint32_t need = static_cast<uint32_t>(P.TG * P.NT), cols = 32;
-  while (cols < need) cols <<= 1;
-  P.tmem_cols = cols;
   const int astep = g.step < 0 ? -g.step : g.step;
   const int halo = (g.taps - 1) * astep;
+  // (M, G): instruction M and the number of tap copies stacked along it.  Small-N MMAs are bound by the operand
+  // reads from shared memory (~(M + NT)/4 clk), the stage load by ~27 B/clk: pick the cheaper bottleneck.
+  struct Cand { int M, G; };
+  Cand cands[5];
+  int nc = 0;
+  if (g.K % 128 == 0) cands[nc++] = {128, 1};
+  else if (g.K == 64) { cands[nc++] = {64, 1}; cands[nc++] = {128, 2}; }
+  else { cands[nc++] = {64, 1}; cands[nc++] = {64, 2}; cands[nc++] = {128, 4}; }
+  double best = 1e30;
+  for (int i = 0; i < nc; ++i) {
+    const int M = cands[i].M, G = cands[i].G;
+    const int mch = (g.K < 128 ? g.K : 128) / 8;
+    const double slots = (g.taps + G - 1) / G;
+    const double mma = slots * 8.0 * ((M + P.NT) / 4.0 > P.NT / 2.0 ? (M + P.NT) / 4.0 : P.NT / 2.0);   // per 128 rows
+    const double load = (static_cast<double>(G) * mch * (128 + halo) + (P.NT / 8) * 128.0) * 16.0 / 27.0;
+    const double cost = mma > load ? mma : load;
+    if (cost < best) { best = cost; P.M = M; P.G = G; P.mch = mch; }
+  }
+  P.n_mtiles = g.K >= 128 ? g.K / 128 : 1;
+  P.n_slots = (g.taps + P.G - 1) / P.G;
+  const int cap = P.M == 128 ? 512 / P.NT : 2 * (512 / P.NT);
+  P.TG = cap < P.n_slots ? cap : P.n_slots;
+  P.n_tgroups = (P.n_slots + P.TG - 1) / P.TG;
+  uint32_t need = static_cast<uint32_t>(P.M == 128 ? P.TG * P.NT : ((P.TG + 1) / 2) * P.NT), cols = 32;
+  while (cols < need) cols <<= 1;
+  P.tmem_cols = cols;
   auto stage_bytes = [&](int tk) {
     const int ri = (tk + halo + 7) / 8 * 8;
-    return static_cast<size_t>(P.mch) * ri * 16 * P.G + static_cast<size_t>(P.NT / 8) * tk * 16;
+    return static_cast<size_t>(P.G) * P.mch * ri * 16 + static_cast<size_t>(P.NT / 8) * tk * 16;
   };
-  P.TK = (128 + halo <= 256 && 3 * stage_bytes(128) <= 200 * 1024) ? 128 : 64;
+  P.TK = (4 * stage_bytes(128) <= 200 * 1024) ? 128 : 64;
   P.RI = (P.TK + halo + 7) / 8 * 8;
   const size_t stage = stage_bytes(P.TK);
   int NS = static_cast<int>((200 * 1024) / stage);
-  P.NS = NS > 6 ? 6 : (NS < 2 ? 2 : NS);
-  const size_t smem = 128 + P.NS * stage + (2 * P.NS + 1) * 8 + 16;
+  P.NS = NS > 8 ? 8 : (NS < 2 ? 2 : NS);
+  // slack: an M = 64 operand over a 32-channel tile reads 4 channel groups past the tile (garbage rows, unused)
+  const size_t smem = 128 + P.NS * stage + (2 * P.NS + 1) * 8 + 16 + 8 * 1024;
   if (smem > 227 * 1024) {
     snprintf(err, errn, "tc_run_wgrad(%s): shared memory budget exceeded (%zu bytes)", L.name.c_str(), smem);
     return 1;

@@ -169,6 +169,9 @@ __device__ __forceinline__ void ktrace(unsigned long long* buf, int slot) {
   }
 }
 
+// Compile-time epilogue features: unused operand paths (and their registers) vanish from the specialisation.
+enum : int { EPI_MASK = 1, EPI_RES = 2, EPI_RES2 = 4, EPI_RAW = 8 };
+
 struct EpiLoads {
   uint4 mask, rest;
   float4 r2a, r2b;
@@ -183,18 +186,25 @@ __device__ __forceinline__ void unpack8(const uint4& raw, float (&f)[8]) {
   }
 }
 
+template <int F>
 __device__ __forceinline__ void epi_prefetch(const Epilogue& e, size_t o, bool valid, EpiLoads& L) {
   if (!valid) return;
-  if (e.mask) L.mask = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(e.mask) + o));
-  if (e.res_t) L.rest = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(e.res_t) + o));
-  if (e.res2) {
-    L.r2a = __ldg(reinterpret_cast<const float4*>(e.res2 + o));
-    L.r2b = __ldg(reinterpret_cast<const float4*>(e.res2 + o) + 1);
+  if constexpr (F & EPI_MASK) L.mask = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(e.mask) + o));
+  if constexpr (F & EPI_RES) L.rest = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(e.res_t) + o));
+  if constexpr (F & EPI_RES2) {
+    if (e.res2) {
+      L.r2a = __ldg(reinterpret_cast<const float4*>(e.res2 + o));
+      L.r2b = __ldg(reinterpret_cast<const float4*>(e.res2 + o) + 1);
+    } else {
+      L.r2a = make_float4(0.f, 0.f, 0.f, 0.f);
+      L.r2b = L.r2a;
+    }
   }
 }
 
 // bias8: the 8 bias values (bias + per-batch bias) of this channel group, staged in shared memory per tile -- a
 // global bias load here would put a full memory latency on the critical path of every 16-column unit.
+template <int F>
 __device__ __forceinline__ void epi_finish(const Epilogue& e, const ConvGeo& g, int b, int ro, int ch0, size_t o,
                                            const EpiLoads& L, const float* bias8, float (&v)[8]) {
   {
@@ -203,29 +213,32 @@ __device__ __forceinline__ void epi_finish(const Epilogue& e, const ConvGeo& g, 
     v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
     v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
   }
-  if (e.mask) {
+  if constexpr (F & EPI_MASK) {
     float m[8];
     unpack8(L.mask, m);
 #pragma unroll
-    for (int n = 0; n < 8; ++n) v[n] *= (m[n] > 0.f ? 1.f : e.mask_slope);
+    for (int n = 0; n < 8; ++n) v[n] *= (m[n] > 0.f ? e.scale : e.mask_slope * e.scale);
   }
-#pragma unroll
-  for (int n = 0; n < 8; ++n) v[n] *= e.scale;
-  if (e.res_t) {
+  if constexpr (F & EPI_RES) {
     float t[8];
     unpack8(L.rest, t);
 #pragma unroll
     for (int n = 0; n < 8; ++n) v[n] += (t[n] > 0.f ? t[n] : t[n] * e.res_inv);
   }
-  if (e.res2) {
+  if constexpr (F & EPI_RES2) {
     v[0] += L.r2a.x; v[1] += L.r2a.y; v[2] += L.r2a.z; v[3] += L.r2a.w;
     v[4] += L.r2b.x; v[5] += L.r2b.y; v[6] += L.r2b.z; v[7] += L.r2b.w;
   }
-  if (e.out_raw) store8<float>(e.out_raw + o, v);
+  if constexpr (F & EPI_RAW) {
+    if (e.out_raw) store8<float>(e.out_raw + o, v);
+  }
   if (e.out_t) {
     float a[8];
 #pragma unroll
-    for (int n = 0; n < 8; ++n) a[n] = lrelu(v[n] * e.tscale, e.act_slope);
+    for (int n = 0; n < 8; ++n) {
+      const float x = v[n] * e.tscale;
+      a[n] = x > 0.f ? x : x * e.act_slope;
+    }
     if (e.zu > 0) {
       const int q = (ro + e.zp) / e.zu, r = (ro + e.zp) - q * e.zu;
       store8<bf16>(reinterpret_cast<bf16*>(e.out_t) + blk_off(b, r * g.creal + ch0, q, e.zu * g.creal, e.zLq), a);
@@ -235,6 +248,7 @@ __device__ __forceinline__ void epi_finish(const Epilogue& e, const ConvGeo& g, 
   }
 }
 
+template <int F>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_kernel(const ConvParams P) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -455,8 +469,8 @@ conv_kernel(const ConvParams P) {
       int u = half;
       if (u < n_units) {
         unit_coords(u, ro_c, v_c, o_c, t_c, ch_c);
-        epi_prefetch(e, o_c, v_c, cur[0]);
-        epi_prefetch(e, o_c + chunk_stride, v_c, cur[1]);
+        epi_prefetch<F>(e, o_c, v_c, cur[0]);
+        epi_prefetch<F>(e, o_c + chunk_stride, v_c, cur[1]);
       }
       mbar_wait(&acc_full[buf], use & 1);
       tc_fence_after();
@@ -465,8 +479,8 @@ conv_kernel(const ConvParams P) {
         const int un = u + 2;
         if (un < n_units) {
           unit_coords(un, ro_n, v_n, o_n, t_n, ch_n);
-          epi_prefetch(e, o_n, v_n, nxt[0]);
-          epi_prefetch(e, o_n + chunk_stride, v_n, nxt[1]);
+          epi_prefetch<F>(e, o_n, v_n, nxt[0]);
+          epi_prefetch<F>(e, o_n + chunk_stride, v_n, nxt[1]);
         }
         float acc[16];
         if (warp == 2 && lane == 0 && it == 0 && u < 6) ktrace(P.trace, 20 + u * 2);       // debug: unit start
@@ -478,7 +492,7 @@ conv_kernel(const ConvParams P) {
             float v[8];
 #pragma unroll
             for (int n = 0; n < 8; ++n) v[n] = acc[h * 8 + n];
-            epi_finish(e, P.g, b, ro_c, ch_c + h * 8, o_c + h * chunk_stride, cur[h],
+            epi_finish<F>(e, P.g, b, ro_c, ch_c + h * 8, o_c + h * chunk_stride, cur[h],
                        bias_s + (it & 1) * 128 + (ch_c - ch_tile) + h * 8, v);
           }
         }
@@ -500,13 +514,14 @@ conv_kernel(const ConvParams P) {
 
 // ---------------------------------------------------------------------------------------------------
 // Weight gradient:  dWp[j][c][n] += sum_t in[b][t + off0 + j*step][c] * dout[b][t][n]     (is = os = 1)
-// GEMM view: D[M][N = n] with the contraction over time.  Both operands are read MN-major straight from the
-// blocked layout (time rows are the 16-byte-strided K direction: LBO = 128 B, SBO = channel-group stride);
-// a tap is again a +16*shift byte offset on the A descriptor.
-// M is always 128: for K_conv >= 128 it is a 128-channel tile of one tap; for K_conv = 64 / 32 the A tile holds
-// G = 2 / 4 copies of the channel groups, copy g displaced by g*step rows, so ONE MMA covers G consecutive taps
-// (rows g*K .. g*K+K-1 of the accumulator belong to tap slot*G + g).
-// One CTA = (channel tile, column tile, slot group, split of the flattened (batch, time block) range); a single
+// GEMM view: D[M = c][N = n] per tap with the contraction over time.  Both operands are read MN-major straight
+// from the blocked layout (time rows are the 16-byte-strided K direction: LBO = 128 B, SBO = channel-group
+// stride); a tap is again a +16*shift byte offset on the A descriptor -- the `in` tile is loaded ONCE per stage.
+//   K_conv >= 128 : M = 128 (one 128-channel tile per CTA), accumulator of tap slot tl at TMEM columns tl*NT.
+//   K_conv <= 64  : M = 64; two accumulators share NT columns (lanes +0 / +16 of every 32-lane quadrant).  For
+//                   K_conv = 32 only rows 0..31 are meaningful (the upper half of the M = 64 operand reads
+//                   whatever follows the tile in shared memory; rows of D are independent).
+// One CTA = (channel tile, column tile, tap group, split of the flattened (batch, time block) range); a single
 // split stores its result directly, several splits combine with fp32 atomics (dWp zeroed by the caller).  Few,
 // long CTAs per layer are preferred: the host runs the weight-gradient kernels of independent layers
 // concurrently on side streams.
@@ -518,10 +533,11 @@ struct WgradParams {
   float* dwp;             // [taps][K][N] fp32
   int taps, K, N, step, off0, minshift;
   int B, L;               // L = rows of dout per batch item (the contraction length)
-  int G, mch, n_mtiles;   // tap copies per MMA, channel groups per copy, channel tiles
+  int M, mch, n_mtiles;   // instruction M (128 | 64), channel groups loaded per tile copy, channel tiles
+  int G;                  // tap copies stacked along M (G*K <= M): copy g is the tile displaced by g*step rows
+  int n_slots;            // accumulator slots in total = ceil(taps / G)
   int NT, n_ntiles;       // column tile (<= 256)
-  int TG, n_tgroups;      // accumulator slots per CTA and number of slot groups
-  int n_slots;            // total slots = ceil(taps / G)
+  int TG, n_tgroups;      // tap slots per CTA and number of tap groups
   int TK, RI;             // time rows per pipeline stage, rows of the A tile (TK + halo)
   int kb_per_item, n_splits, kb_per_split;  // the flattened (batch, time block) range is cut into n_splits
   int NS;
@@ -531,8 +547,6 @@ struct WgradParams {
 __global__ void __launch_bounds__(kThreads, 1)
 wgrad_kernel(const WgradParams P) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
-  // shfl-broadcast warp index: provably warp-uniform, so role branches are uniform and the compiler may use the
-  // uniform datapath (UR registers) for descriptor / address arithmetic inside them
   const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const uint32_t in_copy_bytes = static_cast<uint32_t>(P.mch) * P.RI * 16;
   const uint32_t in_bytes = in_copy_bytes * P.G;
@@ -597,7 +611,7 @@ wgrad_kernel(const WgradParams P) {
     }
   } else if (warp == 1) {
     // MMA issuer: converged warp, elected lane issues
-    const uint32_t idesc = make_idesc(128, P.NT, 1, 1);
+    const uint32_t idesc = make_idesc(P.M, P.NT, 1, 1);
     const uint64_t a_desc0 = make_desc(0, 128, static_cast<uint32_t>(P.RI) * 16);
     const uint64_t b_desc0 = make_desc(0, 128, static_cast<uint32_t>(P.TK) * 16);
     const int kks = P.TK / 16;
@@ -610,7 +624,9 @@ wgrad_kernel(const WgradParams P) {
       const uint64_t b_stage = b_desc0 + ((a_base + in_bytes) >> 4);
       for (int tl = 0; tl < nslots; ++tl) {
         const uint64_t a_slot = a_stage + static_cast<uint32_t>((slot0 + tl) * P.G * P.step - P.minshift);
-        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(tl * P.NT);
+        uint32_t d_tmem;
+        if (P.M == 128) d_tmem = tmem_base + static_cast<uint32_t>(tl * P.NT);
+        else d_tmem = tmem_base + static_cast<uint32_t>((tl >> 1) * P.NT) + (static_cast<uint32_t>((tl & 1) * 16) << 16);
         for (int kk = 0; kk < kks; ++kk) {
           const uint64_t ad = a_slot + kk * 16, bd = b_stage + kk * 16;
           const uint32_t accum = (kb | kk) != 0 ? 1u : 0u;
@@ -623,18 +639,36 @@ wgrad_kernel(const WgradParams P) {
     if (elect_one()) umma_commit(acc_full);
   } else {
     const int quad = warp & 3;
-    const int row = quad * 32 + lane;
     mbar_wait(acc_full, 0);
     tc_fence_after();
-    const int rows_per_tap = 128 / P.G;
-    const int g = row / rows_per_tap;
     for (int tl = 0; tl < nslots; ++tl) {
-      const int j = (slot0 + tl) * P.G + g;
-      const int c = P.G == 1 ? mtile * 128 + row : row - g * rows_per_tap;
-      const bool active = j < P.taps;
+      int row;             // row of the M x NT accumulator held by this thread
+      uint32_t col0;
+      bool active = true;
+      if (P.M == 128) {
+        row = quad * 32 + lane;
+        col0 = static_cast<uint32_t>(tl * P.NT);
+      } else {
+        // lanes 16..31 of a quadrant hold the odd slot of the column block; row i of D sits in lane i%16 of quadrant i/16
+        if ((tl & 1) != (lane >> 4)) active = false;
+        row = quad * 16 + (lane & 15);
+        col0 = static_cast<uint32_t>((tl >> 1) * P.NT);
+      }
+      int j, c;
+      if (P.G == 1) {
+        j = slot0 + tl;
+        c = mtile * P.M + row;
+        if (c >= P.K) active = false;
+      } else {             // G copies of a K-channel tile stacked along M
+        const int g = row / P.K;
+        j = (slot0 + tl) * P.G + g;
+        c = row - g * P.K;
+        if (g >= P.G) active = false;
+      }
+      if (j >= P.taps) active = false;
       for (int c16 = 0; c16 < P.NT / 16; ++c16) {
         float acc[16];
-        tmem_ld16(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(tl * P.NT + c16 * 16), acc);
+        tmem_ld16(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + col0 + c16 * 16, acc);
         if (active) {
           float* dst = P.dwp + (static_cast<size_t>(j) * P.K + c) * P.N + ntile * P.NT + c16 * 16;
           if (P.n_splits == 1) {

@@ -81,6 +81,38 @@ struct ProfScope {
 };
 }  // namespace
 
+// Phase timer (VCD_PHASES=1): CUDA events on the caller-visible stream at the boundaries of the forward core and
+// of every backward segment, in the real (graph-replay, multi-stream) execution mode.
+namespace {
+struct PhaseRec { std::string name; cudaEvent_t a, b; };
+std::vector<PhaseRec> g_phases;
+bool phases_on() { static const bool on = getenv("VCD_PHASES") != nullptr; return on; }
+struct PhaseScope {
+  cudaStream_t s; bool on;
+  PhaseScope(const char* name, cudaStream_t stream) : s(stream), on(phases_on()) {
+    if (!on) return;
+    PhaseRec r{name, nullptr, nullptr};
+    cudaEventCreate(&r.a); cudaEventCreate(&r.b);
+    cudaEventRecord(r.a, s);
+    g_phases.push_back(r);
+  }
+  ~PhaseScope() { if (on) cudaEventRecord(g_phases.back().b, s); }
+};
+}  // namespace
+extern "C" int vcd_phase_dump(int reset) {
+  cudaDeviceSynchronize();
+  for (const PhaseRec& r : g_phases) {
+    float t = 0.f;
+    cudaEventElapsedTime(&t, r.a, r.b);
+    fprintf(stderr, "[phase] %-28s %8.3f ms\n", r.name.c_str(), t);
+  }
+  if (reset) {
+    for (const PhaseRec& r : g_phases) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    g_phases.clear();
+  }
+  return 0;
+}
+
 extern "C" int vcd_profile_enable(int on) { g_prof_on = on != 0; return 0; }
 extern "C" int vcd_profile_num_classes(void) { return PC_COUNT; }
 extern "C" const char* vcd_profile_class_name(int c) { return c >= 0 && c < PC_COUNT ? kProfNames[c] : nullptr; }
@@ -634,6 +666,7 @@ extern "C" int vcd_fold_weights(vcd_plan* p, int mode, const float* const* param
     // pageable->device async copy is staged by the runtime before returning, so h_params may change later
     CU_TRY(cudaMemcpyAsync(p->d_params, p->h_params.data(), np * sizeof(float*), cudaMemcpyHostToDevice, stream));
   }
+  PhaseScope ph__("fold", stream);
   ProfScope ps__(PC_FOLD, 0, 4.0 * p->n_f32, stream);
   if (p->n_norm_blocks) {
     wn_norm_kernel<<<p->n_norm_blocks, 128, 0, stream>>>(p->d_norm_jobs, p->n_norm_jobs, p->d_params, p->d_norms);
@@ -943,7 +976,10 @@ extern "C" int vcd_forward(vcd_plan* p, int mode, const float* x, int64_t xs_b, 
   }
   return 0;
   };
-  TRY(run_graphed(p, GraphKey{0, mode, B, T, save ? 1 : 0, gvec ? 1 : 0, 0, ws, p->params_version}, stream, core));
+  {
+    PhaseScope ph__("forward core", stream);
+    TRY(run_graphed(p, GraphKey{0, mode, B, T, save ? 1 : 0, gvec ? 1 : 0, 0, ws, p->params_version}, stream, core));
+  }
   Lcur = T * p->hop;  // `core` is skipped on a graph replay: do not rely on its side effects
   {  // conv_post + tanh
     const int C = p->stages[S - 1].cout;
@@ -1135,7 +1171,10 @@ extern "C" int vcd_backward(vcd_plan* p, int mode, const float* dy, const float*
     }
     return 0;
     };
-    TRY(run_graphed(p, GraphKey{1 + seg, mode, B, T, 1, gvec ? 1 : 0, dx ? 1 : 0, ws, p->params_version}, stream, core));
+    {
+      PhaseScope ph__(("backward segment " + std::to_string(seg)).c_str(), stream);
+      TRY(run_graphed(p, GraphKey{1 + seg, mode, B, T, 1, gvec ? 1 : 0, dx ? 1 : 0, ws, p->params_version}, stream, core));
+    }
     if (seg == S) {  // kernels that touch caller-owned tensors: cond / conv_pre.bias gradients, dg, dx
       const Layer& L = p->layers[p->l_pre];
       {
