@@ -1,5 +1,6 @@
 // Host side of the tcgen05 kernels: layer eligibility, tile configuration, TMA descriptors, launches.
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include <atomic>
@@ -50,12 +51,41 @@ inline void tc_layer_eligibility(Layer& L) {
     const int left = g.off0 + (g.step < 0 ? (g.taps - 1) * g.step : 0);
     const int right = g.off0 + (g.step > 0 ? (g.taps - 1) * g.step : 0);
     const bool shape_ok = g.is == 1 && g.os == 1 && g.p == 0 && g.creal == g.N && g.N % 16 == 0 &&
-                          (g.N <= 128 || g.N % 128 == 0) && -left <= kPadL && 127 + right + 8 <= kPadR && halo <= 120;
+                          (g.N <= 128 || g.N % 128 == 0) && -left <= kPadL && 127 + right + 8 <= kPadR && (64 + halo + 7) / 8 * 8 <= 128;
     const bool k_ok = (g.K % 128 == 0) || (en_m64 && (g.K == 64 || g.K == 32));
     L.tc_ok_wgr = en_wgr && shape_ok && k_ok;
   }
   L.nt_fwd = L.tc_ok_fwd ? tc_col_tile(L.fwd.creal) : 8;
   L.nt_dgr = L.tc_ok_dgr ? tc_col_tile(L.dgr.creal) : 8;
+}
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline PFN_encodeTiled tc_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(p);
+  }
+  return fn;
+}
+
+// Row-padded blocked bf16 tensor [B][C/8][padded_len(L)][8] viewed as 8-byte elements:
+// dims (2*padded_len(L), C/8, B), box (2*rows, groups, 1) -> shared memory [groups][rows][16 B].
+inline bool tc_make_rows_map(CUtensorMap* map, const void* base, int B, int C, int L, int box_rows, int box_groups) {
+  const cuuint64_t lp = static_cast<cuuint64_t>(padded_len(L));
+  const cuuint64_t dims[3] = {2 * lp, static_cast<cuuint64_t>(C / 8), static_cast<cuuint64_t>(B)};
+  const cuuint64_t strides[2] = {lp * 16, static_cast<cuuint64_t>(C / 8) * lp * 16};
+  const cuuint32_t box[3] = {static_cast<cuuint32_t>(2 * box_rows), static_cast<cuuint32_t>(box_groups), 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  return tc_encode_fn() && tc_encode_fn()(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<void*>(base), dims, strides, box, estr,
+                                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 // Epilogue-specialised instantiations of the convolution kernel.  P == nullptr: only raise the dynamic shared
@@ -247,7 +277,11 @@ inline int tc_run_wgrad(vcd_plan* p, const Layer& L, const void* in, const void*
     const int ri = (tk + halo + 7) / 8 * 8;
     return static_cast<size_t>(P.G) * P.mch * ri * 16 + static_cast<size_t>(P.NT / 8) * tk * 16;
   };
-  P.TK = (4 * stage_bytes(128) <= 200 * 1024) ? 128 : 64;
+  // one tensor-TMA box per operand: at most 128 rows (256 8-byte elements) including the tap halo
+  P.TK = 64;
+  for (int tk : {112, 96, 80}) {
+    if ((tk + halo + 7) / 8 * 8 <= 128 && 4 * stage_bytes(tk) <= 200 * 1024) { P.TK = tk; break; }
+  }
   P.RI = (P.TK + halo + 7) / 8 * 8;
   const size_t stage = stage_bytes(P.TK);
   int NS = static_cast<int>((200 * 1024) / stage);
@@ -273,8 +307,23 @@ inline int tc_run_wgrad(vcd_plan* p, const Layer& L, const void* in, const void*
   P.in = static_cast<const bf16*>(in);
   P.dout = static_cast<const bf16*>(dout);
   P.Lin = Lin;
+  P.trace = nullptr;
+  {
+    static const char* want = getenv("VCD_KTRACE");
+    if (want && p->d_trace && (L.name + ":wgrad") == want) {
+      P.trace = p->d_trace;
+      fprintf(stderr, "[ktrace] %s:wgrad M=%d G=%d mch=%d NT=%d TG=%d tgroups=%d mtiles=%d ntiles=%d TK=%d RI=%d NS=%d splits=%d kb/split=%d taps=%d K=%d N=%d stage=%zu\n",
+              L.name.c_str(), P.M, P.G, P.mch, P.NT, P.TG, P.n_tgroups, P.n_mtiles, P.n_ntiles, P.TK, P.RI, P.NS, P.n_splits,
+              P.kb_per_split, g.taps, g.K, g.N, stage);
+    }
+  }
+  CUtensorMap tmIn, tmD;
+  if (!tc_make_rows_map(&tmIn, in, B, g.K, Lin, P.RI, P.mch) || !tc_make_rows_map(&tmD, dout, B, g.N, Ld, P.TK, P.NT / 8)) {
+    snprintf(err, errn, "tc_run_wgrad(%s): cuTensorMapEncodeTiled failed", L.name.c_str());
+    return 1;
+  }
   const long long grid = base_ctas * P.n_splits;
-  tc::wgrad_kernel<<<static_cast<unsigned>(grid), tc::kThreads, smem, stream>>>(P);
+  tc::wgrad_kernel<<<static_cast<unsigned>(grid), tc::kThreads, smem, stream>>>(tmIn, tmD, P);
   launches.fetch_add(1, std::memory_order_relaxed);
   const cudaError_t ce = cudaGetLastError();
   if (ce != cudaSuccess) {

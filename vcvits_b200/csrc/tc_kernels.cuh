@@ -12,6 +12,8 @@
 // The kernel is persistent: each CTA walks a static tile list; TMEM accumulators are double-buffered so the
 // epilogue of tile i overlaps the MMAs of tile i+1.
 #pragma once
+#include <cuda.h>
+
 #include "common.cuh"
 
 namespace vcd {
@@ -54,6 +56,14 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
+// Tensor TMA, 3-D map over a row-padded blocked tensor viewed as 8-byte elements (dims: 2*rows, channel group,
+// batch): ONE instruction fetches [groups][rows][16 B]; every (group) row run is a contiguous burst.
+__device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
 __device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(smem_u32(bar))
@@ -542,12 +552,14 @@ struct WgradParams {
   int kb_per_item, n_splits, kb_per_split;  // the flattened (batch, time block) range is cut into n_splits
   int NS;
   uint32_t tmem_cols;
+  unsigned long long* trace;
 };
 
 __global__ void __launch_bounds__(kThreads, 1)
-wgrad_kernel(const WgradParams P) {
+wgrad_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ CUtensorMap tmD, const WgradParams P) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) ktrace(P.trace, 0);
   const uint32_t in_copy_bytes = static_cast<uint32_t>(P.mch) * P.RI * 16;
   const uint32_t in_bytes = in_copy_bytes * P.G;
   const uint32_t d_bytes = static_cast<uint32_t>(P.NT / 8) * P.TK * 16;
@@ -569,6 +581,7 @@ wgrad_kernel(const WgradParams P) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) ktrace(P.trace, 1);
 
   // CTA coordinates
   int id = blockIdx.x;
@@ -583,11 +596,9 @@ wgrad_kernel(const WgradParams P) {
   const int nslots = min(P.TG, P.n_slots - slot0);
 
   if (warp == 0) {
-    // bulk-copy producer: one contiguous run of rows per channel group (row-padded layout); converged warp,
-    // elected lane issues
-    const int n_d = P.NT / 8;
-    const uint32_t in_cg_bytes = static_cast<uint32_t>(P.RI) * 16, d_cg_bytes = static_cast<uint32_t>(P.TK) * 16;
-    const size_t in_cg_stride = static_cast<size_t>(padded_len(P.Lin)) * 8, d_cg_stride = static_cast<size_t>(padded_len(P.L)) * 8;
+    // TMA producer (converged warp, elected lane issues).  A stage is G + 1 tensor-TMA instructions: issuing one
+    // 1-D bulk copy per (channel group) row run is limited to ~25 M copies/s per SM (measured), i.e. ~28 GB/s for
+    // the 1-2 KB runs of a 64-row time block.
     Pipe ps;
     for (int kb = 0; kb < kblocks; ++kb) {
       const int f = f_begin + kb;
@@ -595,16 +606,12 @@ wgrad_kernel(const WgradParams P) {
       const int t0 = (f - b * P.kb_per_item) * P.TK;
       mbar_wait(&empty[ps.stage], ps.phase ^ 1);
       uint8_t* st = smem + static_cast<size_t>(ps.stage) * stage_bytes;
-      const bf16* in0 = P.in + blk_row(b, mtile * P.mch, t0 + P.off0 + P.minshift, P.K, P.Lin);
-      const bf16* d0 = P.dout + blk_row(b, ntile * n_d, t0, P.N, P.L);
       if (elect_one()) {
         mbar_expect_tx(&full[ps.stage], stage_bytes);
         for (int g = 0; g < P.G; ++g)
-          for (int cg = 0; cg < P.mch; ++cg)
-            bulk_load(st + (g * P.mch + cg) * in_cg_bytes, in0 + cg * in_cg_stride + static_cast<ptrdiff_t>(g) * P.step * 8,
-                      in_cg_bytes, &full[ps.stage]);
-        for (int cg = 0; cg < n_d; ++cg)
-          bulk_load(st + in_bytes + cg * d_cg_bytes, d0 + cg * d_cg_stride, d_cg_bytes, &full[ps.stage]);
+          tma_load_3d(&tmIn, &full[ps.stage], st + g * in_copy_bytes, 2 * (t0 + P.off0 + P.minshift + g * P.step + kPadL),
+                      mtile * P.mch, b);
+        tma_load_3d(&tmD, &full[ps.stage], st + in_bytes, 2 * (t0 + kPadL), ntile * (P.NT / 8), b);
       }
       __syncwarp();
       ps.advance(P.NS);
@@ -619,6 +626,7 @@ wgrad_kernel(const WgradParams P) {
     for (int kb = 0; kb < kblocks; ++kb) {
       mbar_wait(&full[ps.stage], ps.phase);
       tc_fence_after();
+      if (lane == 0 && kb < 8) ktrace(P.trace, 8 + kb);        // stage kb landed
       const uint32_t a_base = smem_u32(smem + static_cast<size_t>(ps.stage) * stage_bytes);
       const uint64_t a_stage = a_desc0 + (a_base >> 4);
       const uint64_t b_stage = b_desc0 + ((a_base + in_bytes) >> 4);
@@ -637,10 +645,12 @@ wgrad_kernel(const WgradParams P) {
       ps.advance(P.NS);
     }
     if (elect_one()) umma_commit(acc_full);
+    if (lane == 0) ktrace(P.trace, 5);
   } else {
     const int quad = warp & 3;
     mbar_wait(acc_full, 0);
     tc_fence_after();
+    if (warp == 2 && lane == 0) ktrace(P.trace, 12);
     for (int tl = 0; tl < nslots; ++tl) {
       int row;             // row of the M x NT accumulator held by this thread
       uint32_t col0;
@@ -676,7 +686,9 @@ wgrad_kernel(const WgradParams P) {
             for (int n = 0; n < 16; n += 4) *reinterpret_cast<float4*>(dst + n) = make_float4(acc[n], acc[n + 1], acc[n + 2], acc[n + 3]);
           } else {
 #pragma unroll
-            for (int n = 0; n < 16; ++n) atomicAdd(dst + n, acc[n]);
+            for (int n = 0; n < 16; n += 4)
+              asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + n), "f"(acc[n]), "f"(acc[n + 1]),
+                           "f"(acc[n + 2]), "f"(acc[n + 3]) : "memory");
           }
         }
       }
@@ -685,6 +697,7 @@ wgrad_kernel(const WgradParams P) {
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, P.tmem_cols);
+  if (threadIdx.x == 0) ktrace(P.trace, 6);
 }
 
 }  // namespace tc
