@@ -90,7 +90,8 @@ wn_norm_kernel(const NormJob* __restrict__ jobs, int njobs, const float* const* 
   if (threadIdx.x == 0) norms[jb.norm_off + row] = sqrtf(red[0] + red[1] + red[2] + red[3]);
 }
 
-// grid = total 256-element blocks over all jobs, block = 256.
+// grid = total 256-thread blocks over all jobs, block = 256.  FMT_TC jobs: one thread per 8-element (16-byte) group of
+// the destination, so the bf16 stores are fully coalesced; FMT_F32 jobs: one thread per element.
 __global__ void __launch_bounds__(256)
 wn_pack_kernel(const PackJob* __restrict__ jobs, int njobs, const float* const* __restrict__ params,
                const float* __restrict__ norms, float* __restrict__ arena_f32, bf16* __restrict__ arena_bf16) {
@@ -101,31 +102,43 @@ wn_pack_kernel(const PackJob* __restrict__ jobs, int njobs, const float* const* 
   }
   const PackJob jb = jobs[lo];
   const long long e = static_cast<long long>(blockIdx.x - jb.first_block) * 256 + threadIdx.x;
-  if (e >= jb.numel) return;
-  int j, c, n;
+  const float* __restrict__ w = params[jb.p_w];
+  const float* __restrict__ gv = jb.p_g >= 0 ? params[jb.p_g] : nullptr;
   if (jb.fmt == FMT_F32) {
-    n = static_cast<int>(e % jb.N);
+    if (e >= jb.numel) return;
+    const int n = static_cast<int>(e % jb.N);
     const long long r = e / jb.N;
-    c = static_cast<int>(r % jb.K);
-    j = static_cast<int>(r / jb.K);
-  } else {  // [n/NT][tap][k/8][n%NT][k%8]
-    long long r = e;
-    const int c8 = static_cast<int>(r % 8); r /= 8;
-    const int nl = static_cast<int>(r % jb.NT); r /= jb.NT;
-    const int cg = static_cast<int>(r % (jb.K >> 3)); r /= (jb.K >> 3);
-    j = static_cast<int>(r % jb.taps);
-    const int nt = static_cast<int>(r / jb.taps);
-    c = cg * 8 + c8;
-    n = nt * jb.NT + nl;
+    const int c = static_cast<int>(r % jb.K);
+    const int j = static_cast<int>(r / jb.K);
+    int row; size_t idx;
+    float val = 0.f;
+    if (jb.map(j, c, n, row, idx)) {
+      val = w[idx];
+      if (gv) val *= gv[row] / norms[jb.norm_off + row];
+    }
+    arena_f32[jb.dst_off + e] = val;
+    return;
   }
-  int row; size_t idx;
-  float val = 0.f;
-  if (jb.map(j, c, n, row, idx)) {
-    val = params[jb.p_w][idx];
-    if (jb.p_g >= 0) val *= params[jb.p_g][row] / norms[jb.norm_off + row];
+  // [n/NT][tap][k/8][n%NT][k%8], 8 consecutive k per thread
+  if (e * 8 >= jb.numel) return;
+  long long r = e;
+  const int nl = static_cast<int>(r % jb.NT); r /= jb.NT;
+  const int cg = static_cast<int>(r % (jb.K >> 3)); r /= (jb.K >> 3);
+  const int j = static_cast<int>(r % jb.taps);
+  const int nt = static_cast<int>(r / jb.taps);
+  const int n = nt * jb.NT + nl;
+  float v[8];
+#pragma unroll
+  for (int c8 = 0; c8 < 8; ++c8) {
+    int row; size_t idx;
+    float val = 0.f;
+    if (jb.map(j, cg * 8 + c8, n, row, idx)) {
+      val = __ldg(w + idx);
+      if (gv) val *= __ldg(gv + row) / norms[jb.norm_off + row];
+    }
+    v[c8] = val;
   }
-  if (jb.fmt == FMT_F32) arena_f32[jb.dst_off + e] = val;
-  else arena_bf16[jb.dst_off + e] = __float2bfloat16_rn(val);
+  store8<bf16>(arena_bf16 + jb.dst_off + e * 8, v);
 }
 
 // ---- backward: packed weight gradients -> parameter gradients -----------------------------------------

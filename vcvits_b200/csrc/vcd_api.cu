@@ -383,7 +383,7 @@ extern "C" int vcd_plan_create(const vcd_config* cfg, vcd_plan** out_plan) {
       j.dst_off = fmt == FMT_F32 ? (dgrad ? L.f32_dgr : L.f32_fwd) : (dgrad ? L.tc_dgr : L.tc_fwd);
       j.numel = 1LL * g.taps * g.K * g.N;
       j.first_block = blk;
-      blk += static_cast<int>((j.numel + 255) / 256);
+      blk += static_cast<int>(((fmt == FMT_TC ? j.numel / 8 : j.numel) + 255) / 256);
       pj.push_back(j);
     };
     for (const Layer& L : p->layers) {
