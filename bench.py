@@ -299,7 +299,10 @@ def run_b200(args):
     # ---- roofline of the dominant kernel class, measured live with CUDA events around every launch ----
     peaks = load_peaks()
     roofline, classes = None, None
+    if world > 1:
+        dist.barrier()
     if rank == 0:
+        model.set_gradient_sync(None)  # rank-0-only profiling passes must not enter a collective
         lib.vcd_profile_enable(1)
         for _ in range(2):
             step_device()
@@ -372,10 +375,30 @@ def run_b200(args):
 
 def main():
     args = parse_args()
-    if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_b200(args)
+    # Only the JSON line may reach stdout: libraries (e.g. NCCL's version banner) write to fd 1 directly, so fd 1 is
+    # pointed at stderr for the whole run and the result is written to the saved descriptor.
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    real_stdout = os.fdopen(saved, "w")
+    import builtins
+    _print = builtins.print
+
+    def emit(*a, **k):
+        if k.get("file") is None and a and isinstance(a[0], str) and a[0].startswith("{"):
+            _print(*a, file=real_stdout, flush=True)
+        else:
+            _print(*a, **k)
+
+    builtins.print = emit
+    try:
+        if args.impl == "reference":
+            run_reference(args)
+        else:
+            run_b200(args)
+    finally:
+        builtins.print = _print
+        real_stdout.flush()
 
 
 if __name__ == "__main__":
