@@ -332,9 +332,14 @@ def run_b200(args):
             tm = sum(c["ms_per_step"] for c in tcs) * 1e-3
             ln = sum(c["launches_per_step"] for c in tcs)
             achieved = fl / tm / 1e12
+            traffic = None
+            tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+            if args.workload == "train_base_b16" and os.path.exists(tpath):
+                with open(tpath) as tf:
+                    traffic = json.load(tf).get("dram_bytes_per_launch")
             roofline = {"bound": "tensor", "kernel": "tc::conv_kernel / tc::wgrad_kernel (tcgen05 implicit GEMM)",
                         "achieved": achieved, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
-                        "frac": achieved / peaks["bf16_sustained"], "traffic": None,
+                        "frac": achieved / peaks["bf16_sustained"], "traffic": traffic,
                         "peak_source": f"{peaks['source']} sustained bf16 (kernel timed inside a long step)",
                         "gflop_per_launch": fl / ln / 1e9, "avg_launch_us": tm / ln * 1e6,
                         "share_of_step": tm / (sum(c["ms_per_step"] for c in classes) * 1e-3),

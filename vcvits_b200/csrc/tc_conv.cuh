@@ -165,6 +165,10 @@ inline int tc_run_conv(vcd_plan* p, const Layer& L, bool dgrad, const void* in, 
     const double total = waves * per_tile + (cb == 2 ? t_epi : 0.0) + (can_reside ? w_tile_bytes / 27.0 : 0.0);
     if (total < best) { best = total; MT = cand; bufs = cb; }
   }
+  {
+    static const int force_mt = tc_env_int("VCD_CONV_MT", 0);
+    if (force_mt > 0 && force_mt * P.BN <= 512 && force_mt <= mtiles) { MT = force_mt; bufs = 2 * MT * P.BN <= 512 ? 2 : 1; }
+  }
   P.MT = MT;
   P.acc_bufs = bufs;
   P.n_mgroups = (mtiles + MT - 1) / MT;
@@ -179,6 +183,10 @@ inline int tc_run_conv(vcd_plan* p, const Layer& L, bool dgrad, const void* in, 
   const size_t w_all = w_tap * g.taps * (g.K / P.KB);
   const size_t budget = 220 * 1024;
   P.NA = (g.K / P.KB) > 1 ? 3 : 2;
+  {
+    static const int force_na = tc_env_int("VCD_CONV_NA", 0);
+    if (force_na > 0) P.NA = force_na;
+  }
   if (P.NA * a_stage > budget / 2) P.NA = 2;
   P.w_resident = (P.n_tiles_n == 1 && w_all <= 100 * 1024 && P.NA * a_stage + w_all <= budget) ? 1 : 0;
   size_t w_region;
@@ -214,7 +222,12 @@ inline int tc_run_conv(vcd_plan* p, const Layer& L, bool dgrad, const void* in, 
               dgrad ? ":dgrad" : ":fwd", P.acc_bufs, P.BN, P.MT, P.KB, P.RA, P.NA, P.w_resident, P.TPS, P.NW, P.total_tiles, g.taps, g.K);
     }
   }
-  const int grid = P.total_tiles < p->num_sms ? P.total_tiles : p->num_sms;
+  // two co-resident CTAs per SM when both fit (small-channel layers): one CTA's prologue / epilogue overlaps the
+  // other's MMAs.  Needs <= ~110 KB shared memory, <= 256 TMEM columns and a <= 102-register instantiation.
+  static const int occ2 = tc_env_int("VCD_CONV_OCC2", 1);
+  const int ctas_per_sm = (occ2 && smem <= 110 * 1024 && P.tmem_cols <= 256) ? 2 : 1;
+  const int max_ctas = p->num_sms * ctas_per_sm;
+  const int grid = P.total_tiles < max_ctas ? P.total_tiles : max_ctas;
   // epilogue feature set -> instantiation (a superset is always valid: unused operands are null-checked or zero)
   int f = (e.mask ? tc::EPI_MASK : 0) | (e.res_t ? tc::EPI_RES : 0) | (e.res2 ? tc::EPI_RES2 : 0) | (e.out_raw ? tc::EPI_RAW : 0);
   if (f & (tc::EPI_RES2 | tc::EPI_RAW)) {
@@ -235,7 +248,7 @@ inline int tc_run_conv(vcd_plan* p, const Layer& L, bool dgrad, const void* in, 
   return 0;
 }
 
-inline int tc_run_wgrad(vcd_plan* p, const Layer& L, const void* in, const void* dout, float* dwp, int B, int Lin,
+inline int tc_run_wgrad(vcd_plan* p, const Layer& L, const void* in, const void* dout, float* dwp, float* dbias, int B, int Lin,
                         int Ld, cudaStream_t stream, std::atomic<uint64_t>& launches, char* err, size_t errn) {
   const ConvGeo& g = L.wgr;
   tc::WgradParams P{};
@@ -310,6 +323,8 @@ inline int tc_run_wgrad(vcd_plan* p, const Layer& L, const void* in, const void*
   P.in = static_cast<const bf16*>(in);
   P.dout = static_cast<const bf16*>(dout);
   P.Lin = Lin;
+  P.dbias = dbias;
+  P.cmod = L.cout;
   P.trace = nullptr;
   {
     static const char* want = getenv("VCD_KTRACE");

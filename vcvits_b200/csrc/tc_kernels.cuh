@@ -552,6 +552,8 @@ struct WgradParams {
   int kb_per_item, n_splits, kb_per_split;  // the flattened (batch, time block) range is cut into n_splits
   int NS;
   uint32_t tmem_cols;
+  float* dbias;           // bias gradient [cmod] (column sums of dout folded modulo cmod), or null
+  int cmod;
   unsigned long long* trace;
 };
 
@@ -571,8 +573,18 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ C
   uint64_t* acc_full = empty + P.NS;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
 
+  // CTA coordinates
+  int id = blockIdx.x;
+  const int split = id % P.n_splits; id /= P.n_splits;
+  const int tg = id % P.n_tgroups; id /= P.n_tgroups;
+  const int ntile = id % P.n_ntiles; id /= P.n_ntiles;
+  const int mtile = id;
+  // The bias gradient (column sums of dout) is folded into this kernel: the (mtile 0, tap group 0) CTA of every
+  // (column tile, split) sums its dout stages with the four warps that otherwise idle until the epilogue.
+  const bool do_colsum = P.dbias != nullptr && mtile == 0 && tg == 0;
+
   if (threadIdx.x == 0) {
-    for (int i = 0; i < P.NS; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < P.NS; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], do_colsum ? 5 : 1); }
     mbar_init(acc_full, 1);
     fence_barrier_init();
   }
@@ -582,13 +594,6 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ C
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   if (threadIdx.x == 0) ktrace(P.trace, 1);
-
-  // CTA coordinates
-  int id = blockIdx.x;
-  const int split = id % P.n_splits; id /= P.n_splits;
-  const int tg = id % P.n_tgroups; id /= P.n_tgroups;
-  const int ntile = id % P.n_ntiles; id /= P.n_ntiles;
-  const int mtile = id;
   const int f_begin = split * P.kb_per_split;
   const int f_end = min(P.B * P.kb_per_item, f_begin + P.kb_per_split);
   const int kblocks = f_end - f_begin;
@@ -648,6 +653,38 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ C
     if (lane == 0) ktrace(P.trace, 5);
   } else {
     const int quad = warp & 3;
+    if (do_colsum) {
+      // thread -> (channel group cg, row group rg); consecutive threads read consecutive 16-byte rows (conflict-free)
+      const int et = static_cast<int>(threadIdx.x) - 64;
+      const int n_cg = P.NT / 8, RG = 128 / n_cg;
+      const int cg = et / RG, rg = et - cg * RG;
+      float bs[8];
+#pragma unroll
+      for (int n = 0; n < 8; ++n) bs[n] = 0.f;
+      Pipe ps;
+      for (int kb = 0; kb < kblocks; ++kb) {
+        mbar_wait(&full[ps.stage], ps.phase);
+        const uint8_t* dt = smem + static_cast<size_t>(ps.stage) * stage_bytes + in_bytes + static_cast<size_t>(cg) * P.TK * 16;
+        for (int r = rg; r < P.TK; r += RG) {
+          float v[8];
+          unpack8(*reinterpret_cast<const uint4*>(dt + r * 16), v);
+#pragma unroll
+          for (int n = 0; n < 8; ++n) bs[n] += v[n];
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[ps.stage]);
+        ps.advance(P.NS);
+      }
+      // reduce over the RG row groups (RG consecutive lanes, RG in {8, 16, 32}) and add to the bias gradient
+#pragma unroll
+      for (int n = 0; n < 8; ++n) {
+        for (int o = RG >> 1; o > 0; o >>= 1) bs[n] += __shfl_xor_sync(0xffffffffu, bs[n], o);
+      }
+      if (rg == 0) {
+#pragma unroll
+        for (int n = 0; n < 8; ++n) atomicAdd(P.dbias + (ntile * P.NT + cg * 8 + n) % P.cmod, bs[n]);
+      }
+    }
     mbar_wait(acc_full, 0);
     tc_fence_after();
     if (warp == 2 && lane == 0) ktrace(P.trace, 12);

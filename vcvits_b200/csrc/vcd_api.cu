@@ -748,7 +748,10 @@ int run_wgrad(const Ctx& c, cudaStream_t st, const Layer& L, const void* in, con
   float* dwp = c.p->d_gscratch + L.dwp;
   if (c.mode == VCD_MODE_BF16 && L.tc_ok_wgr) {
     ProfScope ps__(PC_TC_WGRAD, flops, 0, st, (L.name + ":wgrad").c_str());
-    TRY(tc_run_wgrad(c.p, L, in, dout, dwp, c.B, Lin, Ld, st, g_launches, g_err, sizeof(g_err)));
+    // the bias gradient (column sums of dout) is produced by the same kernel
+    TRY(tc_run_wgrad(c.p, L, in, dout, dwp, L.dbias >= 0 ? c.p->d_gscratch + L.dbias : nullptr, c.B, Lin, Ld, st, g_launches,
+                     g_err, sizeof(g_err)));
+    return 0;
   } else {
     const long long total = 1LL * c.B * Ld;
     const int blocks_x = g.taps * (g.K / 8) * (g.N / 8);
