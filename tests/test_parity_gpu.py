@@ -157,3 +157,27 @@ def test_inference_and_training_workspaces_agree():
     assert torch.equal(y_inf, y_tr.detach())
     y_host = m.synthesize_host(x.cpu(), g.cpu())
     assert torch.equal(y_host, y_inf.cpu())
+
+
+def test_long_utterance_inference_bf16_and_fp32():
+    """infer.py shape (configs[3], scaled): 938-frame (10 s) latent, forward only, recycled workspaces."""
+    from oracle import mel_oracle as M
+    sd = O.seeded_state_dict(O.BASE48K_CFG, 1234, gain=1.2)
+    torch.manual_seed(42)
+    x, g = torch.randn(1, 128, 938), torch.randn(1, 256, 1)
+    y_ref, _ = oracle_run(O.BASE48K_CFG, sd, x, g, dtype=torch.float32)
+    from vcvits_b200 import Generator
+    for mode in ("fp32", "bf16"):
+        m = Generator(**O.BASE48K_CFG, mode=mode)
+        m.load_state_dict(sd)
+        m = m.cuda()
+        with torch.no_grad():
+            y = m(x.cuda(), g.cuda()).cpu()
+        assert y.shape == (1, 1, 938 * 512)
+        err = float((y - y_ref).abs().max())
+        if mode == "fp32":
+            assert err <= 1e-4 and err <= max(1e-5 * float(y_ref.abs().max()), 5e-7), err
+        else:
+            assert err <= 1e-2, err
+            assert M.log_mel_l1_relative(y[:, 0], y_ref[:, 0], num_mels=128) <= 0.01
+        del m

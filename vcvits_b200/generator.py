@@ -138,18 +138,23 @@ class _DecoderFunction(torch.autograd.Function):
         flat = torch.empty(module._flat_numel, dtype=torch.float32, device=dev)
         views = module._grad_views(flat)
         ptrs = (C.c_void_p * len(views))(*[v.data_ptr() for v in views])
-        reducer = SegmentReducer(flat, module._segment_ranges, module._grad_sync_group)
-        for seg in range(module._num_segments):
+        def run(mask):
             _lib.check(lib.vcd_backward(plan, module._mode, dy.data_ptr(), y.data_ptr(),
                                         gf.data_ptr() if gf is not None else None,
                                         dx.data_ptr() if dx is not None else None,
                                         dg.data_ptr() if dg is not None else None,
-                                        ptrs, ctx.ws.data_ptr(), ctx.ws_bytes, B, T, 1 << seg, stream),
-                       "vcd_backward")
-            # gradients of this segment are final: all-reduce them on NCCL's stream while the next segment's
-            # kernels run (replaces the DDP reducer implied by train.py:99-100)
-            reducer.segment_done(seg)
-        reducer.finish()
+                                        ptrs, ctx.ws.data_ptr(), ctx.ws_bytes, B, T, mask, stream), "vcd_backward")
+
+        if module._grad_sync_group is None:
+            run(0xFFFFFFFF)
+        else:
+            reducer = SegmentReducer(flat, module._segment_ranges, module._grad_sync_group)
+            for seg in range(module._num_segments):
+                run(1 << seg)
+                # gradients of this segment are final: all-reduce them on NCCL's stream while the next segment's
+                # kernels run (replaces the DDP reducer implied by train.py:99-100)
+                reducer.segment_done(seg)
+            reducer.finish()
         module._give_workspace(ctx.ws)
         ctx.ws = None
         grads = [v if p.requires_grad else None for v, p in zip(views, module._ordered_params())]
@@ -220,6 +225,7 @@ class Generator(nn.Module):
             self.cond = _ConvParams(*_default_conv_init(c0, self.gin_channels, 1))
 
         self._plans = {}
+        self._param_cache = None
         self._fold_key = None
         self._ws_cache = {}
         self._ws_pool = {}
@@ -320,18 +326,24 @@ class Generator(nn.Module):
                 raise RuntimeError("backward segments do not cover every parameter")
             self._flat_offsets = [order[i] for i in range(n)]
             self._flat_numel = off
+            by_off = sorted(range(n), key=lambda i: order[i])
+            self._flat_sizes = [own[names[i]].numel() for i in by_off]
+            pos = {i: k for k, i in enumerate(by_off)}
+            self._flat_index = [(pos[i], tuple(own[names[i]].shape)) for i in range(n)]
             self._segment_ranges = ranges
         return plan
 
     def _ordered_params(self) -> List[torch.Tensor]:
-        own = dict(self.named_parameters())
-        return [own[n] for n in self._names]
+        cached = self._param_cache
+        if cached is None:
+            own = dict(self.named_parameters())
+            cached = self._param_cache = [own[n] for n in self._names]
+        return cached
 
     def _grad_views(self, flat: torch.Tensor) -> List[torch.Tensor]:
-        out = []
-        for p, off in zip(self._ordered_params(), self._flat_offsets):
-            out.append(flat[off: off + p.numel()].view(p.shape))
-        return out
+        # one split call in flat-buffer order, then a view per parameter (parameter-table order)
+        pieces = flat.split_with_sizes(self._flat_sizes)
+        return [pieces[k].view(shape) for k, shape in self._flat_index]
 
     def _fold_if_needed(self, params: Sequence[torch.Tensor]) -> None:
         key = (self._mode, tuple((p.data_ptr(), p._version) for p in params))
@@ -372,6 +384,7 @@ class Generator(nn.Module):
     def _apply(self, fn, *args, **kwargs):
         out = super()._apply(fn, *args, **kwargs)
         self._fold_key = None
+        self._param_cache = None
         self._ws_cache = {}
         self._ws_pool = {}
         return out
@@ -429,6 +442,7 @@ class Generator(nn.Module):
     def __getstate__(self):
         state = dict(self.__dict__)
         state["_plans"] = {}        # library handles are per process / per device; rebuilt lazily
+        state["_param_cache"] = None
         state["_ws_cache"] = {}
         state["_ws_pool"] = {}
         state["_fold_key"] = None
