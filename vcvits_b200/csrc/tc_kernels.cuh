@@ -87,6 +87,19 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Same, with the descriptors given as (lo, hi) halves: the hi words (LBO/SBO/version) are loop invariant, so the
+// issue loop only performs 32-bit adds on the start-address words.
+__device__ __forceinline__ void umma_bf16_split(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                                uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+      ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // mbarrier arrives when every previously issued tcgen05.mma of this thread has completed.
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -296,7 +309,8 @@ conv_kernel(const ConvParams P) {
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  // shfl-broadcast: provably warp-uniform, so TMEM addresses stay in uniform registers in the MMA issue loop
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
   if (threadIdx.x == 0) ktrace(P.trace, 1);
 
   if (warp == 0) {
@@ -387,34 +401,39 @@ conv_kernel(const ConvParams P) {
         mbar_wait(&fullA[pa.stage], pa.phase);
         tc_fence_after();
         if (it == 0 && kb == 0 && lane == 0) ktrace(P.trace, 4);
-        const uint64_t a_stage_desc = a_desc0 + (smem_u32(a_smem + static_cast<size_t>(pa.stage) * a_stage_bytes) >> 4);
+        const uint32_t a_hi = static_cast<uint32_t>(a_desc0 >> 32), w_hi = static_cast<uint32_t>(w_desc0 >> 32);
+        const uint32_t a_stage_lo = static_cast<uint32_t>(a_desc0) + (smem_u32(a_smem + static_cast<size_t>(pa.stage) * a_stage_bytes) >> 4);
         int j = 0;
         while (j < P.g.taps) {
           int nj;
-          uint64_t w_desc;
+          uint32_t w_lo;
           if (P.w_resident) {
             nj = P.g.taps;
-            w_desc = w_desc0 + ((smem_u32(w_smem) >> 4) + static_cast<uint32_t>(kb) * w_tap16);
+            w_lo = static_cast<uint32_t>(w_desc0) + (smem_u32(w_smem) >> 4) + static_cast<uint32_t>(kb) * w_tap16;
           } else {
             nj = min(P.TPS, P.g.taps - j);
             mbar_wait(&fullW[pw.stage], pw.phase);
             tc_fence_after();
-            w_desc = w_desc0 + (smem_u32(w_smem + static_cast<size_t>(pw.stage) * P.TPS * w_tap_bytes) >> 4);
+            w_lo = static_cast<uint32_t>(w_desc0) + (smem_u32(w_smem + static_cast<size_t>(pw.stage) * P.TPS * w_tap_bytes) >> 4);
           }
           // resident layout is [tap][K/8][BN][8]: consecutive taps are kblocks*w_tap16 apart
           const uint32_t tap_stride16 = P.w_resident ? w_tap16 * kblocks : w_tap16;
+          uint32_t a_tap = a_stage_lo + static_cast<uint32_t>(j * P.g.step - P.minshift);
           for (int jj = 0; jj < nj; ++jj, ++j) {
-            const uint64_t a_tap = a_stage_desc + static_cast<uint32_t>(j * P.g.step - P.minshift);
-            const uint64_t w_tap = w_desc + jj * tap_stride16;
+            uint32_t d_tmem = d_tile, a_mt = a_tap;
             for (int mt = 0; mt < P.MT; ++mt) {
-              const uint32_t d_tmem = d_tile + static_cast<uint32_t>(mt * P.BN);
-              const uint64_t a_mt = a_tap + mt * a_region16;
+              uint32_t ad = a_mt, bd = w_lo;
               for (int kk = 0; kk < kk_per_block; ++kk) {
-                const uint64_t ad = a_mt + kk * a_kk16, bd = w_tap + kk * w_kk16;
                 const uint32_t accum = (kb | j | kk) != 0 ? 1u : 0u;
-                if (elect_one()) umma_bf16(d_tmem, ad, bd, idesc, accum);
+                if (elect_one()) umma_bf16_split(d_tmem, ad, a_hi, bd, w_hi, idesc, accum);
+                ad += a_kk16;
+                bd += w_kk16;
               }
+              d_tmem += static_cast<uint32_t>(P.BN);
+              a_mt += a_region16;
             }
+            w_lo += tap_stride16;
+            a_tap += static_cast<uint32_t>(P.g.step);
           }
           if (!P.w_resident) {
             if (elect_one()) umma_commit(&emptyW[pw.stage]);
