@@ -611,7 +611,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ C
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
   if (threadIdx.x == 0) ktrace(P.trace, 1);
   const int f_begin = split * P.kb_per_split;
   const int f_end = min(P.B * P.kb_per_item, f_begin + P.kb_per_split);
@@ -652,18 +652,21 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ C
       tc_fence_after();
       if (lane == 0 && kb < 8) ktrace(P.trace, 8 + kb);        // stage kb landed
       const uint32_t a_base = smem_u32(smem + static_cast<size_t>(ps.stage) * stage_bytes);
-      const uint64_t a_stage = a_desc0 + (a_base >> 4);
-      const uint64_t b_stage = b_desc0 + ((a_base + in_bytes) >> 4);
+      const uint32_t a_hi = static_cast<uint32_t>(a_desc0 >> 32), b_hi = static_cast<uint32_t>(b_desc0 >> 32);
+      const uint32_t b_stage = static_cast<uint32_t>(b_desc0) + ((a_base + in_bytes) >> 4);
+      uint32_t a_slot = static_cast<uint32_t>(a_desc0) + (a_base >> 4) + static_cast<uint32_t>(slot0 * P.G * P.step - P.minshift);
       for (int tl = 0; tl < nslots; ++tl) {
-        const uint64_t a_slot = a_stage + static_cast<uint32_t>((slot0 + tl) * P.G * P.step - P.minshift);
         uint32_t d_tmem;
         if (P.M == 128) d_tmem = tmem_base + static_cast<uint32_t>(tl * P.NT);
         else d_tmem = tmem_base + static_cast<uint32_t>((tl >> 1) * P.NT) + (static_cast<uint32_t>((tl & 1) * 16) << 16);
+        uint32_t ad = a_slot, bd = b_stage;
         for (int kk = 0; kk < kks; ++kk) {
-          const uint64_t ad = a_slot + kk * 16, bd = b_stage + kk * 16;
           const uint32_t accum = (kb | kk) != 0 ? 1u : 0u;
-          if (elect_one()) umma_bf16(d_tmem, ad, bd, idesc, accum);
+          if (elect_one()) umma_bf16_split(d_tmem, ad, a_hi, bd, b_hi, idesc, accum);
+          ad += 16;
+          bd += 16;
         }
+        a_slot += static_cast<uint32_t>(P.G * P.step);
       }
       if (elect_one()) umma_commit(&empty[ps.stage]);
       ps.advance(P.NS);
