@@ -310,7 +310,8 @@ inline int tc_run_wgrad(vcd_plan* p, const Layer& L, const void* in, const void*
   // ~48 CTAs per layer for large weight tensors (the split partials are combined with fp32 reductions), up to one
   // CTA per SM when the weight gradient is small (C <= 64: the kernel is bound by the per-SM load rate)
   static const int env_ctas = tc_env_int("VCD_WGRAD_CTAS", 0);
-  const int target_ctas = env_ctas > 0 ? env_ctas : (static_cast<long long>(g.taps) * g.K * g.N <= 64 * 64 * 11 ? 144 : 48);
+  static const int env_small = tc_env_int("VCD_WGRAD_CTAS_SMALL", 64), env_big = tc_env_int("VCD_WGRAD_CTAS_BIG", 32);
+  const int target_ctas = env_ctas > 0 ? env_ctas : (static_cast<long long>(g.taps) * g.K * g.N <= 64 * 64 * 11 ? env_small : env_big);
   const long long base_ctas = 1LL * P.n_mtiles * P.n_ntiles * P.n_tgroups;
   P.kb_per_item = (Ld + P.TK - 1) / P.TK;
   const long long total_kb = 1LL * B * P.kb_per_item;

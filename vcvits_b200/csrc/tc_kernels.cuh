@@ -159,13 +159,13 @@ struct Pipe {
 // ---------------------------------------------------------------------------------------------------
 // Forward / data-gradient convolution (generalised geometry with is == 1).
 //
-// Warp roles (kConvThreads = 320): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer,
+// Warp roles (kConvThreads = 352): warp 0 = activation producer, warp 10 = weight producer, warp 1 = TMEM allocator + MMA issuer,
 // warps 2..9 = epilogue (two warps per TMEM lane quadrant, interleaved over 16-column units).
 // Weights: if the whole [taps][K][BN] set of the column tile fits (and every tile of the launch uses the same
 // column tile) it is loaded ONCE per CTA and stays resident; otherwise it streams through a ring whose stages
 // hold several taps of one K block (fewer barrier round trips than one tap per stage).
 // ---------------------------------------------------------------------------------------------------
-constexpr int kConvThreads = 320;
+constexpr int kConvThreads = 352;
 
 struct ConvParams {
   ConvGeo g;
@@ -314,24 +314,14 @@ conv_kernel(const ConvParams P) {
   if (threadIdx.x == 0) ktrace(P.trace, 1);
 
   if (warp == 0) {
-    // ===================== bulk-copy (TMA) producer: converged warp, elected lane issues =====================
+    // ===================== activation producer: converged warp, elected lane issues =====================
     // An A region is (KB/8) channel groups x RA rows; in the row-padded global layout each channel group's rows
-    // are one contiguous run, so the region is KB/8 1-D bulk copies.
-    if (P.w_resident) {  // whole weight set of column tile 0 (n_tiles_n == 1)
-      const uint32_t total = w_region_bytes;
-      if (elect_one()) {
-        mbar_expect_tx(&fullW[0], total);
-        for (uint32_t off = 0; off < total; off += 65536u)
-          bulk_load(w_smem + off, reinterpret_cast<const uint8_t*>(P.w) + off, min(65536u, total - off), &fullW[0]);
-      }
-      __syncwarp();
-    }
+    // are one contiguous run, so the region is KB/8 1-D bulk copies (TMA bulk engine, mbarrier complete_tx).
     const int cgs = P.KB / 8;
     const uint32_t cg_bytes = static_cast<uint32_t>(P.RA) * 16;
     const size_t cg_stride_g = static_cast<size_t>(padded_len(P.Lin)) * 8;   // elements between channel groups
-    Pipe pa, pw;
+    Pipe pa;
     for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
-      const int nt = tile % P.n_tiles_n;
       const int rest = tile / P.n_tiles_n;
       const int mg = rest % P.n_mgroups;
       const int b = rest / P.n_mgroups;
@@ -353,14 +343,30 @@ conv_kernel(const ConvParams P) {
         __syncwarp();
         if (tile == static_cast<int>(blockIdx.x) && kb == 0 && lane == 0) ktrace(P.trace, 2);
         pa.advance(P.NA);
-        if (!P.w_resident) {
+      }
+    }
+  } else if (warp == 10) {
+    // ===================== weight producer (own warp: never queues behind the activation copies) =====================
+    if (P.w_resident) {  // whole weight set of column tile 0 (n_tiles_n == 1), loaded once
+      const uint32_t total = w_region_bytes;
+      if (elect_one()) {
+        mbar_expect_tx(&fullW[0], total);
+        for (uint32_t off = 0; off < total; off += 65536u)
+          bulk_load(w_smem + off, reinterpret_cast<const uint8_t*>(P.w) + off, min(65536u, total - off), &fullW[0]);
+      }
+      __syncwarp();
+    } else {
+      Pipe pw;
+      const size_t tap_stride_g = static_cast<size_t>(P.g.K / 8) * P.BN * 8;
+      for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+        const int nt = tile % P.n_tiles_n;
+        for (int kb = 0; kb < kblocks; ++kb) {
           for (int j0 = 0; j0 < P.g.taps; j0 += P.TPS) {
             const int nj = min(P.TPS, P.g.taps - j0);
             mbar_wait(&emptyW[pw.stage], pw.phase ^ 1);
             uint8_t* dst = w_smem + static_cast<size_t>(pw.stage) * P.TPS * w_tap_bytes;
             const bf16* src = P.w + ((static_cast<size_t>(nt) * P.g.taps + j0) * (P.g.K / 8) +
                                      static_cast<size_t>(kb) * (P.KB / 8)) * P.BN * 8;
-            const size_t tap_stride_g = static_cast<size_t>(P.g.K / 8) * P.BN * 8;
             if (elect_one()) {
               mbar_expect_tx(&fullW[pw.stage], nj * w_tap_bytes);
               if (kblocks == 1) {  // taps are contiguous in the packed weights: one copy per stage
@@ -447,7 +453,7 @@ conv_kernel(const ConvParams P) {
       if (it < 4 && lane == 0) ktrace(P.trace, 8 + it);       // MMAs of tile `it` issued
     }
     if (lane == 0) ktrace(P.trace, 5);
-  } else {
+  } else if (warp >= 2 && warp <= 9) {
     // ===================== epilogue warps =====================
     const int quad = warp & 3;               // TMEM lane quadrant this warp may access
     const int half = (warp - 2) >> 2;        // two warps per quadrant interleave over 16-column units
