@@ -181,3 +181,72 @@ def test_long_utterance_inference_bf16_and_fp32():
             assert err <= 1e-2, err
             assert M.log_mel_l1_relative(y[:, 0], y_ref[:, 0], num_mels=128) <= 0.01
         del m
+
+
+@pytest.mark.parametrize("cfg_name", ["SMALL_CFG", "SMALL2_CFG"])
+def test_tensor_core_path_against_ffma_path(cfg_name):
+    """bf16 mode (tcgen05 kernels for every conv / wgrad of this config) vs fp32 FFMA mode on the GPU and vs the
+    oracle: forward within bf16 noise, parameter-gradient direction preserved.  Covers ResBlock1 and ResBlock2."""
+    cfg = getattr(O, cfg_name)
+    sd = O.seeded_state_dict(cfg, 77, gain=1.3)
+    torch.manual_seed(4)
+    x, g = torch.randn(3, 64, 45), torch.randn(3, 16, 1)
+    dy = torch.randn(3, 1, 45 * 16)
+    y16, g16, m = b200_run(cfg, sd, x, g, dy, mode="bf16")
+    assert any("tcgen05" in s for s in m.layer_paths())
+    y32, g32, _ = b200_run(cfg, sd, x, g, dy, mode="fp32")
+    y_ref, gref = oracle_run(cfg, sd, x, g, dy)
+    assert float((y32.double() - y_ref).abs().max()) <= 1e-4
+    assert float((y16.double() - y_ref).abs().max()) <= 1e-2
+    a = torch.cat([g16[n].flatten() for n in sorted(gref)]).double()
+    b = torch.cat([gref[n].flatten() for n in sorted(gref)]).double()
+    assert float(torch.dot(a, b) / (a.norm() * b.norm())) >= 0.99
+
+
+def test_error_paths_return_messages():
+    """C-ABI error behaviour: non-zero return + message, nothing aborts."""
+    import ctypes as C
+    from vcvits_b200 import Generator, _lib
+    lib = _lib.load()
+    bad = Generator(**dict(O.TINY_CFG, upsample_initial_channel=24))  # 24 -> 12 -> 6 channels: not multiples of 8
+    with pytest.raises(RuntimeError, match="multiple of"):
+        bad.cuda()(torch.zeros(1, 16, 4, device="cuda"))
+    m = Generator(**O.TINY_CFG, mode="fp32").cuda()
+    plan = m._plan_for(torch.device("cuda", 0))
+    # forward before fold
+    y = torch.empty(1, 1, 32, device="cuda")
+    x = torch.zeros(1, 16, 4, device="cuda")
+    ws = torch.empty(1 << 20, dtype=torch.uint8, device="cuda")
+    rc = lib.vcd_forward(plan, 0, x.data_ptr(), 64, 4, 1, None, y.data_ptr(), ws.data_ptr(), ws.numel(), 1, 4, 0, None)
+    assert rc != 0 and b"vcd_fold_weights" in lib.vcd_last_error()
+    m(x)  # folds
+    rc = lib.vcd_forward(plan, 0, x.data_ptr(), 64, 4, 1, None, y.data_ptr(), ws.data_ptr(), 16, 1, 4, 0, None)
+    assert rc != 0 and b"workspace too small" in lib.vcd_last_error()
+    with pytest.raises(ValueError):
+        m(torch.zeros(1, 7, 4, device="cuda"))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        m(torch.zeros(1, 16, 4))
+
+
+def test_user_side_cuda_graph_capture_of_inference():
+    """The library must cooperate when the caller captures its own CUDA graph around the decoder call."""
+    from vcvits_b200 import Generator
+    sd = O.seeded_state_dict(O.SMALL_CFG, 3, gain=1.3)
+    m = Generator(**O.SMALL_CFG, mode="bf16")
+    m.load_state_dict(sd)
+    m = m.cuda()
+    x = torch.randn(2, 64, 20, device="cuda")
+    g = torch.randn(2, 16, 1, device="cuda")
+    with torch.no_grad():
+        y_eager = m(x, g).clone()
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            m(x, g)  # warm-up on the side stream
+        torch.cuda.current_stream().wait_stream(s)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            y_static = m(x, g)
+        graph.replay()
+        torch.cuda.synchronize()
+    assert torch.equal(y_static, y_eager)

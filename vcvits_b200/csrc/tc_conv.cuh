@@ -177,7 +177,10 @@ inline int tc_run_conv(vcd_plan* p, const Layer& L, bool dgrad, const void* in, 
   while (cols < static_cast<uint32_t>(bufs * MT * P.BN)) cols <<= 1;
   P.tmem_cols = cols;
   // keep two activation stages within ~96 KB so the weight ring keeps most of the shared memory
-  while (P.KB > 16 && 2 * static_cast<size_t>(MT) * (P.KB / 8) * P.RA * 16 > 96 * 1024) P.KB /= 2;
+  // (streamed weights: keep them even smaller -- bytes in flight of the weight ring are what bounds those layers)
+  static const int amax_kb = tc_env_int("VCD_CONV_AMAX_KB", 96);
+  const size_t a_cap = (can_reside ? 96 : static_cast<size_t>(amax_kb)) * 1024;
+  while (P.KB > 16 && 2 * static_cast<size_t>(MT) * (P.KB / 8) * P.RA * 16 > a_cap) P.KB /= 2;
   const size_t a_stage = static_cast<size_t>(MT) * (P.KB / 8) * P.RA * 16;
   const size_t w_tap = static_cast<size_t>(P.KB / 8) * P.BN * 16;
   const size_t w_all = w_tap * g.taps * (g.K / P.KB);

@@ -829,6 +829,10 @@ template <class F>
 int run_graphed(vcd_plan* p, const GraphKey& key, cudaStream_t stream, F&& enqueue) {
   static const int enabled = tc_env_int("VCD_GRAPHS", 1);
   if (!enabled || g_prof_on) return enqueue();
+  {  // the caller may itself be capturing this stream (its own CUDA graph of the training step): just enqueue
+    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(stream, &st) != cudaSuccess || st != cudaStreamCaptureStatusNone) return enqueue();
+  }
   auto it = p->graphs.find(key);
   if (it != p->graphs.end()) {
     CU_TRY(cudaGraphLaunch(it->second, stream));
