@@ -250,3 +250,19 @@ def test_user_side_cuda_graph_capture_of_inference():
         graph.replay()
         torch.cuda.synchronize()
     assert torch.equal(y_static, y_eager)
+
+
+@pytest.mark.parametrize("B,T", [(1, 1), (3, 7), (1, 130), (2, 257)])
+def test_tensor_core_path_ragged_shapes(B, T):
+    """tcgen05 kernels on lengths that do not fill a 128-row tile / cross tile and pad boundaries."""
+    sd = O.seeded_state_dict(O.SMALL_CFG, 5, gain=1.3)
+    torch.manual_seed(B * 1000 + T)
+    x, g = torch.randn(B, 64, T), torch.randn(B, 16, 1)
+    dy = torch.randn(B, 1, T * 16)
+    y16, g16, _ = b200_run(O.SMALL_CFG, sd, x, g, dy, mode="bf16")
+    y_ref, gref = oracle_run(O.SMALL_CFG, sd, x, g, dy)
+    assert float((y16.double() - y_ref).abs().max()) <= 1e-2
+    num = sum(float((g16[n].double() - gref[n]).pow(2).sum()) for n in gref)
+    den = sum(float(gref[n].pow(2).sum()) for n in gref)
+    assert (num / den) ** 0.5 <= 0.12
+    assert all(torch.isfinite(v).all() for v in g16.values())
