@@ -276,8 +276,12 @@ inline int tc_run_wgrad(vcd_plan* p, const Layer& L, const void* in, const void*
     const int M = cands[i].M, G = cands[i].G;
     const int mch = (g.K < 128 ? g.K : 128) / 8;
     const double slots = (g.taps + G - 1) / G;
-    const double mma = slots * 8.0 * ((M + P.NT) / 4.0 > P.NT / 2.0 ? (M + P.NT) / 4.0 : P.NT / 2.0);   // per 128 rows
-    const double load = (static_cast<double>(G) * mch * (128 + halo) + (P.NT / 8) * 128.0) * 16.0 / 27.0;
+    // per 128 rows: an MMA costs max(issue ~55 clk, operand fetch (M + NT)/4 clk, NT/2 clk); loads run at ~22 B/clk
+    double per_mma = (M + P.NT) / 4.0;
+    if (per_mma < P.NT / 2.0) per_mma = P.NT / 2.0;
+    if (per_mma < 55.0) per_mma = 55.0;
+    const double mma = slots * 8.0 * per_mma;
+    const double load = (static_cast<double>(G) * mch * (128 + halo) + (P.NT / 8) * 128.0) * 16.0 / 22.0;
     const double cost = mma > load ? mma : load;
     if (cost < best) { best = cost; P.M = M; P.G = G; P.mch = mch; }
   }
