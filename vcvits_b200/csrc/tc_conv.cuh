@@ -144,7 +144,7 @@ inline int tc_run_conv(vcd_plan* p, const Layer& L, bool dgrad, const void* in, 
   const int mtiles = (Lq + 127) / 128;
   // Rows per CTA tile (MT x 128) from a small cost model (clocks per CTA): the weight stream of a tile is paid once
   // per MT*128 rows, so larger MT trades CTA-level parallelism for less L2->SM traffic per MMA.
-  //   t_mma  = MT * taps * K/16 * BN/2          (128 x BN x 16 UMMA = BN/2 clk)
+  //   t_mma  = MT * taps * K/16 * (128+BN)/4    (128 x BN x 16 UMMA, shared-memory operand fetch bound; tools/mma_rate.cu)
   //   t_load = bytes(A + streamed W) / 27 B/clk  (measured per-SM bulk-copy rate with ~160 KB in flight)
   //   t_epi  = MT * BN/16 units * 450 clk        (8 epilogue warps)
   const double w_tile_bytes = 2.0 * g.taps * g.K * P.BN;
@@ -156,7 +156,7 @@ inline int tc_run_conv(vcd_plan* p, const Layer& L, bool dgrad, const void* in, 
     const int cb = 2 * cand * P.BN <= 512 ? 2 : 1;
     const long long tiles = 1LL * ((mtiles + cand - 1) / cand) * P.n_tiles_n * B;
     const double waves = static_cast<double>((tiles + p->num_sms - 1) / p->num_sms);
-    const double t_mma = 1.0 * cand * g.taps * (g.K / 16) * (P.BN / 2);
+    const double t_mma = 1.0 * cand * g.taps * (g.K / 16) * ((128 + P.BN) / 4);   // operand fetch at 128 B/clk
     const double a_bytes = 2.0 * cand * P.RA * g.K;
     const double t_load = (a_bytes + (can_reside ? 0.0 : w_tile_bytes)) / 27.0;
     const double t_epi = cand * (P.BN / 16) * 450.0;
@@ -173,6 +173,11 @@ inline int tc_run_conv(vcd_plan* p, const Layer& L, bool dgrad, const void* in, 
   P.acc_bufs = bufs;
   P.n_mgroups = (mtiles + MT - 1) / MT;
   P.total_tiles = P.n_mgroups * P.n_tiles_n * B;
+  P.d_tiles_n.init(P.n_tiles_n);
+  P.d_mgroups.init(P.n_mgroups);
+  P.d_creal.init(g.creal);
+  P.units_shift = 0;
+  while ((16 << P.units_shift) < P.BN) ++P.units_shift;
   uint32_t cols = 32;
   while (cols < static_cast<uint32_t>(bufs * MT * P.BN)) cols <<= 1;
   P.tmem_cols = cols;

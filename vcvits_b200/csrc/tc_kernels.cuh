@@ -14,6 +14,8 @@
 #pragma once
 #include <cuda.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace vcd {
@@ -167,6 +169,29 @@ struct Pipe {
 // ---------------------------------------------------------------------------------------------------
 constexpr int kConvThreads = 352;
 
+// Division by a launch-constant through a host-computed multiplier (valid for dividends < 2^31): the tile -> (batch
+// item, row group, column tile) decode sits on every role's per-tile path, and a hardware integer division is a
+// ~100-clock dependent chain for a lone warp.
+struct FastDiv {
+  uint32_t mul, shr, div;
+  __host__ void init(int d) {
+    div = static_cast<uint32_t>(d);
+    if (d == 1) { mul = 0; shr = 0; return; }
+    uint32_t lg = 0;
+    while ((1u << lg) < div) ++lg;
+    const uint32_t pw = 31 + lg;
+    mul = static_cast<uint32_t>(((1ull << pw) + div - 1) / div);
+    shr = pw - 32;
+  }
+  __device__ __forceinline__ int quot(int n) const {
+    return div == 1 ? n : static_cast<int>(__umulhi(static_cast<uint32_t>(n), mul) >> shr);
+  }
+  __device__ __forceinline__ void divmod(int n, int& q, int& r) const {
+    q = quot(n);
+    r = n - q * static_cast<int>(div);
+  }
+};
+
 struct ConvParams {
   ConvGeo g;
   Epilogue e;
@@ -178,6 +203,8 @@ struct ConvParams {
   int w_resident;         // 1: all weights of the column tile live in shared memory for the whole kernel
   int TPS, NW;            // ring mode: taps per stage, stages
   int n_tiles_n, n_mgroups, total_tiles;
+  FastDiv d_tiles_n, d_mgroups, d_creal;   // dividers by n_tiles_n, n_mgroups, g.creal
+  int units_shift;        // log2(BN / 16)
   int minshift;           // min over taps of j*step (<= 0)
   int acc_bufs;           // 2: accumulators double-buffered (epilogue overlaps the next tile's MMAs); 1: MT*BN > 256
   uint32_t tmem_cols;
@@ -322,9 +349,8 @@ conv_kernel(const ConvParams P) {
     const size_t cg_stride_g = static_cast<size_t>(padded_len(P.Lin)) * 8;   // elements between channel groups
     Pipe pa;
     for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
-      const int rest = tile / P.n_tiles_n;
-      const int mg = rest % P.n_mgroups;
-      const int b = rest / P.n_mgroups;
+      int b, mg;
+      P.d_mgroups.divmod(P.d_tiles_n.quot(tile), b, mg);
       const int row0 = mg * 128 * P.MT + P.g.off0 + P.minshift;
       // 128-row tiles that start beyond the last output row are not loaded (their accumulators are never stored)
       int mt_live = P.MT;
@@ -359,7 +385,7 @@ conv_kernel(const ConvParams P) {
       Pipe pw;
       const size_t tap_stride_g = static_cast<size_t>(P.g.K / 8) * P.BN * 8;
       for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
-        const int nt = tile % P.n_tiles_n;
+        const int nt = tile - P.d_tiles_n.quot(tile) * P.n_tiles_n;
         for (int kb = 0; kb < kblocks; ++kb) {
           for (int j0 = 0; j0 < P.g.taps; j0 += P.TPS) {
             const int nj = min(P.TPS, P.g.taps - j0);
@@ -397,60 +423,98 @@ conv_kernel(const ConvParams P) {
       tc_fence_after();
       if (lane == 0) ktrace(P.trace, 3);
     }
-    for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++it) {
-      const int buf = P.acc_bufs == 2 ? (it & 1) : 0;
-      const int use = P.acc_bufs == 2 ? (it >> 1) : it;      // how many times this buffer was used before
-      mbar_wait(&acc_empty[buf], (use & 1) ^ 1);
-      tc_fence_after();
-      const uint32_t d_tile = tmem_base + static_cast<uint32_t>(buf * P.MT * P.BN);
-      for (int kb = 0; kb < kblocks; ++kb) {
-        mbar_wait(&fullA[pa.stage], pa.phase);
+    // KK (MMAs per K block and tap) and MT (row tiles per CTA tile) are compile-time in the common cases: the issue
+    // loop is then one elected region of MT*KK straight-line MMAs per tap with loop-invariant uniform increments.
+    // A per-MMA elect + runtime kk/mt loops cost 85-125 clk per MMA; this form issues at the tensor-pipe rate
+    // (40 clk for 128x32x16, operand-fetch bound -- tools/mma_rate.cu).
+    auto issue_tiles = [&](auto kk_tag, auto mt_tag) {
+      constexpr int KK = decltype(kk_tag)::value;
+      constexpr int MTC = decltype(mt_tag)::value;     // 0 = runtime P.MT
+      const uint32_t a_hi = static_cast<uint32_t>(a_desc0 >> 32), w_hi = static_cast<uint32_t>(w_desc0 >> 32);
+      const uint32_t tap_stride16 = P.w_resident ? w_tap16 * kblocks : w_tap16;   // resident layout: [tap][K/8][BN][8]
+      const uint32_t w_res_lo = static_cast<uint32_t>(w_desc0) + (smem_u32(w_smem) >> 4);
+      const uint32_t a_step = static_cast<uint32_t>(P.g.step), bn = static_cast<uint32_t>(P.BN);
+      const int taps = P.g.taps;
+      for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++it) {
+        const int buf = P.acc_bufs == 2 ? (it & 1) : 0;
+        const int use = P.acc_bufs == 2 ? (it >> 1) : it;      // how many times this buffer was used before
+        mbar_wait(&acc_empty[buf], (use & 1) ^ 1);
         tc_fence_after();
-        if (it == 0 && kb == 0 && lane == 0) ktrace(P.trace, 4);
-        const uint32_t a_hi = static_cast<uint32_t>(a_desc0 >> 32), w_hi = static_cast<uint32_t>(w_desc0 >> 32);
-        const uint32_t a_stage_lo = static_cast<uint32_t>(a_desc0) + (smem_u32(a_smem + static_cast<size_t>(pa.stage) * a_stage_bytes) >> 4);
-        int j = 0;
-        while (j < P.g.taps) {
-          int nj;
-          uint32_t w_lo;
-          if (P.w_resident) {
-            nj = P.g.taps;
-            w_lo = static_cast<uint32_t>(w_desc0) + (smem_u32(w_smem) >> 4) + static_cast<uint32_t>(kb) * w_tap16;
-          } else {
-            nj = min(P.TPS, P.g.taps - j);
-            mbar_wait(&fullW[pw.stage], pw.phase);
-            tc_fence_after();
-            w_lo = static_cast<uint32_t>(w_desc0) + (smem_u32(w_smem + static_cast<size_t>(pw.stage) * P.TPS * w_tap_bytes) >> 4);
-          }
-          // resident layout is [tap][K/8][BN][8]: consecutive taps are kblocks*w_tap16 apart
-          const uint32_t tap_stride16 = P.w_resident ? w_tap16 * kblocks : w_tap16;
-          uint32_t a_tap = a_stage_lo + static_cast<uint32_t>(j * P.g.step - P.minshift);
-          for (int jj = 0; jj < nj; ++jj, ++j) {
-            uint32_t d_tmem = d_tile, a_mt = a_tap;
-            for (int mt = 0; mt < P.MT; ++mt) {
-              uint32_t ad = a_mt, bd = w_lo;
-              for (int kk = 0; kk < kk_per_block; ++kk) {
-                const uint32_t accum = (kb | j | kk) != 0 ? 1u : 0u;
-                if (elect_one()) umma_bf16_split(d_tmem, ad, a_hi, bd, w_hi, idesc, accum);
-                ad += a_kk16;
-                bd += w_kk16;
-              }
-              d_tmem += static_cast<uint32_t>(P.BN);
-              a_mt += a_region16;
+        const uint32_t d_tile = tmem_base + static_cast<uint32_t>(buf * P.MT * P.BN);
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(&fullA[pa.stage], pa.phase);
+          tc_fence_after();
+          if (it == 0 && kb == 0 && lane == 0) ktrace(P.trace, 4);
+          const uint32_t a_stage_lo = static_cast<uint32_t>(a_desc0) + (smem_u32(a_smem + static_cast<size_t>(pa.stage) * a_stage_bytes) >> 4);
+          uint32_t a_tap = a_stage_lo + static_cast<uint32_t>(-P.minshift);
+          int j = 0;
+          while (j < taps) {
+            int nj;
+            uint32_t w_lo;
+            if (P.w_resident) {
+              nj = taps;
+              w_lo = w_res_lo + static_cast<uint32_t>(kb) * w_tap16;
+            } else {
+              nj = min(P.TPS, taps - j);
+              mbar_wait(&fullW[pw.stage], pw.phase);
+              tc_fence_after();
+              w_lo = static_cast<uint32_t>(w_desc0) + (smem_u32(w_smem + static_cast<size_t>(pw.stage) * P.TPS * w_tap_bytes) >> 4);
             }
-            w_lo += tap_stride16;
-            a_tap += static_cast<uint32_t>(P.g.step);
+            uint32_t first = (kb | j) != 0 ? 1u : 0u;    // accumulate flag of the first MMA of this tap
+#pragma unroll 1
+            for (int jj = 0; jj < nj; ++jj) {
+              if constexpr (MTC > 0) {
+                if (elect_one()) {
+#pragma unroll
+                  for (int mt = 0; mt < MTC; ++mt) {
+#pragma unroll
+                    for (int kk = 0; kk < KK; ++kk)
+                      umma_bf16_split(d_tile + static_cast<uint32_t>(mt) * bn,
+                                      a_tap + static_cast<uint32_t>(mt) * a_region16 + static_cast<uint32_t>(kk) * a_kk16, a_hi,
+                                      w_lo + static_cast<uint32_t>(kk) * w_kk16, w_hi, idesc, kk == 0 ? first : 1u);
+                  }
+                }
+              } else {
+                uint32_t d_tmem = d_tile, a_mt = a_tap;
+                for (int mt = 0; mt < P.MT; ++mt) {
+                  if (elect_one()) {
+#pragma unroll
+                    for (int kk = 0; kk < KK; ++kk)
+                      umma_bf16_split(d_tmem, a_mt + static_cast<uint32_t>(kk) * a_kk16, a_hi,
+                                      w_lo + static_cast<uint32_t>(kk) * w_kk16, w_hi, idesc, kk == 0 ? first : 1u);
+                  }
+                  d_tmem += bn;
+                  a_mt += a_region16;
+                }
+              }
+              first = 1u;
+              w_lo += tap_stride16;
+              a_tap += a_step;
+            }
+            j += nj;
+            if (!P.w_resident) {
+              if (elect_one()) umma_commit(&emptyW[pw.stage]);
+              pw.advance(P.NW);
+            }
           }
-          if (!P.w_resident) {
-            if (elect_one()) umma_commit(&emptyW[pw.stage]);
-            pw.advance(P.NW);
-          }
+          if (elect_one()) umma_commit(&emptyA[pa.stage]);
+          pa.advance(P.NA);
         }
-        if (elect_one()) umma_commit(&emptyA[pa.stage]);
-        pa.advance(P.NA);
+        if (elect_one()) umma_commit(&acc_full[buf]);
+        if (it < 4 && lane == 0) ktrace(P.trace, 8 + it);       // MMAs of tile `it` issued
       }
-      if (elect_one()) umma_commit(&acc_full[buf]);
-      if (it < 4 && lane == 0) ktrace(P.trace, 8 + it);       // MMAs of tile `it` issued
+    };
+    using std::integral_constant;
+    if (kk_per_block == 4) {
+      if (P.MT == 1) issue_tiles(integral_constant<int, 4>{}, integral_constant<int, 1>{});
+      else if (P.MT == 2) issue_tiles(integral_constant<int, 4>{}, integral_constant<int, 2>{});
+      else issue_tiles(integral_constant<int, 4>{}, integral_constant<int, 0>{});
+    } else if (kk_per_block == 2) {
+      if (P.MT == 1) issue_tiles(integral_constant<int, 2>{}, integral_constant<int, 1>{});
+      else if (P.MT == 2) issue_tiles(integral_constant<int, 2>{}, integral_constant<int, 2>{});
+      else issue_tiles(integral_constant<int, 2>{}, integral_constant<int, 0>{});
+    } else {
+      issue_tiles(integral_constant<int, 1>{}, integral_constant<int, 0>{});
     }
     if (lane == 0) ktrace(P.trace, 5);
   } else if (warp >= 2 && warp <= 9) {
@@ -461,83 +525,104 @@ conv_kernel(const ConvParams P) {
     const Epilogue& e = P.e;
     const int units_per_mt = P.BN / 16;
     const int n_units = P.MT * units_per_mt;
-    int it = 0;
-    for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++it) {
-      const int nt = tile % P.n_tiles_n;
-      const int rest = tile / P.n_tiles_n;
-      const int mg = rest % P.n_mgroups;
-      const int b = rest / P.n_mgroups;
+    const size_t chunk_stride = static_cast<size_t>(padded_len(P.Lout)) * 8;  // next 8-channel group, same row
+    // per-tile state of this thread's row
+    struct TileC { int b, r_phase, ch_tile, q_first; uint32_t t_lane; };
+    auto tile_coords = [&](int tile, int it) {
+      TileC t;
+      int rest, nt, mg;
+      P.d_tiles_n.divmod(tile, rest, nt);
+      P.d_mgroups.divmod(rest, t.b, mg);
       const int buf = P.acc_bufs == 2 ? (it & 1) : 0;
-      const int use = P.acc_bufs == 2 ? (it >> 1) : it;
-      const int r_phase = (nt * P.BN) / P.g.creal;          // scatter phase of this column tile (os > 1)
-      const int ch_tile = nt * P.BN - r_phase * P.g.creal;  // first output channel of the tile
+      t.r_phase = P.d_creal.quot(nt * P.BN);            // scatter phase of this column tile (os > 1)
+      t.ch_tile = nt * P.BN - t.r_phase * P.g.creal;    // first output channel of the tile
+      t.q_first = mg * P.MT * 128 + row_in_tile;
+      t.t_lane = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(buf * P.MT * P.BN);
+      return t;
+    };
+    struct UnitC { int ro, ch; bool valid; size_t o; uint32_t taddr; };
+    auto unit_coords = [&](const TileC& t, int u) {
+      UnitC c;
+      const int mt = u >> P.units_shift, c16 = u - (mt << P.units_shift);
+      const int q = t.q_first + mt * 128;
+      c.ro = q * P.g.os + t.r_phase - P.g.p;
+      c.valid = q < P.Lq && c.ro >= 0 && c.ro < P.Lout;
+      c.ch = t.ch_tile + c16 * 16;
+      c.o = blk_row(t.b, c.ch >> 3, c.valid ? c.ro : 0, P.g.creal, P.Lout);
+      c.taddr = t.t_lane + static_cast<uint32_t>(mt * P.BN + c16 * 16);
+      return c;
+    };
 
-      {  // stage this tile's bias vector (named barrier 1 = the 256 epilogue threads)
+    // Software pipeline over this warp's units ACROSS tiles: the global operands (mask / residuals) of the next
+    // unit -- the first unit of the next tile when the current tile is exhausted -- are requested before the
+    // current unit is finished (and before the wait for its accumulator), so their latency is off the per-tile
+    // critical path.  The two operand buffers alternate by code duplication (step(A, B); step(B, A)): a register
+    // copy `cur = nxt` would wait for the just-issued loads and serialise the pipeline again.
+    EpiLoads bufA[2], bufB[2];
+    UnitC uc{};
+    TileC tcur = tile_coords(blockIdx.x, 0);
+    int tile = blockIdx.x, it = 0, u = half;
+    const int grid = static_cast<int>(gridDim.x);
+    if (tile < P.total_tiles) {
+      uc = unit_coords(tcur, u);
+      epi_prefetch<F>(e, uc.o, uc.valid, bufA[0]);
+      epi_prefetch<F>(e, uc.o + chunk_stride, uc.valid, bufA[1]);
+    }
+    auto step = [&](EpiLoads (&use)[2], EpiLoads (&fill)[2]) {
+      const int buf = P.acc_bufs == 2 ? (it & 1) : 0;
+      const int use_n = P.acc_bufs == 2 ? (it >> 1) : it;
+      const bool first = u == half;                      // first unit of this warp in the tile
+      const bool last = u + 2 >= n_units;                // last unit of this warp in the tile
+      if (first) {  // stage this tile's bias vector (named barrier 1 = the 256 epilogue threads)
         const int et = static_cast<int>(threadIdx.x) - 64;
         if (et < P.BN) {
-          float bv = e.bias ? __ldg(e.bias + ch_tile + et) : 0.f;
-          if (e.bias2) bv += __ldg(e.bias2 + static_cast<size_t>(b) * P.g.creal + ch_tile + et);
+          float bv = e.bias ? __ldg(e.bias + tcur.ch_tile + et) : 0.f;
+          if (e.bias2) bv += __ldg(e.bias2 + static_cast<size_t>(tcur.b) * P.g.creal + tcur.ch_tile + et);
           bias_s[(it & 1) * 128 + et] = bv;
         }
         asm volatile("bar.sync 1, 256;" ::: "memory");
       }
-      // per-thread row state of each 128-row tile (computed once per tile, not per unit)
-      const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(buf * P.MT * P.BN);
-      const size_t chunk_stride = static_cast<size_t>(padded_len(P.Lout)) * 8;  // next 8-channel group, same row
-      const int q_first = mg * P.MT * 128 + row_in_tile;
-      auto unit_coords = [&](int u, int& ro, bool& valid, size_t& o0, uint32_t& taddr, int& ch) {
-        const int mt = u / units_per_mt, c16 = u - mt * units_per_mt;
-        const int q = q_first + mt * 128;
-        ro = q * P.g.os + r_phase - P.g.p;
-        valid = q < P.Lq && ro >= 0 && ro < P.Lout;
-        ch = ch_tile + c16 * 16;
-        o0 = blk_row(b, ch >> 3, valid ? ro : 0, P.g.creal, P.Lout);
-        taddr = t_lane + static_cast<uint32_t>(mt * P.BN + c16 * 16);
-      };
-
-      // software pipeline: global operands of unit u+2 are requested before unit u is finished
-      EpiLoads cur[2], nxt[2];
-      int ro_c = 0, ro_n = 0, ch_c = 0, ch_n = 0;
-      bool v_c = false, v_n = false;
-      size_t o_c = 0, o_n = 0;
-      uint32_t t_c = 0, t_n = 0;
-      int u = half;
-      if (u < n_units) {
-        unit_coords(u, ro_c, v_c, o_c, t_c, ch_c);
-        epi_prefetch<F>(e, o_c, v_c, cur[0]);
-        epi_prefetch<F>(e, o_c + chunk_stride, v_c, cur[1]);
+      // next unit of this warp: same tile, or the first unit of the next tile
+      const int n_tile = last ? tile + grid : tile, n_it = last ? it + 1 : it, n_u = last ? half : u + 2;
+      TileC tnext = tcur;
+      UnitC un{};
+      if (n_tile < P.total_tiles) {
+        if (last) tnext = tile_coords(n_tile, n_it);
+        un = unit_coords(tnext, n_u);
+        epi_prefetch<F>(e, un.o, un.valid, fill[0]);
+        epi_prefetch<F>(e, un.o + chunk_stride, un.valid, fill[1]);
       }
-      mbar_wait(&acc_full[buf], use & 1);
-      tc_fence_after();
-      if (warp == 2 && lane == 0 && it < 4) ktrace(P.trace, 12 + it);   // accumulators of tile `it` complete
-      for (; u < n_units; u += 2) {
-        const int un = u + 2;
-        if (un < n_units) {
-          unit_coords(un, ro_n, v_n, o_n, t_n, ch_n);
-          epi_prefetch<F>(e, o_n, v_n, nxt[0]);
-          epi_prefetch<F>(e, o_n + chunk_stride, v_n, nxt[1]);
-        }
-        float acc[16];
-        if (warp == 2 && lane == 0 && it == 0 && u < 6) ktrace(P.trace, 20 + u * 2);       // debug: unit start
-        tmem_ld16(t_c, acc);
-        if (warp == 2 && lane == 0 && it == 0 && u < 6) ktrace(P.trace, 21 + u * 2);       // debug: TMEM load done
-        if (v_c) {
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            float v[8];
-#pragma unroll
-            for (int n = 0; n < 8; ++n) v[n] = acc[h * 8 + n];
-            epi_finish<F>(e, P.g, b, ro_c, ch_c + h * 8, o_c + h * chunk_stride, cur[h],
-                       bias_s + (it & 1) * 128 + (ch_c - ch_tile) + h * 8, v);
-          }
-        }
-        cur[0] = nxt[0]; cur[1] = nxt[1];
-        ro_c = ro_n; v_c = v_n; o_c = o_n; t_c = t_n; ch_c = ch_n;
+      if (first) {
+        mbar_wait(&acc_full[buf], use_n & 1);
+        tc_fence_after();
+        if (warp == 2 && lane == 0 && it < 4) ktrace(P.trace, 12 + it);   // accumulators of tile `it` complete
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&acc_empty[buf]);
-      if (warp == 2 && lane == 0 && it < 4) ktrace(P.trace, 16 + it);   // epilogue of tile `it` done
+      float acc[16];
+      tmem_ld16(uc.taddr, acc);
+      if (uc.valid) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          float v[8];
+#pragma unroll
+          for (int n = 0; n < 8; ++n) v[n] = acc[h * 8 + n];
+          epi_finish<F>(e, P.g, tcur.b, uc.ro, uc.ch + h * 8, uc.o + h * chunk_stride, use[h],
+                        bias_s + (it & 1) * 128 + (uc.ch - tcur.ch_tile) + h * 8, v);
+        }
+      }
+      if (last) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[buf]);
+        if (warp == 2 && lane == 0 && it < 4) ktrace(P.trace, 16 + it);   // epilogue of tile `it` done
+      }
+      tile = n_tile; it = n_it; u = n_u;
+      tcur = tnext;
+      uc = un;
+    };
+    while (tile < P.total_tiles) {
+      step(bufA, bufB);
+      if (tile >= P.total_tiles) break;
+      step(bufB, bufA);
     }
   }
 
@@ -653,29 +738,39 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ C
     const uint64_t b_desc0 = make_desc(0, 128, static_cast<uint32_t>(P.TK) * 16);
     const int kks = P.TK / 16;
     Pipe ps;
-    for (int kb = 0; kb < kblocks; ++kb) {
-      mbar_wait(&full[ps.stage], ps.phase);
-      tc_fence_after();
-      if (lane == 0 && kb < 8) ktrace(P.trace, 8 + kb);        // stage kb landed
-      const uint32_t a_base = smem_u32(smem + static_cast<size_t>(ps.stage) * stage_bytes);
-      const uint32_t a_hi = static_cast<uint32_t>(a_desc0 >> 32), b_hi = static_cast<uint32_t>(b_desc0 >> 32);
-      const uint32_t b_stage = static_cast<uint32_t>(b_desc0) + ((a_base + in_bytes) >> 4);
-      uint32_t a_slot = static_cast<uint32_t>(a_desc0) + (a_base >> 4) + static_cast<uint32_t>(slot0 * P.G * P.step - P.minshift);
-      for (int tl = 0; tl < nslots; ++tl) {
-        uint32_t d_tmem;
-        if (P.M == 128) d_tmem = tmem_base + static_cast<uint32_t>(tl * P.NT);
-        else d_tmem = tmem_base + static_cast<uint32_t>((tl >> 1) * P.NT) + (static_cast<uint32_t>((tl & 1) * 16) << 16);
-        uint32_t ad = a_slot, bd = b_stage;
-        for (int kk = 0; kk < kks; ++kk) {
-          const uint32_t accum = (kb | kk) != 0 ? 1u : 0u;
-          if (elect_one()) umma_bf16_split(d_tmem, ad, a_hi, bd, b_hi, idesc, accum);
-          ad += 16;
-          bd += 16;
+    auto issue_stages = [&](auto kks_tag) {
+      constexpr int KKS = decltype(kks_tag)::value;
+      for (int kb = 0; kb < kblocks; ++kb) {
+        mbar_wait(&full[ps.stage], ps.phase);
+        tc_fence_after();
+        if (lane == 0 && kb < 8) ktrace(P.trace, 8 + kb);        // stage kb landed
+        const uint32_t a_base = smem_u32(smem + static_cast<size_t>(ps.stage) * stage_bytes);
+        const uint32_t a_hi = static_cast<uint32_t>(a_desc0 >> 32), b_hi = static_cast<uint32_t>(b_desc0 >> 32);
+        const uint32_t b_stage = static_cast<uint32_t>(b_desc0) + ((a_base + in_bytes) >> 4);
+        uint32_t a_slot = static_cast<uint32_t>(a_desc0) + (a_base >> 4) + static_cast<uint32_t>(slot0 * P.G * P.step - P.minshift);
+        for (int tl = 0; tl < nslots; ++tl) {
+          uint32_t d_tmem;
+          if (P.M == 128) d_tmem = tmem_base + static_cast<uint32_t>(tl * P.NT);
+          else d_tmem = tmem_base + static_cast<uint32_t>((tl >> 1) * P.NT) + (static_cast<uint32_t>((tl & 1) * 16) << 16);
+          // one elected region of KKS straight-line MMAs per tap slot (see the conv kernel / tools/mma_rate.cu)
+          const uint32_t accum0 = kb != 0 ? 1u : 0u;
+          if (elect_one()) {
+#pragma unroll
+            for (int kk = 0; kk < KKS; ++kk)
+              umma_bf16_split(d_tmem, a_slot + 16u * kk, a_hi, b_stage + 16u * kk, b_hi, idesc, kk == 0 ? accum0 : 1u);
+          }
+          a_slot += static_cast<uint32_t>(P.G * P.step);
         }
-        a_slot += static_cast<uint32_t>(P.G * P.step);
+        if (elect_one()) umma_commit(&empty[ps.stage]);
+        ps.advance(P.NS);
       }
-      if (elect_one()) umma_commit(&empty[ps.stage]);
-      ps.advance(P.NS);
+    };
+    switch (kks) {
+      case 7: issue_stages(std::integral_constant<int, 7>{}); break;
+      case 6: issue_stages(std::integral_constant<int, 6>{}); break;
+      case 5: issue_stages(std::integral_constant<int, 5>{}); break;
+      case 4: issue_stages(std::integral_constant<int, 4>{}); break;
+      default: __trap();
     }
     if (elect_one()) umma_commit(acc_full);
     if (lane == 0) ktrace(P.trace, 5);
