@@ -232,7 +232,7 @@ inline int tc_run_conv(vcd_plan* p, const Layer& L, bool dgrad, const void* in, 
   }
   // two co-resident CTAs per SM when both fit (small-channel layers): one CTA's prologue / epilogue overlaps the
   // other's MMAs.  Needs <= ~110 KB shared memory, <= 256 TMEM columns and a <= 102-register instantiation.
-  static const int occ2 = tc_env_int("VCD_CONV_OCC2", 1);
+  static const int occ2 = tc_env_int("VCD_CONV_OCC2", 0);
   const int ctas_per_sm = (occ2 && smem <= 110 * 1024 && P.tmem_cols <= 256) ? 2 : 1;
   const int max_ctas = p->num_sms * ctas_per_sm;
   const int grid = P.total_tiles < max_ctas ? P.total_tiles : max_ctas;
@@ -284,9 +284,11 @@ inline int tc_run_wgrad(vcd_plan* p, const Layer& L, const void* in, const void*
     // per 128 rows: an MMA costs max(issue ~55 clk, operand fetch (M + NT)/4 clk, NT/2 clk); loads run at ~22 B/clk
     double per_mma = (M + P.NT) / 4.0;
     if (per_mma < P.NT / 2.0) per_mma = P.NT / 2.0;
-    if (per_mma < 55.0) per_mma = 55.0;
+    static const int issue_floor = tc_env_int("VCD_WGRAD_ISSUE_FLOOR", 55);
+    if (per_mma < issue_floor) per_mma = issue_floor;
     const double mma = slots * 8.0 * per_mma;
-    const double load = (static_cast<double>(G) * mch * (128 + halo) + (P.NT / 8) * 128.0) * 16.0 / 22.0;
+    static const double load_rate = tc_env_int("VCD_WGRAD_LOAD_RATE", 22);
+    const double load = (static_cast<double>(G) * mch * (128 + halo) + (P.NT / 8) * 128.0) * 16.0 / load_rate;
     const double cost = mma > load ? mma : load;
     if (cost < best) { best = cost; P.M = M; P.G = G; P.mch = mch; }
   }
@@ -309,7 +311,11 @@ inline int tc_run_wgrad(vcd_plan* p, const Layer& L, const void* in, const void*
   }
   P.RI = (P.TK + halo + 7) / 8 * 8;
   const size_t stage = stage_bytes(P.TK);
-  int NS = static_cast<int>((200 * 1024) / stage);
+  // small-channel layers keep the pipeline shallow: a CTA that fills the SM's shared memory cannot share the SM with
+  // the data-gradient CTAs of the other ResBlock branches, whose persistent grids then wait for whole wgrad CTAs
+  static const int ws_kb_big = tc_env_int("VCD_WGRAD_SMEM_KB", 200), ws_kb_small = tc_env_int("VCD_WGRAD_SMEM_KB_SMALL", 96);
+  const bool small_layer = static_cast<long long>(g.taps) * g.K * g.N <= 64 * 64 * 11;
+  int NS = static_cast<int>((static_cast<size_t>(small_layer ? ws_kb_small : ws_kb_big) * 1024) / stage);
   P.NS = NS > 8 ? 8 : (NS < 2 ? 2 : NS);
   // slack: an M = 64 operand over a 32-channel tile reads 4 channel groups past the tile (garbage rows, unused)
   const size_t smem = 128 + P.NS * stage + (2 * P.NS + 1) * 8 + 16 + 8 * 1024;

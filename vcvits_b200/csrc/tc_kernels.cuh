@@ -568,12 +568,17 @@ conv_kernel(const ConvParams P) {
       epi_prefetch<F>(e, uc.o, uc.valid, bufA[0]);
       epi_prefetch<F>(e, uc.o + chunk_stride, uc.valid, bufA[1]);
     }
+    const bool has_bias = e.bias != nullptr || e.bias2 != nullptr;
+    if (!has_bias) {  // data-gradient launches: the staged bias vector is zero for every tile
+      bias_s[static_cast<int>(threadIdx.x) - 64] = 0.f;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+    }
     auto step = [&](EpiLoads (&use)[2], EpiLoads (&fill)[2]) {
       const int buf = P.acc_bufs == 2 ? (it & 1) : 0;
       const int use_n = P.acc_bufs == 2 ? (it >> 1) : it;
       const bool first = u == half;                      // first unit of this warp in the tile
       const bool last = u + 2 >= n_units;                // last unit of this warp in the tile
-      if (first) {  // stage this tile's bias vector (named barrier 1 = the 256 epilogue threads)
+      if (first && has_bias) {  // stage this tile's bias vector (named barrier 1 = the 256 epilogue threads)
         const int et = static_cast<int>(threadIdx.x) - 64;
         if (et < P.BN) {
           float bv = e.bias ? __ldg(e.bias + tcur.ch_tile + et) : 0.f;
@@ -606,7 +611,7 @@ conv_kernel(const ConvParams P) {
 #pragma unroll
           for (int n = 0; n < 8; ++n) v[n] = acc[h * 8 + n];
           epi_finish<F>(e, P.g, tcur.b, uc.ro, uc.ch + h * 8, uc.o + h * chunk_stride, use[h],
-                        bias_s + (it & 1) * 128 + (uc.ch - tcur.ch_tile) + h * 8, v);
+                        bias_s + (has_bias ? (it & 1) * 128 : 0) + (uc.ch - tcur.ch_tile) + h * 8, v);
         }
       }
       if (last) {
