@@ -276,7 +276,7 @@ cond_fwd_kernel(const float* __restrict__ w, const float* __restrict__ bias, con
 __global__ void __launch_bounds__(256)
 cond_bwd_kernel(const float* __restrict__ dcb, const float* __restrict__ w, const float* __restrict__ gv,
                 float* __restrict__ d_pre_bias, float* __restrict__ d_cond_bias, float* __restrict__ d_cond_w,
-                float* __restrict__ dg, int B, int N, int G) {
+                int B, int N, int G) {
   const long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
   if (i < N) {
     float s = 0.f;
@@ -290,11 +290,27 @@ cond_bwd_kernel(const float* __restrict__ dcb, const float* __restrict__ w, cons
     for (int b = 0; b < B; ++b) s = fmaf(dcb[static_cast<size_t>(b) * N + n], gv[static_cast<size_t>(b) * G + c], s);
     d_cond_w[i] = s;
   }
-  if (dg && i < static_cast<long long>(B) * G) {
-    const int b = static_cast<int>(i / G), c = static_cast<int>(i % G);
-    float s = 0.f;
-    for (int n = 0; n < N; ++n) s = fmaf(dcb[static_cast<size_t>(b) * N + n], w[static_cast<size_t>(n) * G + c], s);
-    dg[i] = s;
+}
+
+// dg[b][c] = sum_n dcb[b][n] * w[n][c]  (gradient w.r.t. the speaker embedding).  grid = (ceil(G/32), B), block = 256:
+// the eight warps split n, so no thread walks a 512-long dependent chain of L2-latency loads.
+__global__ void __launch_bounds__(256)
+cond_dg_kernel(const float* __restrict__ dcb, const float* __restrict__ w, float* __restrict__ dg, int N, int G) {
+  const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+  const int b = blockIdx.y, c = blockIdx.x * 32 + lane;
+  float s = 0.f;
+  if (c < G) {
+#pragma unroll 4
+    for (int n = wp; n < N; n += 8) s = fmaf(__ldg(dcb + static_cast<size_t>(b) * N + n), __ldg(w + static_cast<size_t>(n) * G + c), s);
+  }
+  __shared__ float red[8][33];
+  red[wp][lane] = s;
+  __syncthreads();
+  if (wp == 0 && c < G) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += red[k][lane];
+    dg[static_cast<size_t>(b) * G + c] = t;
   }
 }
 

@@ -150,6 +150,12 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// Programmatic dependent launch: a kernel launched with the programmatic-stream-serialization attribute starts while
+// its stream predecessor drains; pdl_wait() blocks until the predecessor has completed and its writes are visible
+// (no-op without the attribute), pdl_launch() lets the successor's CTAs start their prologue.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 struct Pipe {
   int stage = 0;
   uint32_t phase = 0;
@@ -348,7 +354,10 @@ conv_kernel(const ConvParams P) {
     const uint32_t cg_bytes = static_cast<uint32_t>(P.RA) * 16;
     const size_t cg_stride_g = static_cast<size_t>(padded_len(P.Lin)) * 8;   // elements between channel groups
     Pipe pa;
+    pdl_wait();   // the activations are the stream predecessor's output (weights are older: their producer does not wait)
     for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+      // last tile of this CTA: the successor kernel may start its prologue (barriers, TMEM, weight loads) now
+      if (tile + static_cast<int>(gridDim.x) >= P.total_tiles) pdl_launch();
       int b, mg;
       P.d_mgroups.divmod(P.d_tiles_n.quot(tile), b, mg);
       const int row0 = mg * 128 * P.MT + P.g.off0 + P.minshift;
@@ -558,6 +567,7 @@ conv_kernel(const ConvParams P) {
     // current unit is finished (and before the wait for its accumulator), so their latency is off the per-tile
     // critical path.  The two operand buffers alternate by code duplication (step(A, B); step(B, A)): a register
     // copy `cur = nxt` would wait for the just-issued loads and serialise the pipeline again.
+    pdl_wait();   // masks / residuals / running sums may be the stream predecessor's output
     EpiLoads bufA[2], bufB[2];
     UnitC uc{};
     TileC tcur = tile_coords(blockIdx.x, 0);

@@ -1189,12 +1189,16 @@ extern "C" int vcd_backward(vcd_plan* p, int mode, const float* dy, const float*
         const int G = p->cfg.gin_channels;
         const bool have_g = gvec != nullptr && G > 0;
         long long n = C0;
-        if (have_g) n = std::max<long long>(n, std::max<long long>(1LL * C0 * G, 1LL * B * G));
+        if (have_g) n = std::max<long long>(n, 1LL * C0 * G);
         cond_bwd_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(
             PF(w.dcb), have_g ? p->h_params[p->p_cond_w] : nullptr, gvec, p->h_dparams[L.p_b],
             have_g ? p->h_dparams[p->p_cond_b] : nullptr, have_g ? p->h_dparams[p->p_cond_w] : nullptr,
-            have_g ? dg : nullptr, B, C0, std::max(G, 1));
+            B, C0, std::max(G, 1));
         LAUNCH_CHECK("cond_bwd_kernel");
+        if (have_g && dg) {
+          cond_dg_kernel<<<dim3((G + 31) / 32, B), 256, 0, stream>>>(PF(w.dcb), p->h_params[p->p_cond_w], dg, C0, G);
+          LAUNCH_CHECK("cond_dg_kernel");
+        }
         if (!have_g && G > 0) {
           CU_TRY(cudaMemsetAsync(p->h_dparams[p->p_cond_w], 0, sizeof(float) * p->params[p->p_cond_w].numel, stream));
           CU_TRY(cudaMemsetAsync(p->h_dparams[p->p_cond_b], 0, sizeof(float) * p->params[p->p_cond_b].numel, stream));
