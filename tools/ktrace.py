@@ -22,7 +22,8 @@ names = {0: "entry", 1: "setup done", 2: "first A issued", 3: "W resident landed
          14: "acc done t2", 15: "acc done t3", 16: "epi done t0", 17: "epi done t1", 18: "epi done t2", 19: "epi done t3"}
 if os.environ.get("VCD_KTRACE", "").endswith(":wgrad"):
     names = {0: "entry", 1: "setup done", 5: "all MMAs issued", 6: "exit", 12: "acc done"}
-    names.update({8 + i: f"stage {i} landed" for i in range(8)})
+    names.update({8 + i: f"stage {i} landed" for i in range(4)})
+    names.update({21: "accumulators written"})
 for k in sorted(names, key=lambda k: buf[k] if buf[k] else 1 << 62):
     if buf[k]:
         print(f"{names[k]:22s} +{(buf[k] - t0) / 1000:8.2f} us")

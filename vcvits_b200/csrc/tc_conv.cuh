@@ -355,6 +355,8 @@ inline int tc_run_wgrad(vcd_plan* p, const Layer& L, const void* in, const void*
   if (want < 1) want = 1;
   P.kb_per_split = static_cast<int>((total_kb + want - 1) / want);
   P.n_splits = static_cast<int>((total_kb + P.kb_per_split - 1) / P.kb_per_split);
+  static const int dbg_direct = tc_env_int("VCD_WGRAD_DEBUG_DIRECT", 0);   // wrong results: timing experiment only
+  P.direct = (P.n_splits == 1 || dbg_direct) ? 1 : 0;
   P.in = static_cast<const bf16*>(in);
   P.dout = static_cast<const bf16*>(dout);
   P.Lin = Lin;

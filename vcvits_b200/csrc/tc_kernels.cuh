@@ -123,6 +123,22 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// 32 consecutive accumulator columns of this thread's TMEM lane.
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
 // Shared-memory matrix descriptor, SWIZZLE_NONE, version 1 (sm_100).  All byte quantities multiples of 16.
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
   uint64_t d = 0;
@@ -675,6 +691,7 @@ struct WgradParams {
   int TG, n_tgroups;      // tap slots per CTA and number of tap groups
   int TK, RI;             // time rows per pipeline stage, rows of the A tile (TK + halo)
   int kb_per_item, n_splits, kb_per_split;  // the flattened (batch, time block) range is cut into n_splits
+  int direct;             // 1: plain stores of the accumulators (n_splits == 1; debug: timing without reductions)
   int NS;
   uint32_t tmem_cols;
   float* dbias;           // bias gradient [cmod] (column sums of dout folded modulo cmod), or null
@@ -826,19 +843,28 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ C
     mbar_wait(acc_full, 0);
     tc_fence_after();
     if (warp == 2 && lane == 0) ktrace(P.trace, 12);
-    for (int tl = 0; tl < nslots; ++tl) {
-      int row;             // row of the M x NT accumulator held by this thread
+    // the scratch below aliases pipeline stage 0: every epilogue warp must be done with its column sums first
+    asm volatile("bar.sync 2, 128;" ::: "memory");
+    // Accumulators -> global.  A thread owns one accumulator row (TMEM lane); writing it out directly would scatter
+    // every warp-level reduction over 32 rows (32 half-used sectors per instruction).  Each 32-row x 32-column block
+    // is transposed through a per-warp scratch in the (drained) pipeline stages, so one red.v4 covers four rows x
+    // 128 contiguous bytes: full sectors, 8x fewer memory wavefronts.
+    float* scratch = reinterpret_cast<float*>(smem) + (warp - 2) * (32 * 36);   // [32 rows][36]: conflict-free v4 access
+    const int passes = P.M == 128 ? nslots : (nslots + 1) / 2;
+    for (int ps = 0; ps < passes; ++ps) {
+      // this lane's accumulator row: tap slot, tap j, input channel c
+      int tl, row;
       uint32_t col0;
-      bool active = true;
       if (P.M == 128) {
+        tl = ps;
         row = quad * 32 + lane;
         col0 = static_cast<uint32_t>(tl * P.NT);
-      } else {
-        // lanes 16..31 of a quadrant hold the odd slot of the column block; row i of D sits in lane i%16 of quadrant i/16
-        if ((tl & 1) != (lane >> 4)) active = false;
+      } else {  // lanes 16..31 of a quadrant hold the odd slot of the column block; row i of D: lane i%16 of quadrant i/16
+        tl = 2 * ps + (lane >> 4);
         row = quad * 16 + (lane & 15);
-        col0 = static_cast<uint32_t>((tl >> 1) * P.NT);
+        col0 = static_cast<uint32_t>(ps * P.NT);
       }
+      bool active = tl < nslots;
       int j, c;
       if (P.G == 1) {
         j = slot0 + tl;
@@ -851,23 +877,43 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ C
         if (g >= P.G) active = false;
       }
       if (j >= P.taps) active = false;
-      for (int c16 = 0; c16 < P.NT / 16; ++c16) {
-        float acc[16];
-        tmem_ld16(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + col0 + c16 * 16, acc);
-        if (active) {
-          float* dst = P.dwp + (static_cast<size_t>(j) * P.K + c) * P.N + ntile * P.NT + c16 * 16;
-          if (P.n_splits == 1) {
+      const float* row_dst = P.dwp + (static_cast<size_t>(active ? j : 0) * P.K + (active ? c : 0)) * P.N + ntile * P.NT;
+      const unsigned long long row_ptr = reinterpret_cast<unsigned long long>(row_dst);
+      for (int c32 = 0; c32 < P.NT / 32; ++c32) {
+        float acc[32];
+        tmem_ld32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + col0 + c32 * 32, acc);
 #pragma unroll
-            for (int n = 0; n < 16; n += 4) *reinterpret_cast<float4*>(dst + n) = make_float4(acc[n], acc[n + 1], acc[n + 2], acc[n + 3]);
-          } else {
+        for (int n = 0; n < 32; n += 4)
+          *reinterpret_cast<float4*>(scratch + lane * 36 + n) = make_float4(acc[n], acc[n + 1], acc[n + 2], acc[n + 3]);
+        __syncwarp();
+        // gather first (shared-memory loads and shuffles of all eight row groups in flight together), then issue the
+        // eight reductions back to back: the volatile reduction asm is an ordering point for the loads around it
+        float4 v[8];
+        unsigned long long base[8];
+        int act[8];
 #pragma unroll
-            for (int n = 0; n < 16; n += 4)
-              asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + n), "f"(acc[n]), "f"(acc[n + 1]),
-                           "f"(acc[n + 2]), "f"(acc[n + 3]) : "memory");
+        for (int it = 0; it < 8; ++it) {
+          const int r = it * 4 + (lane >> 3);
+          v[it] = *reinterpret_cast<const float4*>(scratch + r * 36 + (lane & 7) * 4);
+          base[it] = __shfl_sync(0xffffffffu, row_ptr, r);
+          act[it] = __shfl_sync(0xffffffffu, active ? 1 : 0, r);
+        }
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          float* dst = reinterpret_cast<float*>(base[it]) + c32 * 32 + (lane & 7) * 4;
+          if (act[it]) {
+            if (P.direct) {
+              *reinterpret_cast<float4*>(dst) = v[it];
+            } else {
+              asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v[it].x), "f"(v[it].y),
+                           "f"(v[it].z), "f"(v[it].w) : "memory");
+            }
           }
         }
+        __syncwarp();
       }
     }
+    if (warp == 2 && lane == 0) ktrace(P.trace, 21);
   }
   tc_fence_before();
   __syncthreads();
