@@ -256,6 +256,11 @@ inline int tc_run_conv(vcd_plan* p, const Layer& L, bool dgrad, const void* in, 
   if (f == (tc::EPI_RAW | tc::EPI_RES2)) f = tc::EPI_RES | tc::EPI_RES2 | tc::EPI_RAW;
   const bool known = f == 0 || f == 1 || f == 2 || f == 3 || f == 6 || f == 7 || f == 8 || f == 14 || f == 15;
   if (!known) f = 15;
+  if (blk_elems(B, g.creal, Lout) >= (1ull << 31)) {  // the epilogue addresses its operands with 32-bit element offsets
+    snprintf(err, errn, "tc_run_conv(%s): output tensor of %zu elements exceeds the 2^31-element limit of the tensor-core path",
+             L.name.c_str(), blk_elems(B, g.creal, Lout));
+    return 1;
+  }
   if (!e.mask && e.scale != 1.f) { snprintf(err, errn, "tc_run_conv(%s): scale without mask is not supported", L.name.c_str()); return 1; }
   if ((f & tc::EPI_MASK) && !e.mask) { snprintf(err, errn, "tc_run_conv(%s): internal epilogue mismatch", L.name.c_str()); return 1; }
   if ((f & tc::EPI_RES) && !e.res_t) { snprintf(err, errn, "tc_run_conv(%s): internal epilogue mismatch", L.name.c_str()); return 1; }

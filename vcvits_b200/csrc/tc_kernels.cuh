@@ -259,7 +259,7 @@ __device__ __forceinline__ void unpack8(const uint4& raw, float (&f)[8]) {
 }
 
 template <int F>
-__device__ __forceinline__ void epi_prefetch(const Epilogue& e, size_t o, bool valid, EpiLoads& L) {
+__device__ __forceinline__ void epi_prefetch(const Epilogue& e, uint32_t o, bool valid, EpiLoads& L) {
   if (!valid) return;
   if constexpr (F & EPI_MASK) L.mask = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(e.mask) + o));
   if constexpr (F & EPI_RES) L.rest = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(e.res_t) + o));
@@ -275,11 +275,14 @@ __device__ __forceinline__ void epi_prefetch(const Epilogue& e, size_t o, bool v
 }
 
 // bias8: the 8 bias values (bias + per-batch bias) of this channel group, staged in shared memory per tile -- a
-// global bias load here would put a full memory latency on the critical path of every 16-column unit.
+// global bias load here would put a full memory latency on the critical path of every 16-column unit; null when the
+// launch has no bias (data gradients).  plain_out: out_t = bf16(v), no activation (tscale == act_slope == 1).
+// o: 32-bit element offset (the host refuses tensors of 2^31 elements or more).
 template <int F>
-__device__ __forceinline__ void epi_finish(const Epilogue& e, const ConvGeo& g, int b, int ro, int ch0, size_t o,
-                                           const EpiLoads& L, const float* bias8, float (&v)[8]) {
-  {
+__device__ __forceinline__ void epi_finish(const Epilogue& e, const ConvGeo& g, int b, int ro, int ch0, uint32_t o,
+                                           const EpiLoads& L, const float* bias8, bool plain_out, float s_pos, float s_neg,
+                                           float (&v)[8]) {
+  if (bias8 != nullptr) {
     const float4 b0 = *reinterpret_cast<const float4*>(bias8);
     const float4 b1 = *reinterpret_cast<const float4*>(bias8 + 4);
     v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
@@ -289,7 +292,7 @@ __device__ __forceinline__ void epi_finish(const Epilogue& e, const ConvGeo& g, 
     float m[8];
     unpack8(L.mask, m);
 #pragma unroll
-    for (int n = 0; n < 8; ++n) v[n] *= (m[n] > 0.f ? e.scale : e.mask_slope * e.scale);
+    for (int n = 0; n < 8; ++n) v[n] *= (m[n] > 0.f ? s_pos : s_neg);   // s_pos = scale, s_neg = mask_slope * scale
   }
   if constexpr (F & EPI_RES) {
     float t[8];
@@ -305,17 +308,18 @@ __device__ __forceinline__ void epi_finish(const Epilogue& e, const ConvGeo& g, 
     if (e.out_raw) store8<float>(e.out_raw + o, v);
   }
   if (e.out_t) {
-    float a[8];
+    if (!plain_out) {
 #pragma unroll
-    for (int n = 0; n < 8; ++n) {
-      const float x = v[n] * e.tscale;
-      a[n] = x > 0.f ? x : x * e.act_slope;
+      for (int n = 0; n < 8; ++n) {
+        const float x = v[n] * e.tscale;
+        v[n] = x > 0.f ? x : x * e.act_slope;
+      }
     }
     if (e.zu > 0) {
       const int q = (ro + e.zp) / e.zu, r = (ro + e.zp) - q * e.zu;
-      store8<bf16>(reinterpret_cast<bf16*>(e.out_t) + blk_off(b, r * g.creal + ch0, q, e.zu * g.creal, e.zLq), a);
+      store8<bf16>(reinterpret_cast<bf16*>(e.out_t) + blk_off(b, r * g.creal + ch0, q, e.zu * g.creal, e.zLq), v);
     } else {
-      store8<bf16>(reinterpret_cast<bf16*>(e.out_t) + o, a);
+      store8<bf16>(reinterpret_cast<bf16*>(e.out_t) + o, v);
     }
   }
 }
@@ -550,7 +554,10 @@ conv_kernel(const ConvParams P) {
     const Epilogue& e = P.e;
     const int units_per_mt = P.BN / 16;
     const int n_units = P.MT * units_per_mt;
-    const size_t chunk_stride = static_cast<size_t>(padded_len(P.Lout)) * 8;  // next 8-channel group, same row
+    const uint32_t chunk_stride = static_cast<uint32_t>(padded_len(P.Lout)) * 8;  // next 8-channel group, same row (elements)
+    const uint32_t b_stride = static_cast<uint32_t>(P.g.creal >> 3) * chunk_stride;   // next batch item
+    const bool plain_out = e.tscale == 1.f && e.act_slope == 1.f;
+    const float s_pos = e.scale, s_neg = e.mask_slope * e.scale;
     // per-tile state of this thread's row
     struct TileC { int b, r_phase, ch_tile, q_first; uint32_t t_lane; };
     auto tile_coords = [&](int tile, int it) {
@@ -565,7 +572,7 @@ conv_kernel(const ConvParams P) {
       t.t_lane = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(buf * P.MT * P.BN);
       return t;
     };
-    struct UnitC { int ro, ch; bool valid; size_t o; uint32_t taddr; };
+    struct UnitC { int ro, ch; bool valid; uint32_t o; uint32_t taddr; };
     auto unit_coords = [&](const TileC& t, int u) {
       UnitC c;
       const int mt = u >> P.units_shift, c16 = u - (mt << P.units_shift);
@@ -573,7 +580,8 @@ conv_kernel(const ConvParams P) {
       c.ro = q * P.g.os + t.r_phase - P.g.p;
       c.valid = q < P.Lq && c.ro >= 0 && c.ro < P.Lout;
       c.ch = t.ch_tile + c16 * 16;
-      c.o = blk_row(t.b, c.ch >> 3, c.valid ? c.ro : 0, P.g.creal, P.Lout);
+      c.o = static_cast<uint32_t>(t.b) * b_stride + static_cast<uint32_t>(c.ch >> 3) * chunk_stride +
+            static_cast<uint32_t>((c.valid ? c.ro : 0) + kPadL) * 8u;
       c.taddr = t.t_lane + static_cast<uint32_t>(mt * P.BN + c16 * 16);
       return c;
     };
@@ -595,10 +603,6 @@ conv_kernel(const ConvParams P) {
       epi_prefetch<F>(e, uc.o + chunk_stride, uc.valid, bufA[1]);
     }
     const bool has_bias = e.bias != nullptr || e.bias2 != nullptr;
-    if (!has_bias) {  // data-gradient launches: the staged bias vector is zero for every tile
-      bias_s[static_cast<int>(threadIdx.x) - 64] = 0.f;
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-    }
     auto step = [&](EpiLoads (&use)[2], EpiLoads (&fill)[2]) {
       const int buf = P.acc_bufs == 2 ? (it & 1) : 0;
       const int use_n = P.acc_bufs == 2 ? (it >> 1) : it;
@@ -637,7 +641,7 @@ conv_kernel(const ConvParams P) {
 #pragma unroll
           for (int n = 0; n < 8; ++n) v[n] = acc[h * 8 + n];
           epi_finish<F>(e, P.g, tcur.b, uc.ro, uc.ch + h * 8, uc.o + h * chunk_stride, use[h],
-                        bias_s + (has_bias ? (it & 1) * 128 : 0) + (uc.ch - tcur.ch_tile) + h * 8, v);
+                        has_bias ? bias_s + (it & 1) * 128 + (uc.ch - tcur.ch_tile) + h * 8 : nullptr, plain_out, s_pos, s_neg, v);
         }
       }
       if (last) {
