@@ -257,16 +257,18 @@ blocked_to_ncl_kernel(const float* __restrict__ in, float* __restrict__ out, int
 
 // -------------------------------------------------------------------------------------------------
 // cond (speaker conditioning, 1x1 conv on a length-1 input): cb[b][n] = bias[n] + sum_c w[n][c] g[b][c]
-// grid = (ceil(N/128), B), block = 128.
+// grid = (ceil(N/8), B), block = 256: one warp per output (lanes walk the G-long weight row, coalesced).
 // -------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
 cond_fwd_kernel(const float* __restrict__ w, const float* __restrict__ bias, const float* __restrict__ gv,
                 float* __restrict__ cb, int N, int G) {
-  const int n = blockIdx.x * 128 + threadIdx.x, b = blockIdx.y;
+  const int lane = threadIdx.x & 31;
+  const int n = blockIdx.x * 8 + (threadIdx.x >> 5), b = blockIdx.y;
   if (n >= N) return;
-  float s = bias[n];
-  for (int c = 0; c < G; ++c) s = fmaf(w[static_cast<size_t>(n) * G + c], gv[static_cast<size_t>(b) * G + c], s);
-  cb[static_cast<size_t>(b) * N + n] = s;
+  float s = 0.f;
+  for (int c = lane; c < G; c += 32) s = fmaf(__ldg(w + static_cast<size_t>(n) * G + c), __ldg(gv + static_cast<size_t>(b) * G + c), s);
+  s = warp_sum(s);
+  if (lane == 0) cb[static_cast<size_t>(b) * N + n] = s + bias[n];
 }
 
 // Backward of cond + conv_pre.bias from dcb[b][n] = sum_t d0[b][t][n].

@@ -267,7 +267,8 @@ inline int tc_run_conv(vcd_plan* p, const Layer& L, bool dgrad, const void* in, 
   // VCD_PDL bit 0: forward launches, bit 1: data-gradient launches.  In the backward pass an early-started successor
   // holds shared memory / TMEM that the concurrent weight-gradient CTAs need (measured: +7 % on the segment), so
   // only the forward chain uses it by default.
-  static const int pdl_mask = tc_env_int("VCD_PDL", 1);
+  static const int pdl_mask = tc_env_int("VCD_PDL", 1), pdl_late_mask = tc_env_int("VCD_PDL_LATE", 2);
+  P.pdl_late = (pdl_late_mask & (dgrad ? 2 : 1)) != 0 ? 1 : 0;
   const cudaError_t ce = tc_conv_dispatch(f, &P, grid, smem, stream, (pdl_mask & (dgrad ? 2 : 1)) != 0);
   launches.fetch_add(1, std::memory_order_relaxed);
   if (ce != cudaSuccess) {

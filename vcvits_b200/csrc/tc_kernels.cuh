@@ -230,6 +230,7 @@ struct ConvParams {
   int minshift;           // min over taps of j*step (<= 0)
   int acc_bufs;           // 2: accumulators double-buffered (epilogue overlaps the next tile's MMAs); 1: MT*BN > 256
   uint32_t tmem_cols;
+  int pdl_late;           // 1: release the stream successor after this CTA's last MMAs are issued (default: at its last tile's loads)
   unsigned long long* trace;  // debug: %globaltimer stamps of CTA 0 (null = off)
 };
 
@@ -377,7 +378,7 @@ conv_kernel(const ConvParams P) {
     pdl_wait();   // the activations are the stream predecessor's output (weights are older: their producer does not wait)
     for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
       // last tile of this CTA: the successor kernel may start its prologue (barriers, TMEM, weight loads) now
-      if (tile + static_cast<int>(gridDim.x) >= P.total_tiles) pdl_launch();
+      if (!P.pdl_late && tile + static_cast<int>(gridDim.x) >= P.total_tiles) pdl_launch();
       int b, mg;
       P.d_mgroups.divmod(P.d_tiles_n.quot(tile), b, mg);
       const int row0 = mg * 128 * P.MT + P.g.off0 + P.minshift;
@@ -545,6 +546,7 @@ conv_kernel(const ConvParams P) {
     } else {
       issue_tiles(integral_constant<int, 1>{}, integral_constant<int, 0>{});
     }
+    if (P.pdl_late) pdl_launch();
     if (lane == 0) ktrace(P.trace, 5);
   } else if (warp >= 2 && warp <= 9) {
     // ===================== epilogue warps =====================
@@ -603,12 +605,19 @@ conv_kernel(const ConvParams P) {
       epi_prefetch<F>(e, uc.o + chunk_stride, uc.valid, bufA[1]);
     }
     const bool has_bias = e.bias != nullptr || e.bias2 != nullptr;
+    // one column tile and no per-batch bias: the bias vector is the same for every tile of the launch -- stage it once
+    const bool bias_once = has_bias && P.n_tiles_n == 1 && e.bias2 == nullptr;
+    if (bias_once) {
+      const int et = static_cast<int>(threadIdx.x) - 64;
+      if (et < P.BN) bias_s[et] = __ldg(e.bias + et);
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+    }
     auto step = [&](EpiLoads (&use)[2], EpiLoads (&fill)[2]) {
       const int buf = P.acc_bufs == 2 ? (it & 1) : 0;
       const int use_n = P.acc_bufs == 2 ? (it >> 1) : it;
       const bool first = u == half;                      // first unit of this warp in the tile
       const bool last = u + 2 >= n_units;                // last unit of this warp in the tile
-      if (first && has_bias) {  // stage this tile's bias vector (named barrier 1 = the 256 epilogue threads)
+      if (first && has_bias && !bias_once) {  // stage this tile's bias vector (named barrier 1 = the 256 epilogue threads)
         const int et = static_cast<int>(threadIdx.x) - 64;
         if (et < P.BN) {
           float bv = e.bias ? __ldg(e.bias + tcur.ch_tile + et) : 0.f;
@@ -641,7 +650,8 @@ conv_kernel(const ConvParams P) {
 #pragma unroll
           for (int n = 0; n < 8; ++n) v[n] = acc[h * 8 + n];
           epi_finish<F>(e, P.g, tcur.b, uc.ro, uc.ch + h * 8, uc.o + h * chunk_stride, use[h],
-                        has_bias ? bias_s + (it & 1) * 128 + (uc.ch - tcur.ch_tile) + h * 8 : nullptr, plain_out, s_pos, s_neg, v);
+                        has_bias ? bias_s + (bias_once ? 0 : (it & 1) * 128) + (uc.ch - tcur.ch_tile) + h * 8 : nullptr, plain_out,
+                        s_pos, s_neg, v);
         }
       }
       if (last) {

@@ -905,8 +905,8 @@ extern "C" int vcd_forward(vcd_plan* p, int mode, const float* x, int64_t xs_b, 
   }
   if (gvec) {
     ProfScope ps__(PC_MISC, 0, 0, stream);
-    dim3 grid((C0 + 127) / 128, B);
-    cond_fwd_kernel<<<grid, 128, 0, stream>>>(p->h_params[p->p_cond_w], p->h_params[p->p_cond_b], gvec, PF(w.cb), C0,
+    dim3 grid((C0 + 7) / 8, B);
+    cond_fwd_kernel<<<grid, 256, 0, stream>>>(p->h_params[p->p_cond_w], p->h_params[p->p_cond_b], gvec, PF(w.cb), C0,
                                               p->cfg.gin_channels);
     LAUNCH_CHECK("cond_fwd_kernel");
   }
