@@ -611,6 +611,14 @@ WsLayout make_layout(const vcd_plan* p, int mode, int B, int T, bool save) {
 
 // Pad-zeroing job tables are uploaded once per layout (outside any stream capture) and cached in the plan.
 int ensure_pad_tables(vcd_plan* p, const WsLayout& w, int mode, int B, int T, bool save) {
+  if (p->pad_tables.size() >= 1024) {  // many distinct shapes (variable-length inference): start over.  Captured graphs
+    CU_TRY(cudaDeviceSynchronize());   // hold the table addresses, so they go first.
+    for (auto& kv : p->graphs) cudaGraphExecDestroy(kv.second);
+    p->graphs.clear();
+    p->graph_kernels.clear();
+    for (auto& kv : p->pad_tables) cudaFree(kv.second);
+    p->pad_tables.clear();
+  }
   for (int bwd = 0; bwd < 2; ++bwd) {
     const auto& phases = bwd ? w.pad_bwd : w.pad_fwd;
     for (size_t ph = 0; ph < phases.size(); ++ph) {
@@ -854,11 +862,8 @@ int run_graphed(vcd_plan* p, const GraphKey& key, cudaStream_t stream, F&& enque
   cudaGraphDestroy(graph);
   if (ie != cudaSuccess) return fail("cudaGraphInstantiate failed: %s", cudaGetErrorString(ie));
   if (p->graphs.size() >= 64) {  // bounded cache: drop everything (shapes / workspaces keep changing)
+    // replays still in flight keep their executable alive until they finish (cudaGraphExecDestroy defers the release)
     for (auto& kv : p->graphs) cudaGraphExecDestroy(kv.second);
-  for (auto& kv : p->pad_tables) cudaFree(kv.second);
-  if (p->own) cudaStreamDestroy(p->own);
-  if (p->hop_in) cudaEventDestroy(p->hop_in);
-  if (p->hop_out) cudaEventDestroy(p->hop_out);
     p->graphs.clear();
     p->graph_kernels.clear();
   }
