@@ -266,3 +266,24 @@ def test_tensor_core_path_ragged_shapes(B, T):
     den = sum(float(gref[n].pow(2).sum()) for n in gref)
     assert (num / den) ** 0.5 <= 0.12
     assert all(torch.isfinite(v).all() for v in g16.values())
+
+
+def test_many_distinct_shapes_recycle_the_graph_cache():
+    """Variable-length inference: more distinct (B, T) shapes than the captured-graph cache holds (64).  The cache is
+    dropped and rebuilt; results must not change and the plan must stay usable."""
+    from vcvits_b200 import Generator
+    sd = O.seeded_state_dict(O.SMALL_CFG, 7, gain=1.1)
+    m = Generator(**O.SMALL_CFG, mode="bf16")
+    m.load_state_dict(sd)
+    m = m.cuda()
+    torch.manual_seed(3)
+    g = torch.randn(1, O.SMALL_CFG["gin_channels"], 1).cuda()
+    xs = {T: torch.randn(1, O.SMALL_CFG["initial_channel"], T).cuda() for T in range(4, 74)}
+    first = {}
+    with torch.no_grad():
+        for T, x in xs.items():          # 70 shapes: evicts the cache at least once
+            first[T] = m(x, g).clone()
+        for T in (4, 40, 73):            # recapture after eviction
+            again = m(xs[T], g)
+            assert torch.equal(again, first[T]), T
+    torch.cuda.synchronize()

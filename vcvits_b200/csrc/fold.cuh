@@ -176,14 +176,16 @@ __device__ __forceinline__ float unfold_fetch(const UnfoldJob& jb, const float* 
 __global__ void __launch_bounds__(256)
 wn_unfold_kernel(const UnfoldJob* __restrict__ jobs, int njobs, const float* const* __restrict__ params,
                  float* const* __restrict__ dparams, const float* __restrict__ norms,
-                 const float* __restrict__ scratch) {
+                 const float* __restrict__ scratch, int block_base) {
+  // block_base: first_block of jobs[0] when only a tail slice of a segment's table is launched
+  const int blk = static_cast<int>(blockIdx.x) + block_base;
   int lo = 0, hi = njobs - 1;
   while (lo < hi) {
     const int mid = (lo + hi + 1) >> 1;
-    if (jobs[mid].first_block <= static_cast<int>(blockIdx.x)) lo = mid; else hi = mid - 1;
+    if (jobs[mid].first_block <= blk) lo = mid; else hi = mid - 1;
   }
   const UnfoldJob jb = jobs[lo];
-  const int row = blockIdx.x - jb.first_block;
+  const int row = blk - jb.first_block;
   if (jb.kind == 1) {
     const long long e = static_cast<long long>(row) * 256 + threadIdx.x;
     if (e < jb.numel) dparams[jb.p_w][e] = scratch[jb.src_off + e];

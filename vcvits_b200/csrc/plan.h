@@ -43,6 +43,7 @@ struct Layer {
 struct SegmentJobs {
   UnfoldJob* d_jobs = nullptr;
   int njobs = 0, nblocks = 0;
+  int lead_jobs = 0, lead_blocks = 0;            // jobs / blocks ahead of the first layer's (conv_post.weight in segment 0)
   long long scratch_begin = 0, scratch_end = 0;  // float range of the gradient scratch to zero
   std::vector<int> params;
 };
@@ -99,7 +100,7 @@ struct vcd_plan {
   std::vector<vcd::SegmentJobs> segments;
 
   // auxiliary streams / events for intra-step concurrency (ResBlock branches, weight-gradient kernels)
-  static constexpr int kMaxAux = 12, kMaxEvents = 256;
+  static constexpr int kMaxAux = 14, kMaxEvents = 256;   // 7 branch + 4 weight-gradient side streams + 3 helpers
   cudaStream_t aux[kMaxAux] = {};
   cudaStream_t own = nullptr;              // stands in for the legacy default stream (not capturable)
   cudaEvent_t hop_in = nullptr, hop_out = nullptr;

@@ -409,6 +409,8 @@ extern "C" int vcd_plan_create(const vcd_config* cfg, vcd_plan** out_plan) {
       sj.params.push_back(param);
     };
     if (seg == 0) copy_job(p->p_post_w, p->post_dw);
+    sj.lead_jobs = static_cast<int>(uj.size());
+    sj.lead_blocks = blk;
     for (const Layer& L : p->layers) {
       if (L.segment != seg) continue;
       const ParamInfo& pw = p->params[L.p_w];
@@ -1041,11 +1043,30 @@ extern "C" int vcd_backward(vcd_plan* p, int mode, const float* dy, const float*
   Ls[0] = T;
   for (int i = 0; i < S; ++i) Ls[i + 1] = Ls[i] * p->stages[i].u;
 
+  // Helper streams outside the captured graphs: the gradient-scratch zero-fill of the NEXT requested segment and
+  // conv_post's weight gradient run beside the current segment's graph instead of in front of it.
+  cudaStream_t zst = c.serial ? stream : p->aux[vcd_plan::kMaxAux - 1];
+  cudaStream_t wst = c.serial ? stream : p->aux[vcd_plan::kMaxAux - 2];
+  auto zero_scratch = [&](int sg, cudaStream_t st) -> int {
+    const SegmentJobs& z = p->segments[sg];
+    if (z.scratch_end > z.scratch_begin)
+      CU_TRY(cudaMemsetAsync(p->d_gscratch + z.scratch_begin, 0, (z.scratch_end - z.scratch_begin) * sizeof(float), st));
+    return 0;
+  };
+  bool first_seg = true;
   for (int seg = 0; seg <= S; ++seg) {
     if (!(segment_mask & (1u << seg))) continue;
     const SegmentJobs& sj = p->segments[seg];
-    if (sj.scratch_end > sj.scratch_begin)
-      CU_TRY(cudaMemsetAsync(p->d_gscratch + sj.scratch_begin, 0, (sj.scratch_end - sj.scratch_begin) * sizeof(float), stream));
+    if (first_seg) TRY(zero_scratch(seg, stream));   // later segments: zeroed beside the previous segment (below)
+    first_seg = false;
+    int next_seg = -1;
+    for (int k = seg + 1; k <= S; ++k)
+      if (segment_mask & (1u << k)) { next_seg = k; break; }
+    if (next_seg >= 0) {
+      c.order(stream, zst);
+      TRY(zero_scratch(next_seg, zst));
+    }
+    bool post_forked = false;
     if (seg == 0) {  // conv_post + tanh backward -> gradient w.r.t. the last stage output
       const int C = p->stages[S - 1].cout, L = Ls[S];
       const int splits = std::max(1, std::min(64, L / 2048));
@@ -1054,18 +1075,25 @@ extern "C" int vcd_backward(vcd_plan* p, int mode, const float* dy, const float*
       const float* wpost = p->h_params[p->p_post_w];
       const int slot = (S - 1) & 1;
       ProfScope ps__(PC_POST, 4.0 * C * 7 * B * L, static_cast<double>(B) * L * (C * 3 * es + 16), stream);
+      // weight gradient (+ its copy into the caller's tensor) beside the data-gradient chain
+      c.order(stream, wst);
+      post_forked = wst != stream;
       if (f32) {
-        conv_post_wgrad_kernel<float><<<gw, 256, 0, stream>>>(dy, y, static_cast<const float*>(P(w.a[S])), p->d_gscratch + p->post_dw, C, L);
+        conv_post_wgrad_kernel<float><<<gw, 256, 0, wst>>>(dy, y, static_cast<const float*>(P(w.a[S])), p->d_gscratch + p->post_dw, C, L);
         LAUNCH_CHECK("conv_post_wgrad_kernel");
         conv_post_dgrad_kernel<float><<<gd, 128, 0, stream>>>(dy, y, wpost, static_cast<const float*>(P(w.a[S])), kFinalSlope, 1.f / NB,
                                                                nullptr, static_cast<float*>(P(w.Gi[slot])), C, L);
       } else {
-        conv_post_wgrad_kernel<bf16><<<gw, 256, 0, stream>>>(dy, y, static_cast<const bf16*>(P(w.a[S])), p->d_gscratch + p->post_dw, C, L);
+        conv_post_wgrad_kernel<bf16><<<gw, 256, 0, wst>>>(dy, y, static_cast<const bf16*>(P(w.a[S])), p->d_gscratch + p->post_dw, C, L);
         LAUNCH_CHECK("conv_post_wgrad_kernel");
         conv_post_dgrad_kernel<bf16><<<gd, 128, 0, stream>>>(dy, y, wpost, static_cast<const bf16*>(P(w.a[S])), kFinalSlope, 1.f / NB,
                                                               nullptr, static_cast<bf16*>(P(w.Gi[slot])), C, L);
       }
       LAUNCH_CHECK("conv_post_dgrad_kernel");
+      if (sj.lead_blocks > 0) {
+        wn_unfold_kernel<<<sj.lead_blocks, 256, 0, wst>>>(sj.d_jobs, sj.lead_jobs, p->d_params, p->d_dparams, p->d_norms, p->d_gscratch, 0);
+        LAUNCH_CHECK("wn_unfold_kernel");
+      }
     }
     auto core = [&]() -> int {
     int side_rr = 0;
@@ -1176,9 +1204,10 @@ extern "C" int vcd_backward(vcd_plan* p, int mode, const float* dy, const float*
     // join the side streams, then the weight-norm backward of this segment's parameters
     for (int k = 0; k < 4; ++k)
       if (side_used[k]) c.order(c.side(k), stream);
-    if (sj.nblocks) {
+    if (sj.nblocks > sj.lead_blocks) {  // (the jobs ahead of the first layer ran with conv_post's weight gradient)
       ProfScope ps__(PC_FOLD, 0, 8.0 * (sj.scratch_end - sj.scratch_begin), stream);
-      wn_unfold_kernel<<<sj.nblocks, 256, 0, stream>>>(sj.d_jobs, sj.njobs, p->d_params, p->d_dparams, p->d_norms, p->d_gscratch);
+      wn_unfold_kernel<<<sj.nblocks - sj.lead_blocks, 256, 0, stream>>>(sj.d_jobs + sj.lead_jobs, sj.njobs - sj.lead_jobs, p->d_params,
+                                                                       p->d_dparams, p->d_norms, p->d_gscratch, sj.lead_blocks);
       LAUNCH_CHECK("wn_unfold_kernel");
     }
     return 0;
@@ -1187,6 +1216,8 @@ extern "C" int vcd_backward(vcd_plan* p, int mode, const float* dy, const float*
       PhaseScope ph__(("backward segment " + std::to_string(seg)).c_str(), stream);
       TRY(run_graphed(p, GraphKey{1 + seg, mode, B, T, 1, gvec ? 1 : 0, dx ? 1 : 0, ws, p->params_version}, stream, core));
     }
+    if (post_forked) c.order(wst, stream);
+    if (next_seg >= 0) c.order(zst, stream);
     if (seg == S) {  // kernels that touch caller-owned tensors: cond / conv_pre.bias gradients, dg, dx
       const Layer& L = p->layers[p->l_pre];
       {
