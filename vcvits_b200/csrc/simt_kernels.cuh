@@ -334,15 +334,24 @@ conv_post_fwd_kernel(const T* __restrict__ a, const float* __restrict__ w, float
   float acc = 0.f;
   for (int cg = 0; cg < (C >> 3); ++cg) {
     const T* base = a + blk_row(b, cg, 0, C, L);
+    // branch-free: all seven row loads of the channel group are in flight before the first FMA (out-of-range taps
+    // re-read row t and are masked out), instead of one L2 round trip per tap
+    float v[7][8];
 #pragma unroll
     for (int j = 0; j < 7; ++j) {
       const int r = t + j - 3;
-      if (r < 0 || r >= L) continue;
-      float v[8];
-      load8<T>(base + static_cast<size_t>(r) * 8, v);
-      const float* wr = ws + j * C + cg * 8;
+      const bool ok = r >= 0 && r < L;
+      load8<T>(base + static_cast<size_t>(ok ? r : t) * 8, v[j]);
+    }
 #pragma unroll
-      for (int c = 0; c < 8; ++c) acc = fmaf(v[c], wr[c], acc);
+    for (int j = 0; j < 7; ++j) {
+      const int r = t + j - 3;
+      const float keep = (r >= 0 && r < L) ? 1.f : 0.f;
+      const float* wr = ws + j * C + cg * 8;
+      float part = 0.f;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) part = fmaf(v[j][c], wr[c], part);
+      acc = fmaf(part, keep, acc);
     }
   }
   y[static_cast<size_t>(b) * L + t] = tanhf(acc);
@@ -358,26 +367,32 @@ conv_post_dgrad_kernel(const float* __restrict__ dy, const float* __restrict__ y
                        T* __restrict__ out_t, int C, int L) {
   const int t = blockIdx.x * 128 + threadIdx.x;
   const int cg = blockIdx.y, b = blockIdx.z;
+  __shared__ float wsm[56];   // the channel group's [8][7] weights
+  if (threadIdx.x < 56) wsm[threadIdx.x] = __ldg(w + cg * 56 + threadIdx.x);
+  __syncthreads();
   if (t >= L) return;
-  float dp[7];
+  // branch-free operand fetch: every load is issued before the first dependent instruction
+  float yy[7], dd[7], dp[7];
 #pragma unroll
   for (int j = 0; j < 7; ++j) {
     const int s = t + 3 - j;
-    if (s >= 0 && s < L) {
-      const float yy = __ldg(y + static_cast<size_t>(b) * L + s);
-      dp[j] = __ldg(dy + static_cast<size_t>(b) * L + s) * (1.f - yy * yy);
-    } else {
-      dp[j] = 0.f;
-    }
+    const bool ok = s >= 0 && s < L;
+    yy[j] = __ldg(y + static_cast<size_t>(b) * L + (ok ? s : t));
+    dd[j] = __ldg(dy + static_cast<size_t>(b) * L + (ok ? s : t));
   }
   const size_t o = blk_off(b, cg * 8, t, C, L);
   float m[8], v[8];
   load8<T>(a + o, m);
 #pragma unroll
+  for (int j = 0; j < 7; ++j) {
+    const int s = t + 3 - j;
+    dp[j] = (s >= 0 && s < L) ? dd[j] * (1.f - yy[j] * yy[j]) : 0.f;
+  }
+#pragma unroll
   for (int c = 0; c < 8; ++c) {
     float s = 0.f;
 #pragma unroll
-    for (int j = 0; j < 7; ++j) s = fmaf(__ldg(w + (cg * 8 + c) * 7 + j), dp[j], s);
+    for (int j = 0; j < 7; ++j) s = fmaf(wsm[c * 7 + j], dp[j], s);
     v[c] = s * (m[c] > 0.f ? 1.f : mask_slope) * scale;
   }
   if (out_raw) store8<float>(out_raw + o, v);
