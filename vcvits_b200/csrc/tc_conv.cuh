@@ -279,7 +279,7 @@ inline int tc_run_conv(vcd_plan* p, const Layer& L, bool dgrad, const void* in, 
 }
 
 inline int tc_run_wgrad(vcd_plan* p, const Layer& L, const void* in, const void* dout, float* dwp, float* dbias, int B, int Lin,
-                        int Ld, cudaStream_t stream, std::atomic<uint64_t>& launches, char* err, size_t errn) {
+                        int Ld, bool tail, cudaStream_t stream, std::atomic<uint64_t>& launches, char* err, size_t errn) {
   const ConvGeo& g = L.wgr;
   tc::WgradParams P{};
   P.dwp = dwp;
@@ -351,7 +351,10 @@ inline int tc_run_wgrad(vcd_plan* p, const Layer& L, const void* in, const void*
   // CTA per SM when the weight gradient is small (C <= 64: the kernel is bound by the per-SM load rate)
   static const int env_ctas = tc_env_int("VCD_WGRAD_CTAS", 0);
   static const int env_small = tc_env_int("VCD_WGRAD_CTAS_SMALL", 64), env_big = tc_env_int("VCD_WGRAD_CTAS_BIG", 32);
-  const int target_ctas = env_ctas > 0 ? env_ctas : (static_cast<long long>(g.taps) * g.K * g.N <= 64 * 64 * 11 ? env_small : env_big);
+  // tail launches (the last weight gradients of a segment: nothing else is left to share the SMs with) may spread wider
+  static const int env_tail = tc_env_int("VCD_WGRAD_CTAS_TAIL", 96);
+  int target_ctas = env_ctas > 0 ? env_ctas : (static_cast<long long>(g.taps) * g.K * g.N <= 64 * 64 * 11 ? env_small : env_big);
+  if (tail && env_tail > 0) target_ctas = env_tail;
   const long long base_ctas = 1LL * P.n_mtiles * P.n_ntiles * P.n_tgroups;
   P.kb_per_item = (Ld + P.TK - 1) / P.TK;
   const long long total_kb = 1LL * B * P.kb_per_item;

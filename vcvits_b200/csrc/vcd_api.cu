@@ -753,13 +753,14 @@ int run_conv(const Ctx& c, cudaStream_t st, const Layer& L, bool dgrad, const vo
 
 // Weight gradient (+ bias gradient) of layer L: in = layer input (length Lin), dout = gradient w.r.t. the layer
 // output in the layer's wgr view (length Ld; for ConvTranspose1d the phase-packed tensor).
-int run_wgrad(const Ctx& c, cudaStream_t st, const Layer& L, const void* in, const void* dout, int Lin, int Ld, double flops) {
+int run_wgrad(const Ctx& c, cudaStream_t st, const Layer& L, const void* in, const void* dout, int Lin, int Ld, double flops,
+              bool tail = false) {
   const ConvGeo& g = L.wgr;
   float* dwp = c.p->d_gscratch + L.dwp;
   if (c.mode == VCD_MODE_BF16 && L.tc_ok_wgr) {
     ProfScope ps__(PC_TC_WGRAD, flops, 0, st, (L.name + ":wgrad").c_str());
     // the bias gradient (column sums of dout) is produced by the same kernel
-    TRY(tc_run_wgrad(c.p, L, in, dout, dwp, L.dbias >= 0 ? c.p->d_gscratch + L.dbias : nullptr, c.B, Lin, Ld, st, g_launches,
+    TRY(tc_run_wgrad(c.p, L, in, dout, dwp, L.dbias >= 0 ? c.p->d_gscratch + L.dbias : nullptr, c.B, Lin, Ld, tail, st, g_launches,
                      g_err, sizeof(g_err)));
     return 0;
   } else {
@@ -1140,7 +1141,7 @@ extern "C" int vcd_backward(vcd_plan* p, int mode, const float* dy, const float*
             ev_first = c.serial ? nullptr : c.record(sjs);
           }
           const Layer& L1 = p->layers[sd.convs[j][q][0]];
-          TRY(run_wgrad(c, side_after(ev_first), L1, in_first, d_first, L, L, layer_flops(L1, B, L)));
+          TRY(run_wgrad(c, side_after(ev_first), L1, in_first, d_first, L, L, layer_flops(L1, B, L), q == 0 && j == NB - 1));
           Epilogue e = epi();
           e.mask = in_first;
           e.mask_slope = kSlope;
@@ -1171,7 +1172,7 @@ extern "C" int vcd_backward(vcd_plan* p, int mode, const float* dy, const float*
       // upsample conv: weight/bias gradients (side stream) and data gradient, fused with the lrelu mask and the
       // 1/NB of the previous stage's branch mean
       cudaEvent_t ev_du = c.serial ? nullptr : c.record(stream);
-      TRY(run_wgrad(c, side_after(ev_du), U, P(w.a[i]), P(w.duz), Lprev, Lz, layer_flops(U, B, Lprev)));
+      TRY(run_wgrad(c, side_after(ev_du), U, P(w.a[i]), P(w.duz), Lprev, Lz, layer_flops(U, B, Lprev), true));
       Epilogue e = epi();
       e.mask = P(w.a[i]);
       e.mask_slope = kSlope;
