@@ -1,6 +1,11 @@
 // Microbenchmark: tcgen05.mma issue/execute rate for the operand layouts the conv / wgrad kernels use.
-//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o /tmp/mma_rate tools/mma_rate.cu && /tmp/mma_rate
-// Prints clocks per MMA (issue loop + drain) for M x N x 16 bf16 MMAs, operands in shared memory.
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o build_tools/mma_rate tools/mma_rate.cu   (also built by
+//   __graft_entry__.build()); run on the GPU box: gpurun -- ./build_tools/mma_rate
+// Prints clocks per MMA (issue loop, and issue loop + drain) for M x N x 16 bf16 MMAs with both operands in shared memory,
+// for 1 and 2 CTAs per SM, 1..4 issuing warps, and three issue-loop shapes: unroll=0 runtime kk loop with one elect per MMA,
+// unroll=1 one elected block of two MMAs per tap, unroll=2 one elected block per tile.  Results on B200 (this round):
+//   128xNx16: 40 / 48 / 64 / 128 clk at N = 32 / 64 / 128 / 256 (= (128+N)/4: operand fetch at 128 B/clk; math-bound from N = 128),
+//   never below ~23 clk per MMA, 85-87 clk per MMA with unroll=0 whatever the shape.
 #include <cstdio>
 #include <cstdlib>
 
@@ -99,11 +104,8 @@ static void run(const char* name, RateParams P, int ctas_per_sm) {
   P.out = d;
   const int smem = ctas_per_sm == 1 ? 200 * 1024 : 110 * 1024;
   cudaFuncSetAttribute(rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  RateParams Q = P;
-  if (ctas_per_sm == 2) {
-    // B region at +96 KB does not fit: the kernel uses smem + 96 KB; keep everything inside 110 KB
-  }
-  for (int rep = 0; rep < 2; ++rep) rate_kernel<<<grid, 128, smem>>>(Q);
+  // operands: A region at +0, B region at +64 KB (both fit the 110 KB of the two-CTAs-per-SM runs)
+  for (int rep = 0; rep < 2; ++rep) rate_kernel<<<grid, 128, smem>>>(P);
   cudaError_t err = cudaDeviceSynchronize();
   if (err != cudaSuccess) { printf("%-44s ERROR %s\n", name, cudaGetErrorString(err)); exit(1); }
   long long h[2 * 296];
