@@ -7,10 +7,12 @@
 //               A dilated tap is the SAME tile read through a descriptor whose start address is advanced by
 //               shift*16 B: descriptor SBO = 128 B makes rows uniformly 16 B apart, LBO = RA*16 B.
 //     W stage : [K_blk/8][BN cols][8]   -- K-major B operand, LBO = BN*16 B, SBO = 128 B.
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer,
-// warps 2..5 = epilogue (TMEM -> registers -> fused bias/mask/residual/leaky_relu -> global).
-// The kernel is persistent: each CTA walks a static tile list; TMEM accumulators are double-buffered so the
-// epilogue of tile i overlaps the MMAs of tile i+1.
+// Two kernels share these helpers: conv_kernel (forward / data gradient; 352 threads: activation producer, weight
+// producer, MMA issuer, eight epilogue warps) and wgrad_kernel (weight gradient; 192 threads: tensor-TMA producer,
+// MMA issuer, four epilogue warps).  Both are persistent over a static tile / split list; conv_kernel's TMEM
+// accumulators are double-buffered so the epilogue of tile i overlaps the MMAs of tile i+1.  The MMA issue loops are
+// compile-time shaped (one elected block of straight-line UTCHMMA per tap): see tools/mma_rate.cu for the measured
+// issue / operand-fetch rates that motivate it.
 #pragma once
 #include <cuda.h>
 
