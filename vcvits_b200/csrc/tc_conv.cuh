@@ -180,6 +180,11 @@ inline int tc_run_conv(vcd_plan* p, const Layer& L, bool dgrad, const void* in, 
     static const int force_mt = tc_env_int("VCD_CONV_MT", 0);
     if (force_mt > 0 && force_mt * P.BN <= 512 && force_mt <= mtiles) { MT = force_mt; bufs = 2 * MT * P.BN <= 512 ? 2 : 1; }
   }
+  const int kb0 = P.KB;
+  size_t a_stage = 0, w_region = 0;
+  for (;; MT /= 2) {  // a row-tile count whose rings do not fit the shared-memory budget falls back to the next smaller one
+  bufs = 2 * MT * P.BN <= 512 ? 2 : 1;
+  P.KB = kb0;
   P.MT = MT;
   P.acc_bufs = bufs;
   P.n_mgroups = (mtiles + MT - 1) / MT;
@@ -197,7 +202,7 @@ inline int tc_run_conv(vcd_plan* p, const Layer& L, bool dgrad, const void* in, 
   static const int amax_kb = tc_env_int("VCD_CONV_AMAX_KB", 96);
   const size_t a_cap = (can_reside ? 96 : static_cast<size_t>(amax_kb)) * 1024;
   while (P.KB > 16 && 2 * static_cast<size_t>(MT) * (P.KB / 8) * P.RA * 16 > a_cap) P.KB /= 2;
-  const size_t a_stage = static_cast<size_t>(MT) * (P.KB / 8) * P.RA * 16;
+  a_stage = static_cast<size_t>(MT) * (P.KB / 8) * P.RA * 16;
   const size_t w_tap = static_cast<size_t>(P.KB / 8) * P.BN * 16;
   const size_t w_all = w_tap * g.taps * (g.K / P.KB);
   static const int smem_kb = tc_env_int("VCD_CONV_SMEM_KB", 220);
@@ -209,11 +214,15 @@ inline int tc_run_conv(vcd_plan* p, const Layer& L, bool dgrad, const void* in, 
   }
   if (P.NA * a_stage > budget / 2) P.NA = 2;
   P.w_resident = (P.n_tiles_n == 1 && w_all <= 100 * 1024 && P.NA * a_stage + w_all <= budget) ? 1 : 0;
-  size_t w_region;
   if (P.w_resident) {
     P.TPS = g.taps; P.NW = 1;
     w_region = w_all;
   } else {
+    if (P.NA * a_stage + 2 * w_tap > budget) {  // not even two one-tap weight stages beside the activation stages
+      if (MT > 1) continue;
+      snprintf(err, errn, "tc_run_conv(%s): no room for the weight ring", L.name.c_str());
+      return 1;
+    }
     int tps = static_cast<int>((32 * 1024) / w_tap);
     if (tps < 1) tps = 1;
     if (tps > g.taps) tps = g.taps;
@@ -221,11 +230,14 @@ inline int tc_run_conv(vcd_plan* p, const Layer& L, bool dgrad, const void* in, 
     while (nw < 2 && tps > 1) { --tps; nw = static_cast<int>((budget - P.NA * a_stage) / (tps * w_tap)); }
     if (nw > 6) nw = 6;
     if (nw < 2) {
+      if (MT > 1) continue;
       snprintf(err, errn, "tc_run_conv(%s): no room for the weight ring", L.name.c_str());
       return 1;
     }
     P.TPS = tps; P.NW = nw;
     w_region = static_cast<size_t>(tps) * nw * w_tap;
+  }
+  break;
   }
   const size_t smem = 128 + P.NA * a_stage + w_region + (2 * P.NA + 16 + 4) * 8 + 16 + 2 * 128 * 4;
   if (smem > 227 * 1024) {
