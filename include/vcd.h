@@ -35,7 +35,10 @@ extern "C" {
 
 /* Arithmetic mode of the decoder activations / tensor-core operands. */
 #define VCD_MODE_FP32 0 /* fp32 storage, fp32 FFMA math: the parity mode (<=1e-4 max-abs vs. the oracle)   */
-#define VCD_MODE_BF16 1 /* bf16 operands on tcgen05 tensor cores, fp32 accumulation and residual stream */
+#define VCD_MODE_BF16 1 /* bf16 operands on tcgen05 tensor cores, fp32 accumulation in TMEM.  Every tensor kept between
+                         * layers is bf16(leaky_relu(.)); the raw residual stream of a ResBlock is NOT stored but recovered
+                         * from that bf16 tensor through the exact inverse of leaky_relu; fp32 survives
+                         * only in the running sums over ResBlock branches and the boundary tensors. */
 
 /* Constructor arguments of `Generator` (synthesizer_tts.py:71-78; values from configs/base.json:55-67). */
 typedef struct vcd_config {
@@ -77,10 +80,13 @@ int vcd_hop(const vcd_plan* plan);
  * keeps every activation the backward pass needs (training step); 0 recycles buffers (infer.py path). */
 size_t vcd_workspace_bytes(const vcd_plan* plan, int mode, int B, int T, int save_for_backward);
 
-/* Stands in for the weight_norm forward pre-hooks (modules.py:10,190-199,229-230: w = g * v / ||v||) plus
- * `remove_weight_norm` (modules.py:218-222): folds all parameters into the packed operand layouts the
- * kernels consume.  params_dev_ptrs: host array of vcd_num_params() DEVICE pointers (fp32, contiguous,
- * shapes per vcd_param_info).  Must be called after every parameter update and before forward. */
+/* Stands in for the weight_norm forward pre-hooks (modules.py:10,190-199,229-230: w = g * v / ||v||):
+ * folds all parameters into the packed operand layouts the kernels consume.  params_dev_ptrs: host array
+ * of vcd_num_params() DEVICE pointers (fp32, contiguous, shapes per vcd_param_info).  Must be called after
+ * every parameter update and before forward.
+ * `remove_weight_norm` (modules.py:218-222): a NULL pointer in a `weight_g` slot says that layer carries no
+ * weight norm any more -- its `weight_v` slot then holds the baked weight, which is used as is (and whose
+ * plain gradient vcd_backward returns in the `weight_v` slot; the `weight_g` gradient pointer may be NULL). */
 int vcd_fold_weights(vcd_plan* plan, int mode, const float* const* params_dev_ptrs, void* stream);
 
 /* Stands in for Generator.forward(x, g) (call sites synthesizer_tts.py:140, synthesizer_svc.py:87,108).
@@ -141,6 +147,21 @@ int vcd_phase_dump(int reset);
 
 /* Debug only: 64 in-kernel %globaltimer stamps of the kernel selected with the VCD_KTRACE environment variable. */
 int vcd_debug_read_trace(vcd_plan* plan, unsigned long long* out64);
+
+/* Debug / tests only: where an internal tensor lives inside the caller-owned workspace.  Layout: blocked
+ * channels-last with row pads, [B][C/8][pad_l + L + pad_r][8] elements of 2 bytes (bf16 mode) or 4 (fp32 mode).
+ * Names: xin, a<i>, ua<i>, ma<i>.<j>.<q>, xa<i>.<j>.<q> (forward activations; i = stage, j = ResBlock branch,
+ * q = conv pair) and Gi<i>, Gt<i>.<j>.<q>, dm<i>.<j>.<q>, duz<i> (phase-packed), d0 (gradients; the buffers are
+ * shared between stages, so they are valid right after the backward segment of stage i ran).  The parity tests
+ * use it to check every kernel launch against the oracle on that launch's own stored operands. */
+int vcd_debug_ws_tensor(const vcd_plan* plan, int mode, int B, int T, int save_for_backward, const char* name,
+                        size_t* offset_bytes, int* C, int* L, int* pad_l, int* pad_r);
+
+/* Debug / tests only: for plans created AFTER the call, run the forward / data-gradient / weight-gradient
+ * convolutions of bf16 mode on the tcgen05 kernels (1) or on the FFMA kernels with the same bf16 operands (0);
+ * a negative value leaves that flag unchanged.  The environment variables VCD_TC_FWD / VCD_TC_DGRAD /
+ * VCD_TC_WGRAD give the initial values. */
+int vcd_debug_tc_paths(int fwd, int dgrad, int wgrad);
 
 /* Per-layer timing / debugging: name of the arithmetic path ("simt-fp32", "tcgen05-bf16", ...) used by
  * layer `index` of the forward schedule in `mode`; NULL past the end. */

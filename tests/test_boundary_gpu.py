@@ -1,0 +1,166 @@
+"""GPU: the drop-in boundary -- AMP / autocast, remove_weight_norm, DDP-style gradient sync,
+stale-state protections of the Python module."""
+import os
+import socket
+
+import pytest
+import torch
+
+from oracle import hifigan_oracle as O
+from tests.helpers import b200_run, oracle_run, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+def _small(mode="fp32", seed=3, gain=1.3):
+    from vcvits_b200 import Generator
+    sd = O.seeded_state_dict(O.SMALL_CFG, seed, gain=gain)
+    m = Generator(**O.SMALL_CFG, mode=mode)
+    m.load_state_dict(sd)
+    return m.cuda(), sd
+
+
+def test_fp16_autocast_with_grad_scaler():
+    """Lightning AMP (train.py:104-106, precision 16): the decoder is called inside autocast with fp16 latents and the
+    loss is scaled by a GradScaler.  Output is fp32, gradients come back in the inputs' dtypes, unscaled gradients
+    match the fp64 oracle (fp32 mode: the only error is the fp16 rounding of the inputs, which the oracle sees too)."""
+    m, sd = _small("fp32")
+    torch.manual_seed(0)
+    x16 = torch.randn(2, 64, 24, device="cuda").half().requires_grad_(True)
+    g16 = torch.randn(2, 16, 1, device="cuda").half().requires_grad_(True)
+    dy = torch.randn(2, 1, 24 * 16, device="cuda")
+    scaler = torch.amp.GradScaler("cuda", init_scale=1024.0)
+    opt = torch.optim.SGD(m.parameters(), lr=0.0)
+    with torch.autocast("cuda", dtype=torch.float16):
+        y = m(x16, g16)
+        loss = (y.float() * dy).sum()
+    assert y.dtype == torch.float32
+    scaler.scale(loss).backward()
+    scaler.unscale_(opt)
+    assert x16.grad.dtype == torch.float16 and g16.grad.dtype == torch.float16
+    y_ref, gref = oracle_run(O.SMALL_CFG, sd, x16.detach().float().cpu(), g16.detach().float().cpu(), dy.cpu())
+    assert float((y.detach().cpu().double() - y_ref).abs().max()) <= 1e-4
+    for n, p in m.named_parameters():
+        assert rel_l2(p.grad.cpu(), gref[n]) <= 2e-3, n
+    assert rel_l2(x16.grad.float().cpu() / 1024.0, gref["__x__"]) <= 2e-3     # fp16 storage of the (scaled) gradient
+    # bf16 mode under the same autocast region runs too (its own arithmetic mode; autocast is disabled inside)
+    m16, _ = _small("bf16")
+    with torch.autocast("cuda", dtype=torch.float16):
+        y16 = m16(x16.detach(), g16.detach())
+    assert y16.dtype == torch.float32 and float((y16.cpu().double() - y_ref).abs().max()) <= 1e-2
+
+
+def test_remove_weight_norm_matches_reference_convention():
+    """modules.py:218-222: after remove_weight_norm the module holds `weight` (+ `bias`) and no weight_g / weight_v; the
+    waveform is unchanged and the baked model is still differentiable (plain weight gradients)."""
+    import warnings
+    m, sd = _small("fp32")
+    torch.manual_seed(1)
+    x, g = torch.randn(2, 64, 20, device="cuda"), torch.randn(2, 16, 1, device="cuda")
+    with torch.no_grad():
+        y_before = m(x, g).clone()
+    m.remove_weight_norm()
+    keys = list(m.state_dict().keys())
+    assert not any(k.endswith(("weight_g", "weight_v")) for k in keys)
+    assert "ups.0.weight" in keys and "resblocks.0.convs1.0.weight" in keys and "conv_pre.weight" in keys
+    # the same keys, in the same order, as torch's remove_weight_norm leaves on the oracle
+    ref = O.build(O.SMALL_CFG, sd)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for mod in list(ref.ups) + [c for rb in ref.resblocks for c in list(rb.convs1) + list(rb.convs2)]:
+            torch.nn.utils.remove_weight_norm(mod)
+    assert keys == list(ref.state_dict().keys())
+    for k, v in ref.state_dict().items():
+        assert torch.allclose(m.state_dict()[k].cpu(), v, rtol=1e-6, atol=1e-8), k
+    with torch.no_grad():
+        y_after = m(x, g)
+    assert float((y_after - y_before).abs().max()) <= 1e-6
+    # still trainable: gradients w.r.t. the baked weights equal autograd through the baked oracle
+    dy = torch.randn_like(y_after)
+    m(x, g).backward(dy)
+    ref64 = ref.double()
+    ref64(x.cpu().double(), g.cpu().double()).backward(dy.cpu().double())
+    for (n, p), (_, q) in zip(m.named_parameters(), ref64.named_parameters()):
+        assert rel_l2(p.grad.cpu(), q.grad) <= 1e-3, n
+    # a checkpoint saved before the call no longer loads (as in the reference)
+    with pytest.raises(RuntimeError):
+        m.load_state_dict(sd)
+
+
+def test_in_place_parameter_edits_are_seen():
+    """`p.data` edits do not bump `_version`.  Training-mode forwards always re-fold; inference needs
+    invalidate_weights()."""
+    m, sd = _small("fp32")
+    x, g = torch.randn(1, 64, 12, device="cuda"), torch.randn(1, 16, 1, device="cuda")
+    y0 = m(x, g).detach().clone()                    # training-mode forward (parameters require grad)
+    m.conv_post.weight.data.mul_(0.5)                # invisible to the version counter
+    y1 = m(x, g).detach()
+    assert float((y1 - y0).abs().max()) > 1e-4
+    with torch.no_grad():
+        y2 = m(x, g).clone()
+        m.resblocks[0].convs1[0].weight_g.data.mul_(2.0)
+        m.invalidate_weights()
+        y3 = m(x, g)
+    assert float((y3 - y2).abs().max()) > 1e-6
+    # replacing a Parameter object without _apply is picked up
+    new_w = torch.nn.Parameter(m.conv_pre.weight.detach() * 0.0)
+    m.conv_pre.weight = new_w
+    y4 = m(x, g)
+    y4.sum().backward()
+    assert new_w.grad is not None and float(new_w.grad.abs().sum()) > 0
+
+
+def test_refold_between_forward_and_backward_raises():
+    m, _ = _small("fp32")
+    x, g = torch.randn(1, 64, 12, device="cuda"), torch.randn(1, 16, 1, device="cuda")
+    y = m(x, g)
+    m(x, g)                                          # second training-mode forward re-folds the plan's weights
+    with pytest.raises(RuntimeError, match="re-folded"):
+        y.sum().backward()
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _ddp_worker(rank, world, port, out):
+    import torch.distributed as dist
+    from vcvits_b200 import Generator
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)   # both ranks share cuda:0 (NCCL needs one GPU per rank)
+    try:
+        torch.cuda.set_device(0)
+        sd = O.seeded_state_dict(O.SMALL_CFG, 9, gain=1.3)
+        m = Generator(**O.SMALL_CFG, mode="fp32")
+        m.load_state_dict(sd)
+        m = m.cuda()
+        m.set_gradient_sync(dist.group.WORLD)
+        torch.manual_seed(5)
+        x, g, dy = torch.randn(4, 64, 20), torch.randn(4, 16, 1), torch.randn(4, 1, 320)
+        lo, hi = rank * 2, rank * 2 + 2
+        m(x[lo:hi].cuda(), g[lo:hi].cuda()).backward(dy[lo:hi].cuda())
+        out[rank] = {n: p.grad.cpu() for n, p in m.named_parameters()}
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gradient_sync_equals_single_process_full_batch():
+    """b5 / train.py:99-100: two ranks, half the batch each, segment-wise all-reduce inside backward == the full-batch
+    gradient / world (DDP averaging)."""
+    import torch.multiprocessing as mp
+    mgr = mp.get_context("spawn").Manager()
+    out = mgr.dict()
+    mp.spawn(_ddp_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    m, sd = _small("fp32", seed=9)
+    torch.manual_seed(5)
+    x, g, dy = torch.randn(4, 64, 20), torch.randn(4, 16, 1), torch.randn(4, 1, 320)
+    m(x.cuda(), g.cuda()).backward(dy.cuda())
+    full = {n: p.grad.cpu() / 2 for n, p in m.named_parameters()}
+    for r in (0, 1):
+        for n in full:
+            assert rel_l2(out[r][n], full[n]) <= 1e-5, (r, n)
+    for n in full:
+        assert torch.equal(out[0][n], out[1][n]), n

@@ -49,3 +49,35 @@ def test_state_dict_round_trip_with_reference_key_order():
         assert torch.equal(out[k], sd[k]), k
     assert "conv_post.bias" not in out and "conv_post.weight" in out
     assert any(k.endswith("weight_g") for k in out) and any(k.endswith("weight_v") for k in out)
+
+
+def test_remove_weight_norm_keys_and_slot_resolution():
+    """modules.py:218-222 convention on the host side: baked `weight` replaces weight_g / weight_v (key order of
+    torch.nn.utils.remove_weight_norm), and the library's parameter table (reference checkpoint keys) resolves to the
+    baked weight in the weight_v slot and to None in the weight_g slot."""
+    import warnings
+    sd = O.seeded_state_dict(O.TINY_CFG, 4, gain=1.2)
+    m = Generator(**O.TINY_CFG, mode="fp32")
+    m.load_state_dict(sd)
+    names = list(sd.keys())                      # == the library's parameter table (tests/test_cabi_symbols.py)
+    before = m._resolve_params(names)
+    assert all(t is not None for t in before)
+    m.remove_weight_norm()
+    ref = O.build(O.TINY_CFG, sd)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for mod in list(ref.ups) + [c for rb in ref.resblocks for c in list(rb.convs1) + list(rb.convs2)]:
+            torch.nn.utils.remove_weight_norm(mod)
+    assert list(m.state_dict().keys()) == list(ref.state_dict().keys())
+    for k, v in ref.state_dict().items():
+        assert torch.allclose(m.state_dict()[k], v, rtol=1e-6, atol=1e-8), k
+    after = m._resolve_params(names)
+    for n, t in zip(names, after):
+        if n.endswith("weight_g"):
+            assert t is None, n
+        elif n.endswith("weight_v"):
+            assert t is m.get_submodule(n.rsplit(".", 1)[0]).weight, n
+        else:
+            assert t is not None, n
+    with pytest.raises(RuntimeError):
+        m.load_state_dict(sd)

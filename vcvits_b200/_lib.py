@@ -108,6 +108,9 @@ _SIGNATURES = {
     "vcd_phase_dump": (C.c_int, [C.c_int]),
     "vcd_debug_read_trace": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
     "vcd_layer_path": (C.c_char_p, [C.c_void_p, C.c_int, C.c_int]),
+    "vcd_debug_ws_tensor": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_char_p, C.POINTER(C.c_size_t),
+                                      C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "vcd_debug_tc_paths": (C.c_int, [C.c_int, C.c_int, C.c_int]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

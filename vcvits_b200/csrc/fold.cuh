@@ -64,6 +64,7 @@ struct PackJob {
   int norm_off;
   int taps, K, N, NT;  // logical dims; NT = tensor-core column tile (FMT_TC only)
   int fmt;
+  int round_bf16;      // FMT_F32 in bf16 mode: values rounded through bf16 (the FFMA kernels then see the tensor cores' operands)
   long long dst_off;   // element offset into the fp32 or bf16 packed arena
   long long numel;     // taps*K*N
   int first_block;     // first blockIdx.x (256 elements per block)
@@ -103,7 +104,7 @@ wn_pack_kernel(const PackJob* __restrict__ jobs, int njobs, const float* const* 
   const PackJob jb = jobs[lo];
   const long long e = static_cast<long long>(blockIdx.x - jb.first_block) * 256 + threadIdx.x;
   const float* __restrict__ w = params[jb.p_w];
-  const float* __restrict__ gv = jb.p_g >= 0 ? params[jb.p_g] : nullptr;
+  const float* __restrict__ gv = jb.p_g >= 0 ? params[jb.p_g] : nullptr;   // NULL weight_g: baked weight, no scale
   if (jb.fmt == FMT_F32) {
     if (e >= jb.numel) return;
     const int n = static_cast<int>(e % jb.N);
@@ -116,6 +117,7 @@ wn_pack_kernel(const PackJob* __restrict__ jobs, int njobs, const float* const* 
       val = w[idx];
       if (gv) val *= gv[row] / norms[jb.norm_off + row];
     }
+    if (jb.round_bf16) val = __bfloat162float(__float2bfloat16_rn(val));
     arena_f32[jb.dst_off + e] = val;
     return;
   }
@@ -192,7 +194,7 @@ wn_unfold_kernel(const UnfoldJob* __restrict__ jobs, int njobs, const float* con
     return;
   }
   float* dw = dparams[jb.p_w] + static_cast<size_t>(row) * jb.row_len;
-  if (jb.p_g < 0) {
+  if (jb.p_g < 0 || params[jb.p_g] == nullptr) {   // plain weight (never weight-normed, or remove_weight_norm was called)
     for (int i = threadIdx.x; i < jb.row_len; i += 256) dw[i] = unfold_fetch(jb, scratch, row, i);
     return;
   }

@@ -91,6 +91,7 @@ struct vcd_plan {
   float** d_dparams = nullptr;
   std::vector<const float*> h_params;
   std::vector<float*> h_dparams;
+  std::vector<char> is_weight_g;     // parameter i is a weight_g (may be NULL after remove_weight_norm)
   bool folded[2] = {false, false};
 
   vcd::NormJob* d_norm_jobs = nullptr;

@@ -12,11 +12,16 @@
 
 namespace vcd {
 
-// Debug switches (environment): VCD_TC_FWD / VCD_TC_DGRAD / VCD_TC_WGRAD = 0 force the FFMA kernels for that
-// direction in bf16 mode; VCD_TC_MINLAYER / VCD_TC_MAXLAYER restrict the tensor-core path to a layer range.
+// Debug switches: VCD_TC_FWD / VCD_TC_DGRAD / VCD_TC_WGRAD = 0 (environment, or vcd_debug_tc_paths() at run time for
+// plans created afterwards) force the FFMA kernels for that direction in bf16 mode -- same bf16 operands, fp32 FFMA
+// arithmetic: the on-device cross-check of the tcgen05 kernels.
 inline int tc_env_int(const char* name, int dflt) {
   const char* s = getenv(name);
   return s && *s ? atoi(s) : dflt;
+}
+inline int* tc_path_flags() {   // {forward, data gradient, weight gradient}
+  static int f[3] = {tc_env_int("VCD_TC_FWD", 1), tc_env_int("VCD_TC_DGRAD", 1), tc_env_int("VCD_TC_WGRAD", 1)};
+  return f;
 }
 
 inline int tc_col_tile(int creal) {
@@ -40,8 +45,7 @@ inline bool tc_geo_ok(const ConvGeo& g) {
 }
 
 inline void tc_layer_eligibility(Layer& L) {
-  static const int en_fwd = tc_env_int("VCD_TC_FWD", 1), en_dgr = tc_env_int("VCD_TC_DGRAD", 1),
-                   en_wgr = tc_env_int("VCD_TC_WGRAD", 1);
+  const int en_fwd = tc_path_flags()[0], en_dgr = tc_path_flags()[1], en_wgr = tc_path_flags()[2];
   L.tc_ok_fwd = en_fwd && tc_geo_ok(L.fwd);
   L.tc_ok_dgr = en_dgr && tc_geo_ok(L.dgr);
   static const int en_m64 = tc_env_int("VCD_TC_WGRAD_M64", 1);
@@ -123,9 +127,6 @@ inline cudaError_t tc_conv_dispatch(int f, const tc::ConvParams* P, int grid, si
 }
 
 inline int tc_plan_init(vcd_plan* p) {
-  // restrict the tensor-core path to a layer range (debug bisect)
-  const int lo = tc_env_int("VCD_TC_MINLAYER", 0), hi = tc_env_int("VCD_TC_MAXLAYER", 1 << 30);
-  (void)lo; (void)hi; (void)p;
   cudaError_t e = cudaSuccess;
   for (int f = 0; f < 16 && e == cudaSuccess; ++f) e = tc_conv_dispatch(f, nullptr, 0, 0, 0, false);
   if (e != cudaSuccess) return 1;

@@ -353,6 +353,9 @@ extern "C" int vcd_plan_create(const vcd_config* cfg, vcd_plan** out_plan) {
   CU_TRY(cudaMalloc(&p->d_dparams, np * sizeof(float*)));
   p->h_params.assign(np, nullptr);
   p->h_dparams.assign(np, nullptr);
+  p->is_weight_g.assign(np, 0);
+  for (const Layer& L : p->layers)
+    if (L.p_g >= 0) p->is_weight_g[L.p_g] = 1;
 
   // ---- fold job tables ----
   {
@@ -380,6 +383,7 @@ extern "C" int vcd_plan_create(const vcd_config* cfg, vcd_plan** out_plan) {
       j.taps = g.taps; j.K = g.K; j.N = g.N;
       j.NT = dgrad ? L.nt_dgr : L.nt_fwd;
       j.fmt = fmt;
+      j.round_bf16 = (mode == VCD_MODE_BF16 && fmt == FMT_F32) ? 1 : 0;
       j.dst_off = fmt == FMT_F32 ? (dgrad ? L.f32_dgr : L.f32_fwd) : (dgrad ? L.tc_dgr : L.tc_fwd);
       j.numel = 1LL * g.taps * g.K * g.N;
       j.first_block = blk;
@@ -667,7 +671,9 @@ extern "C" int vcd_fold_weights(vcd_plan* p, int mode, const float* const* param
   const size_t np = p->params.size();
   bool changed = false;
   for (size_t i = 0; i < np; ++i) {
-    if (!params[i]) return fail("vcd_fold_weights: parameter %s is null", p->params[i].name.c_str());
+    // a NULL weight_g means "this layer carries no weight norm" (remove_weight_norm, modules.py:218-222): its weight_v
+    // slot then holds the baked weight and is used as is
+    if (!params[i] && !p->is_weight_g[i]) return fail("vcd_fold_weights: parameter %s is null", p->params[i].name.c_str());
     changed |= p->h_params[i] != params[i];
   }
   if (changed) {
@@ -686,6 +692,7 @@ extern "C" int vcd_fold_weights(vcd_plan* p, int mode, const float* const* param
                                                               p->d_params, p->d_norms, p->d_f32, p->d_bf16);
   LAUNCH_CHECK("wn_pack_kernel");
   p->folded[mode] = true;
+  p->folded[1 - mode] = false;   // the fp32 arena is shared between the modes (bf16 mode stores bf16-rounded values in it)
   return 0;
 }
 
@@ -1032,7 +1039,8 @@ extern "C" int vcd_backward(vcd_plan* p, int mode, const float* dy, const float*
   const size_t np = p->params.size();
   bool changed = false;
   for (size_t i = 0; i < np; ++i) {
-    if (!dparams[i]) return fail("vcd_backward: gradient pointer of %s is null", p->params[i].name.c_str());
+    if (!dparams[i] && !(p->is_weight_g[i] && !p->h_params[i]))
+      return fail("vcd_backward: gradient pointer of %s is null", p->params[i].name.c_str());
     changed |= p->h_dparams[i] != dparams[i];
   }
   if (changed) {
@@ -1293,6 +1301,65 @@ extern "C" int vcd_debug_read_trace(vcd_plan* p, unsigned long long* out64) {
   if (!p || !p->d_trace) return fail("tracing is off (set VCD_KTRACE=<layer>:<fwd|dgrad>)");
   CU_TRY(cudaDeviceSynchronize());
   CU_TRY(cudaMemcpy(out64, p->d_trace, 64 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+// Debug / test hook: location of one internal tensor inside the caller-owned workspace (blocked channels-last, row
+// padded: [B][C/8][pad_l + L + pad_r][8] elements of 2 (bf16 mode) or 4 (fp32 mode) bytes).  Names:
+//   xin | a<i> | ua<i> | ma<i>.<j>.<q> | xa<i>.<j>.<q>            (forward; i = stage, j = ResBlock branch, q = pair)
+//   Gi<i> | Gt<i>.<j>.<q> | dm<i>.<j>.<q> | duz<i> | d0            (backward; buffers shared between stages: valid
+//                                                                   right after the segment of stage i has run)
+// The parity tests use it to check every kernel launch against the oracle on the kernel's own stored operands.
+extern "C" int vcd_debug_ws_tensor(const vcd_plan* p, int mode, int B, int T, int save, const char* name, size_t* offset,
+                                   int* C, int* L, int* pad_l, int* pad_r) {
+  if (!p || !name || !offset || !C || !L) return fail("vcd_debug_ws_tensor: null argument");
+  const WsLayout w = make_layout(p, mode, B, T, save != 0);
+  const int S = static_cast<int>(p->stages.size()), NB = p->cfg.num_kernels;
+  const int npairs = p->cfg.resblock == 1 ? 3 : 2;
+  std::vector<int> Ls(S + 1);
+  Ls[0] = T;
+  for (int i = 0; i < S; ++i) Ls[i + 1] = Ls[i] * p->stages[i].u;
+  if (pad_l) *pad_l = kPadL;
+  if (pad_r) *pad_r = kPadR;
+  int i = -1, j = -1, q = -1;
+  auto stage_ok = [&]() { return i >= 0 && i < S; };
+  auto bq_ok = [&]() { return stage_ok() && j >= 0 && j < NB && q >= 0 && q < npairs; };
+  size_t off = 0;
+  bool found = false;
+  if (!strcmp(name, "xin")) { off = w.xin; *C = p->cfg.initial_channel; *L = T; found = true; }
+  else if (!strcmp(name, "d0")) { off = w.d0; *C = p->cfg.upsample_initial_channel; *L = T; found = save != 0; }
+  else if (sscanf(name, "ma%d.%d.%d", &i, &j, &q) == 3) { if (bq_ok() && p->cfg.resblock == 1) { off = w.st[i].ma[j][q]; found = true; } }
+  else if (sscanf(name, "xa%d.%d.%d", &i, &j, &q) == 3) { if (bq_ok() && q < npairs - 1) { off = w.st[i].xa[j][q]; found = true; } }
+  else if (sscanf(name, "Gt%d.%d.%d", &i, &j, &q) == 3) { if (bq_ok() && q > 0 && save) { off = w.Gt[j][q]; found = true; } }
+  else if (sscanf(name, "dm%d.%d.%d", &i, &j, &q) == 3) { if (bq_ok() && save && p->cfg.resblock == 1) { off = w.dm[j][q]; found = true; } }
+  else if (sscanf(name, "ua%d", &i) == 1) { if (stage_ok()) { off = w.st[i].ua; found = true; } }
+  else if (sscanf(name, "Gi%d", &i) == 1) { if (stage_ok() && save) { off = w.Gi[i & 1]; found = true; } }
+  else if (sscanf(name, "duz%d", &i) == 1) {
+    if (stage_ok() && save) {
+      const Layer& U = p->layers[p->stages[i].up_layer];
+      *offset = w.duz; *C = U.wgr.N; *L = Ls[i] + U.fwd.taps - 1;
+      return 0;
+    }
+  }
+  else if (sscanf(name, "a%d", &i) == 1) {
+    if (i >= 0 && i <= S) {
+      *offset = w.a[i]; *C = i == 0 ? p->cfg.upsample_initial_channel : p->stages[i - 1].cout; *L = Ls[i];
+      return 0;
+    }
+  }
+  if (!found) return fail("vcd_debug_ws_tensor: unknown or unavailable tensor '%s'", name);
+  *offset = off;
+  if (stage_ok()) { *C = p->stages[i].cout; *L = Ls[i + 1]; }
+  return 0;
+}
+
+// Debug / test hook: choose, for plans created AFTER this call, which directions of bf16 mode run on the tcgen05
+// kernels (1) or on the FFMA kernels with the same bf16 operands (0); a negative value leaves a flag unchanged.
+extern "C" int vcd_debug_tc_paths(int fwd, int dgrad, int wgrad) {
+  int* f = tc_path_flags();
+  if (fwd >= 0) f[0] = fwd != 0;
+  if (dgrad >= 0) f[1] = dgrad != 0;
+  if (wgrad >= 0) f[2] = wgrad != 0;
   return 0;
 }
 

@@ -51,6 +51,18 @@ class _WeightNormParams(nn.Module):
         self.weight_g = nn.Parameter(norm)
         self.weight_v = nn.Parameter(weight)
 
+    def bake(self) -> None:
+        """``torch.nn.utils.remove_weight_norm`` on this holder: ``weight = g * v / ||v||`` becomes a plain
+        parameter (registered after ``bias``, like the reference), ``weight_g`` / ``weight_v`` disappear."""
+        if "weight_v" not in self._parameters:
+            return
+        v, g = self.weight_v.detach(), self.weight_g.detach()
+        norm = v.reshape(v.shape[0], -1).norm(dim=1).reshape(g.shape)
+        w = v * (g / norm)
+        del self._parameters["weight_g"]
+        del self._parameters["weight_v"]
+        self.weight = nn.Parameter(w)
+
 
 class _ResBlock1Params(nn.Module):
     def __init__(self, convs1: Sequence[nn.Module], convs2: Sequence[nn.Module]):
@@ -94,7 +106,7 @@ class _DecoderFunction(torch.autograd.Function):
         B, _, T = x.shape
         plan = module._plan_for(x.device)
         mode = module._mode
-        module._fold_if_needed(params)
+        module._fold_if_needed(params, force=need_grad)
         stream = torch.cuda.current_stream(x.device).cuda_stream
         xf = x if x.dtype == torch.float32 else x.float()
         gf = None
@@ -108,6 +120,7 @@ class _DecoderFunction(torch.autograd.Function):
                                    ws_bytes, B, T, 1 if need_grad else 0, stream), "vcd_forward")
         if need_grad:
             ctx.module = module
+            ctx.fold_serial = module._fold_serial
             ctx.ws = ws
             ctx.ws_bytes = ws_bytes
             ctx.shape = (B, T)
@@ -119,11 +132,22 @@ class _DecoderFunction(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dy: torch.Tensor):
+        with torch.cuda.device(dy.device):
+            return _DecoderFunction._backward(ctx, dy)
+
+    @staticmethod
+    def _backward(ctx, dy: torch.Tensor):
         lib = _lib.load()
         module: Generator = ctx.module
         if ctx.ws is None:
             raise RuntimeError("vcvits_b200.Generator: backward through the same forward twice is not supported "
                                "(the activation workspace is recycled after the first backward)")
+        if ctx.fold_serial != module._fold_serial:
+            # the packed weights / norms live in the plan, not in the autograd graph: a re-fold between this forward and
+            # its backward (in-place parameter update, set_mode, a second training forward) would silently mix new
+            # weights with old activations
+            raise RuntimeError("vcvits_b200.Generator: the decoder weights were re-folded between this forward and its "
+                               "backward (parameter update, set_mode() or another training-mode forward in between)")
         y, gf = ctx.saved_tensors
         if not ctx.has_g:
             gf = None
@@ -137,7 +161,8 @@ class _DecoderFunction(torch.autograd.Function):
         dg = torch.empty((B, module.gin_channels), dtype=torch.float32, device=dev) if need_dg else None
         flat = torch.empty(module._flat_numel, dtype=torch.float32, device=dev)
         views = module._grad_views(flat)
-        ptrs = (C.c_void_p * len(views))(*[v.data_ptr() for v in views])
+        ptrs = (C.c_void_p * len(views))(*[v.data_ptr() if p is not None else None
+                                           for v, p in zip(views, module._ordered_params())])
         def run(mask):
             _lib.check(lib.vcd_backward(plan, module._mode, dy.data_ptr(), y.data_ptr(),
                                         gf.data_ptr() if gf is not None else None,
@@ -157,7 +182,7 @@ class _DecoderFunction(torch.autograd.Function):
             reducer.finish()
         module._give_workspace(ctx.ws)
         ctx.ws = None
-        grads = [v if p.requires_grad else None for v, p in zip(views, module._ordered_params())]
+        grads = [v if (p is not None and p.requires_grad) else None for v, p in zip(views, module._ordered_params())]
         gx = dx.to(ctx.x_dtype) if dx is not None else None
         gg = dg.reshape(ctx.g_shape).to(ctx.g_dtype) if dg is not None else None
         return (None, None, gx, gg, *grads)
@@ -226,7 +251,9 @@ class Generator(nn.Module):
 
         self._plans = {}
         self._param_cache = None
+        self._slots = None
         self._fold_key = None
+        self._fold_serial = 0
         self._ws_cache = {}
         self._ws_pool = {}
         self._grad_sync_group = None
@@ -255,9 +282,22 @@ class Generator(nn.Module):
         return self
 
     def remove_weight_norm(self) -> "Generator":
-        """Reference convention (modules.py:218-222).  The fold ``w = g*v/||v||`` already happens once per
-        parameter version inside ``vcd_fold_weights``, so inference pays it once; parameters keep the
-        weight_g/weight_v layout so checkpoints stay loadable."""
+        """Reference convention (modules.py:218-222,245-247 and upstream ``Generator.remove_weight_norm``): every
+        weight-normed convolution (``ups.*``, ``resblocks.*``) is baked, ``weight = g * v / ||v||`` -- afterwards the
+        module exposes ``weight``/``bias`` and no ``weight_g``/``weight_v``, exactly like
+        ``torch.nn.utils.remove_weight_norm``.  The library is told so by a NULL ``weight_g`` pointer.  As in the
+        reference, a checkpoint saved before the call no longer loads afterwards (and vice versa)."""
+        for holder in self.modules():
+            if isinstance(holder, _WeightNormParams):
+                holder.bake()
+        self.invalidate_weights()
+        self._param_cache = None
+        return self
+
+    def invalidate_weights(self) -> "Generator":
+        """Forget the cached weight fold.  Training-mode forwards always re-fold; inference (``torch.no_grad``)
+        caches the fold keyed on the parameters' (address, version) -- an in-place edit through ``p.data`` does not
+        bump the version, so call this after such an edit (EMA copy, manual clipping, ...)."""
         self._fold_key = None
         return self
 
@@ -301,14 +341,14 @@ class Generator(nn.Module):
                 _lib.check(lib.vcd_param_info(plan, i, C.byref(name), shape, C.byref(ndim)), "vcd_param_info")
                 names.append(name.value.decode())
                 numels.append(tuple(shape[: ndim.value]))
-            own = dict(self.named_parameters())
-            if set(names) != set(own):
-                raise RuntimeError(f"parameter table mismatch between module and library: "
-                                   f"{sorted(set(names) ^ set(own))[:8]}")
-            for nme, shp in zip(names, numels):
-                if tuple(own[nme].shape) != shp:
-                    raise RuntimeError(f"shape mismatch for {nme}: module {tuple(own[nme].shape)} vs library {shp}")
             self._names = names
+            self._slots = None
+            own = {}
+            for nme, shp, prm in zip(names, numels, self._resolve_params(names)):
+                if prm is not None and tuple(prm.shape) != shp:
+                    raise RuntimeError(f"shape mismatch for {nme}: module {tuple(prm.shape)} vs library {shp}")
+                own[nme] = shp
+            numel_of = {nme: int(math.prod(shp)) for nme, shp in own.items()}
             # flat gradient buffer layout: parameters grouped by backward segment, in completion order
             nseg = lib.vcd_num_backward_segments(plan)
             self._num_segments = nseg
@@ -320,24 +360,54 @@ class Generator(nn.Module):
                 for j in range(cnt):
                     idx = buf[j]
                     order[idx] = off
-                    off += own[names[idx]].numel()
+                    off += numel_of[names[idx]]
                 ranges.append((lo, off))
             if len(order) != n:
                 raise RuntimeError("backward segments do not cover every parameter")
             self._flat_offsets = [order[i] for i in range(n)]
             self._flat_numel = off
             by_off = sorted(range(n), key=lambda i: order[i])
-            self._flat_sizes = [own[names[i]].numel() for i in by_off]
+            self._flat_sizes = [numel_of[names[i]] for i in by_off]
             pos = {i: k for k, i in enumerate(by_off)}
-            self._flat_index = [(pos[i], tuple(own[names[i]].shape)) for i in range(n)]
+            self._flat_index = [(pos[i], own[names[i]]) for i in range(n)]
             self._segment_ranges = ranges
         return plan
 
-    def _ordered_params(self) -> List[torch.Tensor]:
-        cached = self._param_cache
+    def _resolve_params(self, names: Sequence[str]) -> List[Optional[torch.Tensor]]:
+        """Library parameter table (reference checkpoint keys) -> this module's Parameters.  After
+        ``remove_weight_norm`` a layer's ``weight_v`` slot is its baked ``weight`` and its ``weight_g`` slot is None."""
+        slots, out = [], []
+        for name in names:
+            prefix, leaf = name.rsplit(".", 1)
+            holder = self.get_submodule(prefix)
+            if leaf in ("weight_g", "weight_v") and leaf not in holder._parameters:
+                if "weight" not in holder._parameters:
+                    raise RuntimeError(f"parameter table mismatch between module and library: {name}")
+                leaf = "weight" if leaf == "weight_v" else None
+            elif leaf not in holder._parameters:
+                raise RuntimeError(f"parameter table mismatch between module and library: {name}")
+            slots.append((holder, leaf))
+            out.append(holder._parameters[leaf] if leaf is not None else None)
+        n_own = sum(1 for _ in self.parameters())
+        if n_own != sum(1 for t in out if t is not None):
+            raise RuntimeError("parameter table mismatch between module and library: the module holds parameters the "
+                               "library does not know")
+        self._slots = slots
+        return out
+
+    def _ordered_params(self) -> List[Optional[torch.Tensor]]:
+        """Parameters in library order.  The cached list is validated by identity on every call, so a Parameter that was
+        replaced without ``_apply`` (``load_state_dict(assign=True)``, ``m.conv_pre.weight = nn.Parameter(..)``,
+        pruning / parametrize utilities) is picked up instead of silently using the orphaned tensor."""
+        cached, slots = self._param_cache, self._slots
+        if cached is not None and slots is not None:
+            for (holder, leaf), t in zip(slots, cached):
+                if (holder._parameters.get(leaf) if leaf is not None else None) is not t:
+                    cached = None
+                    break
         if cached is None:
-            own = dict(self.named_parameters())
-            cached = self._param_cache = [own[n] for n in self._names]
+            cached = self._param_cache = self._resolve_params(self._names)
+            self._fold_key = None
         return cached
 
     def _grad_views(self, flat: torch.Tensor) -> List[torch.Tensor]:
@@ -345,19 +415,23 @@ class Generator(nn.Module):
         pieces = flat.split_with_sizes(self._flat_sizes)
         return [pieces[k].view(shape) for k, shape in self._flat_index]
 
-    def _fold_if_needed(self, params: Sequence[torch.Tensor]) -> None:
-        key = (self._mode, tuple((p.data_ptr(), p._version) for p in params))
-        if key == self._fold_key:
+    def _fold_if_needed(self, params: Sequence[Optional[torch.Tensor]], force: bool = False) -> None:
+        """Fold the parameters into the packed operand layouts.  Training-mode forwards (``force``) always fold: the
+        parameters change every optimizer step and an in-place edit through ``p.data`` is invisible to any version key
+        (two launches, part of the timed step in bench.py).  Inference caches on (address, version) per parameter."""
+        key = (self._mode, tuple((p.data_ptr(), p._version) if p is not None else None for p in params))
+        if not force and key == self._fold_key:
             return
         lib = _lib.load()
-        dev = params[0].device
+        dev = next(p for p in params if p is not None).device
         for p in params:
-            if p.dtype != torch.float32 or not p.is_contiguous():
+            if p is not None and (p.dtype != torch.float32 or not p.is_contiguous()):
                 raise RuntimeError("decoder parameters must be contiguous fp32 tensors")
-        ptrs = (C.c_void_p * len(params))(*[p.data_ptr() for p in params])
+        ptrs = (C.c_void_p * len(params))(*[p.data_ptr() if p is not None else None for p in params])
         stream = torch.cuda.current_stream(dev).cuda_stream
         _lib.check(lib.vcd_fold_weights(self._plan_for(dev), self._mode, ptrs, stream), "vcd_fold_weights")
         self._fold_key = key
+        self._fold_serial += 1
 
     def _workspace(self, nbytes: int, device: torch.device, cache: bool) -> torch.Tensor:
         if not cache:
@@ -400,12 +474,15 @@ class Generator(nn.Module):
                 raise ValueError("g given but the decoder was built with gin_channels=0")
             if g.shape[0] != x.shape[0] or g.numel() != x.shape[0] * self.gin_channels:
                 raise ValueError(f"expected g of shape [B, {self.gin_channels}, 1], got {tuple(g.shape)}")
-        self._plan_for(x.device)
-        params = self._ordered_params()
-        need_grad = torch.is_grad_enabled() and (x.requires_grad or (g is not None and g.requires_grad)
-                                                 or any(p.requires_grad for p in params))
-        with torch.autocast(device_type="cuda", enabled=False):
-            return _DecoderFunction.apply(self, need_grad, x, g, *params)
+        # the library launches on this device's plan streams: make it current (single-process multi-GPU callers)
+        with torch.cuda.device(x.device):
+            self._plan_for(x.device)
+            params = self._ordered_params()
+            need_grad = torch.is_grad_enabled() and (x.requires_grad or (g is not None and g.requires_grad)
+                                                     or any(p is not None and p.requires_grad for p in params))
+            # Lightning AMP (train.py:104-106) calls this inside autocast: the decoder computes in its own mode
+            with torch.autocast(device_type="cuda", enabled=False):
+                return _DecoderFunction.apply(self, need_grad, x, g, *params)
 
     def synthesize_host(self, x_host: torch.Tensor, g_host: Optional[torch.Tensor] = None,
                         device: Optional[torch.device] = None) -> torch.Tensor:
@@ -413,7 +490,8 @@ class Generator(nn.Module):
         lib = _lib.load()
         device = device or next(self.parameters()).device
         plan = self._plan_for(device)
-        self._fold_if_needed(self._ordered_params())
+        with torch.cuda.device(device):
+            self._fold_if_needed(self._ordered_params())
         B, _, T = x_host.shape
         xh = x_host.contiguous().float()
         gh = g_host.reshape(B, -1).contiguous().float() if g_host is not None else None
@@ -443,6 +521,7 @@ class Generator(nn.Module):
         state = dict(self.__dict__)
         state["_plans"] = {}        # library handles are per process / per device; rebuilt lazily
         state["_param_cache"] = None
+        state["_slots"] = None
         state["_ws_cache"] = {}
         state["_ws_pool"] = {}
         state["_fold_key"] = None
