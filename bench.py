@@ -7,14 +7,17 @@ A "step" is one pass of the hot path over one batch of synthetic latents:
   train_base_b16 (default, BASELINE.json configs[1]): configs/base.json decoder, batch 16 x 32-frame segments,
       bf16 tensor-core mode: weight-norm fold + forward + backward (all 233 parameter gradients, dz, dg).
   train_48k_b32 (configs[2]): 48k_base.json (inter_channels 128), batch 32 per GPU, same step.
-  infer_10s (configs[3], scaled by --infer-batch): forward only on 938-frame (10 s) latents.
+  infer_10s (configs[3]): forward only on 938-frame (10 s) latents, batch 64 per GPU (--infer-batch overrides).
+  fwd_base_b1 (configs[0]'s shape on the GPU): forward, batch 1 x 32 frames.
+  full_synth (configs[4]): decoder share of a full synthesizer forward -- see tools/full_synth.py.
 N > 1 (torchrun): one rank per GPU, identical weights, different latents per rank, gradient all-reduce (NCCL)
 overlapped with backward inside the step; value = audio-seconds of ALL ranks / max-over-ranks step time.
 
 One JSON line is printed by rank 0 (see the contract in the task description): `value` is device-resident
-throughput, `e2e` the same step fed from pinned host memory with the waveform read back, `roofline` the
-dominant kernel class (tcgen05 implicit-GEMM convolutions) against the measured bf16 peak, `cpu_baseline`
-the CPU oracle timed on this box's host cores.
+throughput, `e2e` the same step fed from pinned host memory with the waveform read back, `roofline` the tcgen05
+implicit-GEMM kernels against the measured bf16 peak (`roofline_classes` lists every kernel class, the HBM-bound
+ones against the measured copy bandwidth), `cpu_baseline` the CPU oracle timed on this box's host cores, and
+`configs` short sub-records of the other BASELINE.json GPU configurations (configs[2], configs[3]) at the same N.
 """
 from __future__ import annotations
 
@@ -36,9 +39,10 @@ WORKLOADS = {
     #                cfg name      B   T    train
     "train_base_b16": ("BASE_CFG", 16, 32, True),
     "train_48k_b32": ("BASE48K_CFG", 32, 32, True),
-    "infer_10s": ("BASE_CFG", 8, 938, False),
+    "infer_10s": ("BASE_CFG", 64, 938, False),
     "fwd_base_b1": ("BASE_CFG", 1, 32, False),
 }
+METRIC = "decoder_audio_seconds_per_second"
 
 
 def parse_args():
@@ -47,11 +51,12 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="train_base_b16", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="train_base_b16", choices=sorted(WORKLOADS) + ["full_synth"])
     ap.add_argument("--mode", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--infer-batch", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the configs[2] / configs[3] sub-records")
     ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed steps")
     ap.add_argument("--profile-classes", action="store_true", help="print the per-kernel-class table to stderr")
     ap.add_argument("--dump-launches", default=None, help="write the per-launch CSV of the profiled steps here")
@@ -67,6 +72,24 @@ def load_peaks():
                 "hbm": d["hbm_gbs"], "source": "measured"}
     # fallback stated in /opt/skills/guides/B200_PROFILING.md
     return {"bf16_burst": 1590.0, "bf16_sustained": 1400.0, "hbm": 6650.0, "source": "fallback"}
+
+
+def workload_shape(args, name):
+    cfg_name, B, T, train = WORKLOADS[name]
+    if name == "infer_10s" and args.infer_batch:
+        B = args.infer_batch
+    return cfg_name, B, T, train
+
+
+def make_config(args, name, world):
+    """The `config` object -- identical in the b200 arm and the reference arm for the same command line."""
+    cfg_name, B, T, train = workload_shape(args, name)
+    step = "weight-norm fold + fwd + bwd (233 param grads, dz, dg)" if train else "fwd"
+    if train and world > 1:
+        step += " + gradient all-reduce"
+    return {"workload": name, "cfg": cfg_name, "batch_per_gpu": B, "frames": T, "step": step,
+            "l2": "no flush" if args.no_flush else "256 MB L2 flush between timed steps",
+            "random_init_weights": True}
 
 
 class ClockSampler:
@@ -124,11 +147,25 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------------------
 # reference arm / CPU baseline: the oracle (PyTorch CPU restatement of the reference decoder) on host cores
 # ---------------------------------------------------------------------------------------------------------
-def cpu_step_time(cfg, B, T, train, steps, warmup, seed=1234):
+def use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1 to its workers: the CPU arm must not inherit that."""
     import torch
+    n = os.cpu_count() or 1
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        pass
+    torch.set_num_threads(n)
+    return torch.get_num_threads()
+
+
+def cpu_model(cfg, seed=1234):
     from oracle import hifigan_oracle as O
-    sd = O.seeded_state_dict(cfg, seed)
-    model = O.build(cfg, sd)
+    return O.build(cfg, O.seeded_state_dict(cfg, seed))
+
+
+def cpu_time_steps(model, cfg, B, T, train, steps, warmup, seed=1234):
+    import torch
     torch.manual_seed(seed)
     x = torch.randn(B, cfg["initial_channel"], T)
     g = torch.randn(B, cfg["gin_channels"], 1)
@@ -151,32 +188,42 @@ def cpu_step_time(cfg, B, T, train, steps, warmup, seed=1234):
         dt = time.perf_counter() - t0
         if i >= warmup:
             times.append(dt)
-    return sum(times) / len(times), torch.get_num_threads()
+    return sum(times) / len(times)
+
+
+def cpu_bounded_sample(cfg, B, T, train, steps, warmup, budget_s):
+    """Batch size of the per-step sample so that `steps + warmup` CPU steps fit in about `budget_s` seconds: one probe
+    step on a single utterance gives the cost per utterance (the decoder is independent per utterance)."""
+    model = cpu_model(cfg)
+    per_item = cpu_time_steps(model, cfg, 1, T, train, 1, 1)
+    sB = int(max(1, min(B, (budget_s / max(1, steps + warmup)) / max(per_item, 1e-6))))
+    return model, sB
 
 
 def run_reference(args):
-    import torch
     from oracle import hifigan_oracle as O
     rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return
-    cfg_name, B, T, train = WORKLOADS[args.workload]
-    if args.workload == "infer_10s" and args.infer_batch:
-        B = args.infer_batch
+    if args.workload == "full_synth":
+        print(json.dumps({"impl": "reference", "unavailable": "full_synth is a decoder-share harness, not a throughput metric"}))
+        return
+    cores = use_all_host_threads()
+    cfg_name, B, T, train = workload_shape(args, args.workload)
     cfg = getattr(O, cfg_name)
-    # bounded sample of the workload: the CPU step is slow, keep the whole run within a few minutes
-    steps = max(1, min(args.steps, 3))
-    warmup = max(1, min(args.warmup, 1))
-    sB = B if (train and T * B <= 512) else max(1, min(B, 2))
-    t, cores = cpu_step_time(cfg, sB, T, train, steps, warmup)
+    steps, warmup = max(1, args.steps), max(1, args.warmup)
+    model, sB = cpu_bounded_sample(cfg, B, T, train, steps, warmup, budget_s=150.0)
+    t = cpu_time_steps(model, cfg, sB, T, train, steps, warmup)
     value = O.audio_seconds(sB, T) / t
-    sample = f"{'fwd+bwd' if train else 'fwd'} of {cfg_name} B={sB} T={T} fp32, {steps} timed steps after {warmup} warm-up"
-    line = {"impl": "reference", "metric": "decoder_audio_seconds_per_second", "value": value, "unit": "audio-s/s",
+    sample = (f"{'fwd+bwd' if train else 'fwd'} of {cfg_name}, {sB} of the {B} utterances per step, T={T}, fp32, "
+              f"{steps} timed steps after {warmup} warm-up, {cores} threads")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "audio-s/s",
             "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": args.workload, "cfg": cfg_name, "batch_per_step": sB, "frames": T,
-                       "note": "CPU oracle (PyTorch restatement of the reference decoder; the reference ships no "
-                               "Generator class) on host cores; rank 0 only"},
+            "config": make_config(args, args.workload, world),
+            "note": "CPU oracle (PyTorch restatement of the reference decoder; the reference ships no Generator class) on "
+                    "the host cores; rank 0 only; throughput is per utterance, so a bounded sample of the batch is exact",
             "cpu_baseline": {"value": value, "unit": "audio-s/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -185,82 +232,37 @@ def run_reference(args):
 # ---------------------------------------------------------------------------------------------------------
 # B200 arm
 # ---------------------------------------------------------------------------------------------------------
-def run_b200(args):
-    import torch
-    import torch.distributed as dist
-    from oracle import hifigan_oracle as O
-    from vcvits_b200 import Generator, _lib
+class Bench:
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist, self.args = torch, dist, args
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py --impl b200 needs a CUDA device (no CPU fallback)")
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
+        from vcvits_b200 import _lib
+        self.lib = _lib.load()
+        self.flush_buf = None if args.no_flush else torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=self.dev)
+        self.peaks = load_peaks()
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py --impl b200 needs a CUDA device (no CPU fallback)")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-
-    cfg_name, B, T, train = WORKLOADS[args.workload]
-    if args.workload == "infer_10s" and args.infer_batch:
-        B = args.infer_batch
-    cfg = getattr(O, cfg_name)
-    lib = _lib.load()
-
-    torch.manual_seed(1234)  # identical weights on every rank (configs/base.json:12)
-    model = Generator(**cfg, mode=args.mode).to(dev)
-    if world > 1 and train:
-        model.set_gradient_sync(dist.group.WORLD)
-    hop = model.hop
-    gen = torch.Generator(device="cpu").manual_seed(1000 + rank)  # different data per rank
-    x_host = torch.randn(B, cfg["initial_channel"], T, generator=gen).pin_memory()
-    g_host = torch.randn(B, cfg["gin_channels"], 1, generator=gen).pin_memory()
-    dy_host = torch.randn(B, 1, T * hop, generator=gen).pin_memory()
-    y_host = torch.empty(B, 1, T * hop).pin_memory()
-    x_dev, g_dev, dy_dev = x_host.to(dev), g_host.to(dev), dy_host.to(dev)
-    flush_buf = None if args.no_flush else torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
-    params = list(model.parameters())
-
-    def step_device():
-        if train:
-            for p in params:
-                p.grad = None
-            model._fold_key = None  # parameters change every optimizer step: the fold is part of the step
-            xx = x_dev.detach().requires_grad_(True)
-            gg = g_dev.detach().requires_grad_(True)
-            y = model(xx, gg)
-            y.backward(dy_dev)
-            return y
-        with torch.no_grad():
-            return model(x_dev, g_dev)
-
-    def step_e2e():
-        xd = x_host.to(dev, non_blocking=True)
-        gd = g_host.to(dev, non_blocking=True)
-        if train:
-            dyd = dy_host.to(dev, non_blocking=True)
-            for p in params:
-                p.grad = None
-            model._fold_key = None
-            y = model(xd.requires_grad_(True), gd.requires_grad_(True))
-            y.backward(dyd)
-        else:
-            with torch.no_grad():
-                y = model(xd, gd)
-        y_host.copy_(y.detach(), non_blocking=True)
-
-    def timed(fn, steps, warmup):
+    def timed(self, fn, steps, warmup):
+        torch, dist = self.torch, self.dist
         for _ in range(warmup):
             fn()
         torch.cuda.synchronize()
-        if world > 1:
+        if self.world > 1:
             dist.barrier()
         torch.cuda.synchronize()
-        evs = []
-        host = 0.0
+        evs, host = [], 0.0
         for _ in range(steps):
-            if flush_buf is not None:
-                flush_buf.fill_(1)  # evict L2 (256 MB write > 126 MB L2); outside the timed events
+            if self.flush_buf is not None:
+                self.flush_buf.fill_(1)  # evict L2 (256 MB write > 126 MB L2); outside the timed events
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
             h0 = time.perf_counter()
@@ -269,39 +271,73 @@ def run_b200(args):
             b.record()
             evs.append((a, b))
         torch.cuda.synchronize()
-        if world > 1:
+        if self.world > 1:
             dist.barrier()
         torch.cuda.synchronize()
         total_ms = sum(a.elapsed_time(b) for a, b in evs)
-        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-        if world > 1:
+        t = torch.tensor([total_ms], dtype=torch.float64, device=self.dev)
+        if self.world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        timed.host_ms = host / steps * 1e3
+        self.host_ms = host / steps * 1e3
         return float(t.item()) / steps
 
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    lib.vcd_launch_count(1)
-    ms = timed(step_device, args.steps, args.warmup)
-    host_ms = timed.host_ms
-    launches_total = lib.vcd_launch_count(1)
-    clocks = sampler.stop() if rank == 0 else None
-    launches_per_step = launches_total / (args.steps + args.warmup)
+    def setup(self, name):
+        """Model + synthetic inputs of one workload; returns the two step functions."""
+        torch, dist, args = self.torch, self.dist, self.args
+        from oracle import hifigan_oracle as O
+        from vcvits_b200 import Generator
+        cfg_name, B, T, train = workload_shape(args, name)
+        cfg = getattr(O, cfg_name)
+        torch.manual_seed(1234)  # identical weights on every rank (configs/base.json:12)
+        model = Generator(**cfg, mode=args.mode).to(self.dev)
+        if self.world > 1 and train:
+            model.set_gradient_sync(dist.group.WORLD)
+        hop = model.hop
+        gen = torch.Generator(device="cpu").manual_seed(1000 + self.rank)  # different data per rank
+        x_host = torch.randn(B, cfg["initial_channel"], T, generator=gen).pin_memory()
+        g_host = torch.randn(B, cfg["gin_channels"], 1, generator=gen).pin_memory()
+        dy_host = torch.randn(B, 1, T * hop, generator=gen).pin_memory() if train else None
+        y_host = torch.empty(B, 1, T * hop).pin_memory()
+        x_dev, g_dev = x_host.to(self.dev), g_host.to(self.dev)
+        dy_dev = dy_host.to(self.dev) if train else None
+        params = list(model.parameters())
+        dev = self.dev
 
-    e2e = None
-    if not args.no_e2e:
-        ms_e2e = timed(step_e2e, args.steps, max(3, args.warmup // 2))
+        def step_device():
+            if train:
+                for p in params:
+                    p.grad = None
+                # parameters change every optimizer step: training-mode forwards always re-fold (part of the step)
+                xx = x_dev.detach().requires_grad_(True)
+                gg = g_dev.detach().requires_grad_(True)
+                y = model(xx, gg)
+                y.backward(dy_dev)
+                return y
+            with torch.no_grad():
+                return model(x_dev, g_dev)
+
+        def step_e2e():
+            xd = x_host.to(dev, non_blocking=True)
+            gd = g_host.to(dev, non_blocking=True)
+            if train:
+                dyd = dy_host.to(dev, non_blocking=True)
+                for p in params:
+                    p.grad = None
+                y = model(xd.requires_grad_(True), gd.requires_grad_(True))
+                y.backward(dyd)
+            else:
+                with torch.no_grad():
+                    y = model(xd, gd)
+            y_host.copy_(y.detach(), non_blocking=True)
+
         h2d = x_host.numel() * 4 + g_host.numel() * 4 + (dy_host.numel() * 4 if train else 0)
-        e2e = {"value": world * O.audio_seconds(B, T) / (ms_e2e * 1e-3), "unit": "audio-s/s",
-               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": y_host.numel() * 4, "ms_per_step": ms_e2e}
+        info = {"cfg": cfg, "cfg_name": cfg_name, "B": B, "T": T, "train": train, "model": model, "h2d": h2d,
+                "d2h": y_host.numel() * 4}
+        return step_device, step_e2e, info
 
-    # ---- roofline of the dominant kernel class, measured live with CUDA events around every launch ----
-    peaks = load_peaks()
-    roofline, classes = None, None
-    if world > 1:
-        dist.barrier()
-    if rank == 0:
+    def profile_classes(self, step_device, model, psteps=3):
+        """CUDA events around every launch (serial streams, no graphs): device ms / FLOPs / bytes per kernel class."""
+        lib = self.lib
         model.set_gradient_sync(None)  # rank-0-only profiling passes must not enter a collective
         lib.vcd_profile_enable(1)
         for _ in range(2):
@@ -310,72 +346,149 @@ def run_b200(args):
         arr_ms, arr_l = (C.c_double * n)(), (C.c_uint64 * n)()
         arr_f, arr_b = (C.c_double * n)(), (C.c_double * n)()
         lib.vcd_profile_read(1, arr_ms, arr_l, arr_f, arr_b)
-        psteps = 3
         for _ in range(psteps):
-            if flush_buf is not None:
-                flush_buf.fill_(1)
+            if self.flush_buf is not None:
+                self.flush_buf.fill_(1)
             step_device()
-        if args.dump_launches:
-            lib.vcd_profile_dump(args.dump_launches.encode())
+        if self.args.dump_launches:
+            lib.vcd_profile_dump(self.args.dump_launches.encode())
         lib.vcd_profile_read(1, arr_ms, arr_l, arr_f, arr_b)
         lib.vcd_profile_enable(0)
         classes = []
         for c in range(n):
             if arr_l[c]:
-                classes.append({"class": lib.vcd_profile_class_name(c).decode(), "ms_per_step": arr_ms[c] / psteps,
+                ms = arr_ms[c] / psteps
+                classes.append({"class": lib.vcd_profile_class_name(c).decode(), "ms_per_step": ms,
                                 "launches_per_step": arr_l[c] / psteps, "gflop_per_step": arr_f[c] / psteps / 1e9,
-                                "tflops": arr_f[c] / (arr_ms[c] * 1e-3) / 1e12 if arr_ms[c] > 0 else 0.0})
-        dom = max(classes, key=lambda d: d["ms_per_step"]) if classes else None
+                                "gbyte_per_step": arr_b[c] / psteps / 1e9,
+                                "tflops": arr_f[c] / (arr_ms[c] * 1e-3) / 1e12 if arr_ms[c] > 0 else 0.0,
+                                "gbs": arr_b[c] / (arr_ms[c] * 1e-3) / 1e9 if arr_ms[c] > 0 else 0.0})
+        return classes
+
+    def rooflines(self, classes, workload):
+        peaks = self.peaks
+        total_ms = sum(c["ms_per_step"] for c in classes)
+        per_class = []
+        for c in classes:
+            if c["class"].startswith("tc_") and c["gflop_per_step"] > 0:
+                per_class.append({"class": c["class"], "bound": "tensor", "achieved": c["tflops"], "peak": peaks["bf16_sustained"],
+                                  "unit": "TFLOP/s", "frac": c["tflops"] / peaks["bf16_sustained"],
+                                  "avg_launch_us": c["ms_per_step"] / c["launches_per_step"] * 1e3,
+                                  "share_of_step": c["ms_per_step"] / total_ms})
+            elif c["gbyte_per_step"] > 0:
+                per_class.append({"class": c["class"], "bound": "hbm", "achieved": c["gbs"], "peak": peaks["hbm"], "unit": "GB/s",
+                                  "frac": c["gbs"] / peaks["hbm"],
+                                  "avg_launch_us": c["ms_per_step"] / c["launches_per_step"] * 1e3,
+                                  "share_of_step": c["ms_per_step"] / total_ms})
         tcs = [c for c in classes if c["class"].startswith("tc_")]
-        if tcs:
-            fl = sum(c["gflop_per_step"] for c in tcs) * 1e9
-            tm = sum(c["ms_per_step"] for c in tcs) * 1e-3
-            ln = sum(c["launches_per_step"] for c in tcs)
-            achieved = fl / tm / 1e12
-            traffic = None
-            tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
-            if args.workload == "train_base_b16" and os.path.exists(tpath):
-                with open(tpath) as tf:
-                    traffic = json.load(tf).get("dram_bytes_per_launch")
-            roofline = {"bound": "tensor", "kernel": "tc::conv_kernel / tc::wgrad_kernel (tcgen05 implicit GEMM)",
-                        "achieved": achieved, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
-                        "frac": achieved / peaks["bf16_sustained"], "traffic": traffic,
-                        "peak_source": f"{peaks['source']} sustained bf16 (kernel timed inside a long step)",
-                        "gflop_per_launch": fl / ln / 1e9, "avg_launch_us": tm / ln * 1e6,
-                        "share_of_step": tm / (sum(c["ms_per_step"] for c in classes) * 1e-3),
-                        "dominant_class": dom["class"] if dom else None}
-        if args.profile_classes:
-            for c in classes:
-                print(json.dumps(c), file=sys.stderr)
+        if not tcs:
+            return None, per_class
+        fl = sum(c["gflop_per_step"] for c in tcs) * 1e9
+        tm = sum(c["ms_per_step"] for c in tcs) * 1e-3
+        ln = sum(c["launches_per_step"] for c in tcs)
+        achieved = fl / tm / 1e12
+        # DRAM bytes per launch cannot be measured without a profiler attached: it is taken from THIS round's committed
+        # `ncu --set full` capture of the same command, or reported as null when that capture is absent
+        traffic, traffic_src = None, None
+        tpath = os.path.join(ROOT, "profiles", "r02_traffic.json")
+        if os.path.exists(tpath):
+            with open(tpath) as tf:
+                td = json.load(tf)
+            if td.get("workload") == workload:
+                traffic, traffic_src = td.get("dram_bytes_per_launch"), td.get("source")
+        dom = max(classes, key=lambda d: d["ms_per_step"])
+        roofline = {"bound": "tensor", "kernel": "tc::conv_kernel / tc::pair_kernel / tc::wgrad_kernel (tcgen05 implicit GEMM)",
+                    "achieved": achieved, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
+                    "frac": achieved / peaks["bf16_sustained"], "traffic": traffic, "traffic_source": traffic_src,
+                    "peak_source": f"{peaks['source']} sustained bf16 (kernel timed inside a long step)",
+                    "gflop_per_launch": fl / ln / 1e9, "avg_launch_us": tm / ln * 1e6,
+                    "share_of_step": tm / (total_ms * 1e-3), "dominant_class": dom["class"]}
+        return roofline, per_class
 
-    cpu_baseline = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        sB = B if (train and B * T <= 512) else max(1, min(B, 2))
-        t_cpu, cores = cpu_step_time(cfg, sB, T, train, 2, 1)
-        cpu_baseline = {"value": O.audio_seconds(sB, T) / t_cpu, "unit": "audio-s/s", "cores": cores, "kind": "port",
-                        "sample": f"{'fwd+bwd' if train else 'fwd'} of {cfg_name} B={sB} T={T} fp32 CPU oracle, "
-                                  f"2 timed steps after 1 warm-up ({t_cpu:.2f} s/step)"}
+    def sub_record(self, name, steps, warmup):
+        """Short measurement of another BASELINE.json configuration at the same N (no profiling, no CPU leg)."""
+        from oracle import hifigan_oracle as O
+        torch = self.torch
+        step_device, step_e2e, info = self.setup(name)
+        ms = self.timed(step_device, steps, warmup)
+        ms_e2e = self.timed(step_e2e, max(2, steps // 2), 2)
+        audio_s = self.world * O.audio_seconds(info["B"], info["T"])
+        flops = O.forward_flops(info["cfg"], info["B"], info["T"]) * (3 if info["train"] else 1)
+        rec = {"config": make_config(self.args, name, self.world), "value": audio_s / (ms * 1e-3), "unit": "audio-s/s",
+               "ms_per_step": ms, "steps": steps, "warmup": warmup,
+               "tflops_algorithmic_per_gpu": flops / (ms * 1e-3) / 1e12,
+               "frac_of_bf16_peak_sustained": flops / (ms * 1e-3) / 1e12 / self.peaks["bf16_sustained"],
+               "e2e": {"value": audio_s / (ms_e2e * 1e-3), "unit": "audio-s/s", "ms_per_step": ms_e2e,
+                       "h2d_bytes_per_step": info["h2d"], "d2h_bytes_per_step": info["d2h"]}}
+        del step_device, step_e2e, info
+        torch.cuda.empty_cache()
+        return rec
 
-    if rank == 0:
-        audio_s = world * O.audio_seconds(B, T)
-        flops = O.forward_flops(cfg, B, T) * (3 if train else 1)
-        value = audio_s / (ms * 1e-3)
-        line = {"metric": "decoder_audio_seconds_per_second", "value": value, "unit": "audio-s/s", "n_gpus": world,
-                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": args.mode, "data": "synthetic",
-                "config": {"workload": args.workload, "cfg": cfg_name, "batch_per_gpu": B, "frames": T,
-                           "step": "weight-norm fold + fwd + bwd (233 param grads, dz, dg)" + (" + NCCL grad all-reduce" if world > 1 else "") if train else "fwd",
-                           "l2": "256 MB L2 flush between timed steps" if flush_buf is not None else "no flush",
-                           "random_init_weights": True},
-                "tflops_algorithmic": flops / (ms * 1e-3) / 1e12,
-                "frac_of_bf16_peak_sustained": flops / (ms * 1e-3) / 1e12 / peaks["bf16_sustained"],
-                "host_enqueue_ms_per_step": host_ms,
-                "gpu_launches": round(launches_per_step * args.steps), "gpu_launches_per_step": launches_per_step,
-                "clocks": clocks, "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu_baseline,
-                "kernel_classes": classes}
-        print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    def run(self):
+        from oracle import hifigan_oracle as O
+        args, torch, dist, lib = self.args, self.torch, self.dist, self.lib
+        rank, world = self.rank, self.world
+        step_device, step_e2e, info = self.setup(args.workload)
+        cfg, B, T, train, model = info["cfg"], info["B"], info["T"], info["train"], info["model"]
+
+        sampler = ClockSampler(self.local)
+        if rank == 0:
+            sampler.start()
+        lib.vcd_launch_count(1)
+        ms = self.timed(step_device, args.steps, args.warmup)
+        host_ms = self.host_ms
+        launches_total = lib.vcd_launch_count(1)
+        clocks = sampler.stop() if rank == 0 else None
+        launches_per_step = launches_total / (args.steps + args.warmup)
+
+        e2e = None
+        if not args.no_e2e:
+            ms_e2e = self.timed(step_e2e, args.steps, max(3, args.warmup // 2))
+            e2e = {"value": world * O.audio_seconds(B, T) / (ms_e2e * 1e-3), "unit": "audio-s/s",
+                   "h2d_bytes_per_step": info["h2d"], "d2h_bytes_per_step": info["d2h"], "ms_per_step": ms_e2e}
+
+        extra = {}
+        if not args.no_extra and args.workload == "train_base_b16" and args.mode == "bf16":
+            extra["train_48k_b32"] = self.sub_record("train_48k_b32", 10, 3)
+            extra["infer_10s"] = self.sub_record("infer_10s", 5, 3)
+
+        # ---- rooflines, measured live with CUDA events around every launch (rank 0) ----
+        roofline, classes, per_class = None, None, None
+        if world > 1:
+            dist.barrier()
+        if rank == 0:
+            classes = self.profile_classes(step_device, model)
+            roofline, per_class = self.rooflines(classes, args.workload)
+            if args.profile_classes:
+                for c in classes:
+                    print(json.dumps(c), file=sys.stderr)
+
+        cpu_baseline = None
+        if rank == 0 and world == 1 and not args.no_cpu_baseline:
+            cores = use_all_host_threads()
+            cpu_mod, sB = cpu_bounded_sample(cfg, B, T, train, 3, 1, budget_s=20.0)
+            t_cpu = cpu_time_steps(cpu_mod, cfg, sB, T, train, 3, 1)
+            cpu_baseline = {"value": O.audio_seconds(sB, T) / t_cpu, "unit": "audio-s/s", "cores": cores, "kind": "port",
+                            "sample": f"{'fwd+bwd' if train else 'fwd'} of {info['cfg_name']}, {sB} of the {B} utterances per step, "
+                                      f"T={T}, fp32 CPU oracle, 3 timed steps after 1 warm-up ({t_cpu:.2f} s/step), {cores} threads"}
+
+        if rank == 0:
+            audio_s = world * O.audio_seconds(B, T)
+            flops = O.forward_flops(cfg, B, T) * (3 if train else 1)
+            value = audio_s / (ms * 1e-3)
+            line = {"metric": METRIC, "value": value, "unit": "audio-s/s", "n_gpus": world,
+                    "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+                    "scaling": "weak", "vs_baseline": None, "dtype": args.mode, "data": "synthetic",
+                    "config": make_config(args, args.workload, world),
+                    "tflops_algorithmic": flops / (ms * 1e-3) / 1e12,
+                    "frac_of_bf16_peak_sustained": flops / (ms * 1e-3) / 1e12 / self.peaks["bf16_sustained"],
+                    "host_enqueue_ms_per_step": host_ms,
+                    "gpu_launches": round(launches_per_step * args.steps), "gpu_launches_per_step": launches_per_step,
+                    "clocks": clocks, "e2e": e2e, "roofline": roofline, "roofline_classes": per_class,
+                    "cpu_baseline": cpu_baseline, "kernel_classes": classes, "configs": extra or None}
+            print(json.dumps(line), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
 
 
 def main():
@@ -397,10 +510,13 @@ def main():
 
     builtins.print = emit
     try:
-        if args.impl == "reference":
+        if args.workload == "full_synth" and args.impl == "b200":
+            from tools import full_synth
+            full_synth.main(args)
+        elif args.impl == "reference":
             run_reference(args)
         else:
-            run_b200(args)
+            Bench(args).run()
     finally:
         builtins.print = _print
         real_stdout.flush()

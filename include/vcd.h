@@ -116,6 +116,11 @@ int vcd_backward(vcd_plan* plan, int mode, const float* dy_dev, const float* y_d
                  float* dx_dev, float* dg_dev, float* const* dparams_dev_ptrs, void* ws_dev, size_t ws_bytes,
                  int B, int T, uint32_t segment_mask, void* stream);
 
+/* Data-parallel training: every PARAMETER gradient written by vcd_backward is multiplied by `scale` (not dx / dg).
+ * With scale = 1 / world_size a plain SUM all-reduce of the gradient buffers yields the DDP average
+ * (train.py:99-100) without a separate scaling pass.  Default 1. */
+int vcd_set_gradient_scale(vcd_plan* plan, float scale);
+
 /* Backward segments, in execution order: segment 0 = conv_post + last upsample stage, ...,
  * last segment = conv_pre + cond.  vcd_segment_params lists the parameter indices finalised by a segment. */
 int vcd_num_backward_segments(const vcd_plan* plan);

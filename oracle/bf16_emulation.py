@@ -130,6 +130,29 @@ class _StoreAct(torch.autograd.Function):
         return gt * torch.where(t > 0, 1.0, ctx.slope).to(gt.dtype) + gx, None, None, None, None
 
 
+class _ActStore(torch.autograd.Function):
+    """Stored activation t = bf16(lrelu(x, slope)).  Backward: d x = d t * (t > 0 ? 1 : slope) -- the mask is taken from
+    the STORED tensor, exactly like the CUDA epilogues (on a knife-edge |x| ~ 1e-7 the sign of a recomputed x may differ)."""
+
+    @staticmethod
+    def forward(ctx, x, slope, stored, name):
+        t = _bf16(torch.where(x > 0, x, x * slope))
+        if stored is not None:
+            t = stored.check_and_substitute(name, t)
+        ctx.save_for_backward(t)
+        ctx.slope = slope
+        return t
+
+    @staticmethod
+    def backward(ctx, g):
+        (t,) = ctx.saved_tensors
+        return g * torch.where(t > 0, 1.0, ctx.slope).to(g.dtype), None, None, None
+
+
+def act_store(x, slope, stored=None, name=None):
+    return _ActStore.apply(x, slope, stored, name)
+
+
 def round_ste(x, stored=None, name=None):
     return _RoundSTE.apply(x, stored, name)
 
@@ -176,7 +199,7 @@ class EmulatedGenerator:
         for q in range(npairs):
             if self.rb1:
                 h1 = grad_round(self._wn_conv(f"{name}.convs1.{q}", t, dilations[q]), st, f"dm{i}.{j}.{q}")
-                mid = round_ste(_lrelu(h1, SLOPE), st, f"ma{i}.{j}.{q}")
+                mid = act_store(h1, SLOPE, st, f"ma{i}.{j}.{q}")
                 h2 = self._wn_conv(f"{name}.convs2.{q}", mid, 1)
             else:
                 h2 = self._wn_conv(f"{name}.convs.{q}", t, dilations[q])
@@ -191,7 +214,7 @@ class EmulatedGenerator:
         h = F.conv1d(round_ste(x, st, "xin"), round_ste(p["conv_pre.weight"]), p["conv_pre.bias"], 1, 3)
         if g is not None:
             h = h + F.conv1d(g, p["cond.weight"], p["cond.bias"])
-        a = round_ste(_lrelu(grad_round(h, st, "d0"), SLOPE), st, "a0")
+        a = act_store(grad_round(h, st, "d0"), SLOPE, st, "a0")
         nb = self.num_kernels
         inv_nb = float(np.float32(1.0) / np.float32(nb))
         n_up = len(cfg["upsample_rates"])
@@ -204,7 +227,7 @@ class EmulatedGenerator:
                 out = self._resblock(i, j, t0, x0, cfg["resblock_dilation_sizes"][j])
                 acc = out if acc is None else acc + out
             acc = grad_round(acc, st, f"Gi{i}")
-            a = round_ste(_lrelu(acc * inv_nb, FINAL_SLOPE if i == n_up - 1 else SLOPE), st, f"a{i + 1}")
+            a = act_store(acc * inv_nb, FINAL_SLOPE if i == n_up - 1 else SLOPE, st, f"a{i + 1}")
         return torch.tanh(F.conv1d(a, p["conv_post.weight"], None, 1, 3))
 
 

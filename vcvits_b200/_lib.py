@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libvcd.so")
 CSRC = os.path.join(_HERE, "csrc")
 SOURCES = ["vcd_api.cu"]
-HEADERS = ["common.cuh", "simt_kernels.cuh", "fold.cuh", "plan.h", "tc_conv.cuh", "tc_kernels.cuh"]
+HEADERS = ["common.cuh", "simt_kernels.cuh", "fold.cuh", "fold_fast.cuh", "plan.h", "tc_conv.cuh", "tc_kernels.cuh"]
 
 MODE_FP32 = 0
 MODE_BF16 = 1
@@ -93,6 +93,7 @@ _SIGNATURES = {
                               C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "vcd_backward": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                _FLOATPP, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_uint32, C.c_void_p]),
+    "vcd_set_gradient_scale": (C.c_int, [C.c_void_p, C.c_float]),
     "vcd_num_backward_segments": (C.c_int, [C.c_void_p]),
     "vcd_segment_params": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.c_int]),
     "vcd_host_call_extra_bytes": (C.c_size_t, [C.c_void_p, C.c_int, C.c_int]),

@@ -178,7 +178,7 @@ __device__ __forceinline__ float unfold_fetch(const UnfoldJob& jb, const float* 
 __global__ void __launch_bounds__(256)
 wn_unfold_kernel(const UnfoldJob* __restrict__ jobs, int njobs, const float* const* __restrict__ params,
                  float* const* __restrict__ dparams, const float* __restrict__ norms,
-                 const float* __restrict__ scratch, int block_base) {
+                 const float* __restrict__ scratch, int block_base, float gscale) {
   // block_base: first_block of jobs[0] when only a tail slice of a segment's table is launched
   const int blk = static_cast<int>(blockIdx.x) + block_base;
   int lo = 0, hi = njobs - 1;
@@ -190,12 +190,12 @@ wn_unfold_kernel(const UnfoldJob* __restrict__ jobs, int njobs, const float* con
   const int row = blk - jb.first_block;
   if (jb.kind == 1) {
     const long long e = static_cast<long long>(row) * 256 + threadIdx.x;
-    if (e < jb.numel) dparams[jb.p_w][e] = scratch[jb.src_off + e];
+    if (e < jb.numel) dparams[jb.p_w][e] = scratch[jb.src_off + e] * gscale;
     return;
   }
   float* dw = dparams[jb.p_w] + static_cast<size_t>(row) * jb.row_len;
   if (jb.p_g < 0 || params[jb.p_g] == nullptr) {   // plain weight (never weight-normed, or remove_weight_norm was called)
-    for (int i = threadIdx.x; i < jb.row_len; i += 256) dw[i] = unfold_fetch(jb, scratch, row, i);
+    for (int i = threadIdx.x; i < jb.row_len; i += 256) dw[i] = unfold_fetch(jb, scratch, row, i) * gscale;
     return;
   }
   const float* v = params[jb.p_w] + static_cast<size_t>(row) * jb.row_len;
@@ -209,8 +209,8 @@ wn_unfold_kernel(const UnfoldJob* __restrict__ jobs, int njobs, const float* con
   const float norm = norms[jb.norm_off + row];
   const float gval = params[jb.p_g][row];
   const float inv = 1.f / norm;
-  if (threadIdx.x == 0) dparams[jb.p_g][row] = dot * inv;
-  const float a = gval * inv, bcoef = dot * inv * inv;
+  if (threadIdx.x == 0) dparams[jb.p_g][row] = dot * inv * gscale;
+  const float a = gval * inv * gscale, bcoef = dot * inv * inv;
   for (int i = threadIdx.x; i < jb.row_len; i += 256) dw[i] = a * (unfold_fetch(jb, scratch, row, i) - v[i] * bcoef);
 }
 

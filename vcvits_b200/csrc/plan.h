@@ -10,6 +10,7 @@
 #include "../../include/vcd.h"
 #include "common.cuh"
 #include "fold.cuh"
+#include "fold_fast.cuh"
 
 namespace vcd {
 
@@ -43,6 +44,10 @@ struct Layer {
 struct SegmentJobs {
   UnfoldJob* d_jobs = nullptr;
   int njobs = 0, nblocks = 0;
+  // bandwidth-shaped variant (fold_fast.cuh), used when every layer of the segment qualifies
+  FastUnfoldJob* d_fast = nullptr;
+  int fast_njobs = 0, fast_nblocks = 0, fast_lead_jobs = 0, fast_lead_blocks = 0;
+  size_t fast_smem = 0;
   int lead_jobs = 0, lead_blocks = 0;            // jobs / blocks ahead of the first layer's (conv_post.weight in segment 0)
   long long scratch_begin = 0, scratch_end = 0;  // float range of the gradient scratch to zero
   std::vector<int> params;
@@ -98,6 +103,14 @@ struct vcd_plan {
   int n_norm_jobs = 0, n_norm_blocks = 0;
   vcd::PackJob* d_pack_jobs[2] = {nullptr, nullptr};  // per mode
   int n_pack_jobs[2] = {0, 0}, n_pack_blocks[2] = {0, 0};
+  // bf16 mode: layers whose two tensor-core operand formats are written by wn_pack_fast_kernel (norms included);
+  // the generic norm / pack tables of that mode then only hold the remaining layers
+  vcd::FastPackJob* d_fast_pack = nullptr;
+  int n_fast_pack_jobs = 0, n_fast_pack_blocks = 0;
+  size_t fast_pack_smem = 0;
+  vcd::NormJob* d_norm_jobs_bf16 = nullptr;
+  int n_norm_jobs_bf16 = 0, n_norm_blocks_bf16 = 0;
+  float grad_scale = 1.f;                  // multiplies every parameter gradient (vcd_set_gradient_scale)
   std::vector<vcd::SegmentJobs> segments;
 
   // auxiliary streams / events for intra-step concurrency (ResBlock branches, weight-gradient kernels)

@@ -278,19 +278,19 @@ cond_fwd_kernel(const float* __restrict__ w, const float* __restrict__ bias, con
 __global__ void __launch_bounds__(256)
 cond_bwd_kernel(const float* __restrict__ dcb, const float* __restrict__ w, const float* __restrict__ gv,
                 float* __restrict__ d_pre_bias, float* __restrict__ d_cond_bias, float* __restrict__ d_cond_w,
-                int B, int N, int G) {
+                int B, int N, int G, float gscale) {
   const long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
   if (i < N) {
     float s = 0.f;
     for (int b = 0; b < B; ++b) s += dcb[static_cast<size_t>(b) * N + i];
-    if (d_pre_bias) d_pre_bias[i] = s;
-    if (d_cond_bias) d_cond_bias[i] = s;
+    if (d_pre_bias) d_pre_bias[i] = s * gscale;
+    if (d_cond_bias) d_cond_bias[i] = s * gscale;
   }
   if (d_cond_w && i < static_cast<long long>(N) * G) {
     const int n = static_cast<int>(i / G), c = static_cast<int>(i % G);
     float s = 0.f;
     for (int b = 0; b < B; ++b) s = fmaf(dcb[static_cast<size_t>(b) * N + n], gv[static_cast<size_t>(b) * G + c], s);
-    d_cond_w[i] = s;
+    d_cond_w[i] = s * gscale;
   }
 }
 
@@ -318,43 +318,55 @@ cond_dg_kernel(const float* __restrict__ dcb, const float* __restrict__ w, float
 
 // -------------------------------------------------------------------------------------------------
 // conv_post (C -> 1, k = 7, no bias) + tanh.  HBM-bound: 2*C bytes read per output sample (bf16).
-// w is the raw parameter [1][C][7].  grid = (ceil(L/256), B), block = 256, smem = C*7 floats.
+// One thread owns one INPUT ROW (time step): it loads the row once (C/8 16-byte loads, consecutive threads read
+// consecutive 16-byte rows of a channel group: perfectly coalesced, no halo re-reads) and forms the seven per-tap
+// partial dot products  p_j[r] = sum_c a[r][c] * w[c][j];  the output  y[t] = tanh(sum_j p_j[t + j - 3])  then
+// gathers seven floats through shared memory.  A CTA of 256 rows produces 250 outputs (3-row halo each side; the
+// zero pad rows of the layout ARE the convolution's zero padding).  The round-1 kernel re-read every row seven
+// times through L1 (one thread per output, seven overlapping row loads).
+// w is the raw parameter [1][C][7].  grid = (ceil(L/250), B), block = 256, smem = C*8 floats.
 // -------------------------------------------------------------------------------------------------
+constexpr int kPostOut = 250;
+
 template <typename T>
 __global__ void __launch_bounds__(256)
 conv_post_fwd_kernel(const T* __restrict__ a, const float* __restrict__ w, float* __restrict__ y, int C, int L) {
-  extern __shared__ float ws[];  // [7][C]
-  for (int i = threadIdx.x; i < C * 7; i += 256) {
-    const int c = i / 7, j = i - c * 7;
-    ws[j * C + c] = w[i];
+  extern __shared__ float ws[];          // [C][8]: the seven taps of a channel, padded to two float4
+  __shared__ float part[7][256 + 8];
+  for (int i = threadIdx.x; i < C * 8; i += 256) {
+    const int c = i >> 3, j = i & 7;
+    ws[i] = j < 7 ? __ldg(w + c * 7 + j) : 0.f;
   }
   __syncthreads();
-  const int t = blockIdx.x * 256 + threadIdx.x, b = blockIdx.y;
-  if (t >= L) return;
-  float acc = 0.f;
-  for (int cg = 0; cg < (C >> 3); ++cg) {
-    const T* base = a + blk_row(b, cg, 0, C, L);
-    // branch-free: all seven row loads of the channel group are in flight before the first FMA (out-of-range taps
-    // re-read row t and are masked out), instead of one L2 round trip per tap
-    float v[7][8];
+  const int b = blockIdx.y;
+  const int r = blockIdx.x * kPostOut - 3 + static_cast<int>(threadIdx.x);   // this thread's input row
+  float p[7];
 #pragma unroll
-    for (int j = 0; j < 7; ++j) {
-      const int r = t + j - 3;
-      const bool ok = r >= 0 && r < L;
-      load8<T>(base + static_cast<size_t>(ok ? r : t) * 8, v[j]);
-    }
+  for (int j = 0; j < 7; ++j) p[j] = 0.f;
+  if (r < L + kPadR) {                    // r >= -3 >= -kPadL always
+    for (int cg = 0; cg < (C >> 3); ++cg) {
+      float v[8];
+      load8<T>(a + blk_row(b, cg, r, C, L), v);
 #pragma unroll
-    for (int j = 0; j < 7; ++j) {
-      const int r = t + j - 3;
-      const float keep = (r >= 0 && r < L) ? 1.f : 0.f;
-      const float* wr = ws + j * C + cg * 8;
-      float part = 0.f;
-#pragma unroll
-      for (int c = 0; c < 8; ++c) part = fmaf(v[j][c], wr[c], part);
-      acc = fmaf(part, keep, acc);
+      for (int c = 0; c < 8; ++c) {
+        const float4 w0 = *reinterpret_cast<const float4*>(ws + (cg * 8 + c) * 8);
+        const float4 w1 = *reinterpret_cast<const float4*>(ws + (cg * 8 + c) * 8 + 4);
+        p[0] = fmaf(v[c], w0.x, p[0]); p[1] = fmaf(v[c], w0.y, p[1]); p[2] = fmaf(v[c], w0.z, p[2]);
+        p[3] = fmaf(v[c], w0.w, p[3]); p[4] = fmaf(v[c], w1.x, p[4]); p[5] = fmaf(v[c], w1.y, p[5]);
+        p[6] = fmaf(v[c], w1.z, p[6]);
+      }
     }
   }
-  y[static_cast<size_t>(b) * L + t] = tanhf(acc);
+#pragma unroll
+  for (int j = 0; j < 7; ++j) part[j][threadIdx.x] = p[j];
+  __syncthreads();
+  const int t = blockIdx.x * kPostOut + static_cast<int>(threadIdx.x);
+  if (threadIdx.x < kPostOut && t < L) {
+    float acc = 0.f;
+#pragma unroll
+    for (int j = 0; j < 7; ++j) acc += part[j][threadIdx.x + j];   // row t + j - 3 is thread (t - t0) + j
+    y[static_cast<size_t>(b) * L + t] = tanhf(acc);
+  }
 }
 
 // Data gradient of conv_post + tanh, fused with the final leaky_relu(0.01) mask and the 1/num_kernels of the

@@ -122,13 +122,18 @@ inline cudaError_t tc_conv_dispatch(int f, const tc::ConvParams* P, int grid, si
     case 8: return tc_conv_launch_one<8>(P, grid, smem, stream, pdl);
     case 14: return tc_conv_launch_one<14>(P, grid, smem, stream, pdl);
     case 15: return tc_conv_launch_one<15>(P, grid, smem, stream, pdl);
+    case 17: return tc_conv_launch_one<17>(P, grid, smem, stream, pdl);   // EPI_SMEM variants of 1, 2, 3, 7, 15
+    case 18: return tc_conv_launch_one<18>(P, grid, smem, stream, pdl);
+    case 19: return tc_conv_launch_one<19>(P, grid, smem, stream, pdl);
+    case 23: return tc_conv_launch_one<23>(P, grid, smem, stream, pdl);
+    case 31: return tc_conv_launch_one<31>(P, grid, smem, stream, pdl);
     default: return P ? cudaErrorInvalidValue : cudaSuccess;
   }
 }
 
 inline int tc_plan_init(vcd_plan* p) {
   cudaError_t e = cudaSuccess;
-  for (int f = 0; f < 16 && e == cudaSuccess; ++f) e = tc_conv_dispatch(f, nullptr, 0, 0, 0, false);
+  for (int f = 0; f < 32 && e == cudaSuccess; ++f) e = tc_conv_dispatch(f, nullptr, 0, 0, 0, false);
   if (e != cudaSuccess) return 1;
   e = cudaFuncSetAttribute(tc::wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   if (e != cudaSuccess) return 1;
@@ -181,6 +186,24 @@ inline int tc_run_conv(vcd_plan* p, const Layer& L, bool dgrad, const void* in, 
     static const int force_mt = tc_env_int("VCD_CONV_MT", 0);
     if (force_mt > 0 && force_mt * P.BN <= 512 && force_mt <= mtiles) { MT = force_mt; bufs = 2 * MT * P.BN <= 512 ? 2 : 1; }
   }
+  // epilogue feature set -> instantiation (a superset is always valid: unused operands are null-checked or zero)
+  int f = (e.mask ? tc::EPI_MASK : 0) | (e.res_t ? tc::EPI_RES : 0) | (e.res2 ? tc::EPI_RES2 : 0) | (e.out_raw ? tc::EPI_RAW : 0);
+  if (f & (tc::EPI_RES2 | tc::EPI_RAW)) {
+    if (f & tc::EPI_RES) f |= tc::EPI_RES2 | tc::EPI_RAW;      // running-sum variants: {RES,RES2,RAW} (+MASK)
+  }
+  if (f == (tc::EPI_RAW | tc::EPI_RES2)) f = tc::EPI_RES | tc::EPI_RES2 | tc::EPI_RAW;
+  {
+    const bool known = f == 0 || f == 1 || f == 2 || f == 3 || f == 6 || f == 7 || f == 8 || f == 14 || f == 15;
+    if (!known) f = 15;
+  }
+  // EPI_SMEM candidates: bf16 operands in the output's own layout (plain convolution geometry), instantiations 1, 2, 3, 7, 15
+  static const int esmem_on = tc_env_int("VCD_CONV_ESMEM", 1), ne_want = tc_env_int("VCD_CONV_NE", 2),
+                   na_small = tc_env_int("VCD_CONV_NA_SMALL", 4);
+  const int e_nops = ((f & tc::EPI_MASK) && e.mask ? 1 : 0) + ((f & tc::EPI_RES) && e.res_t ? 1 : 0);
+  const bool e_cand = esmem_on && e_nops > 0 && g.os == 1 && g.p == 0 && g.creal == g.N &&
+                      (f == 1 || f == 2 || f == 3 || f == 7 || f == 15) &&
+                      ((f & tc::EPI_MASK) == 0 || e.mask) && ((f & tc::EPI_RES) == 0 || e.res_t);
+  P.NE = 0; P.e_ops = 0; P.e_stage_bytes = 0;
   const int kb0 = P.KB;
   size_t a_stage = 0, w_region = 0;
   for (;; MT /= 2) {  // a row-tile count whose rings do not fit the shared-memory budget falls back to the next smaller one
@@ -215,9 +238,20 @@ inline int tc_run_conv(vcd_plan* p, const Layer& L, bool dgrad, const void* in, 
   }
   if (P.NA * a_stage > budget / 2) P.NA = 2;
   P.w_resident = (P.n_tiles_n == 1 && w_all <= 100 * 1024 && P.NA * a_stage + w_all <= budget) ? 1 : 0;
+  P.NE = 0; P.e_ops = 0; P.e_stage_bytes = 0;
   if (P.w_resident) {
     P.TPS = g.taps; P.NW = 1;
     w_region = w_all;
+    // Small-channel layers are bound by the LATENCY of their loads (a 128-row tile of 32 channels is 8 KB): keep more
+    // tiles in flight -- a deeper activation ring and the epilogue operands staged by the bulk-copy engine.
+    size_t used = P.NA * a_stage + w_all;
+    if (e_cand) {
+      const size_t e_stage = static_cast<size_t>(e_nops) * MT * P.BN * 256;
+      int ne = ne_want;
+      while (ne >= 2 && used + ne * e_stage > budget) --ne;
+      if (ne >= 2) { P.NE = ne > 4 ? 4 : ne; P.e_ops = e_nops; P.e_stage_bytes = static_cast<uint32_t>(e_stage); used += P.NE * e_stage; }
+    }
+    while (P.NA < na_small && used + a_stage <= budget && (P.NA + 1) * a_stage <= 96 * 1024) { ++P.NA; used += a_stage; }
   } else {
     if (P.NA * a_stage + 2 * w_tap > budget) {  // not even two one-tap weight stages beside the activation stages
       if (MT > 1) continue;
@@ -240,7 +274,8 @@ inline int tc_run_conv(vcd_plan* p, const Layer& L, bool dgrad, const void* in, 
   }
   break;
   }
-  const size_t smem = 128 + P.NA * a_stage + w_region + (2 * P.NA + 16 + 4) * 8 + 16 + 2 * 128 * 4;
+  const size_t smem = 128 + P.NA * a_stage + w_region + static_cast<size_t>(P.NE) * P.e_stage_bytes + (2 * P.NA + 16 + 4 + 8) * 8 + 16 + 2 * 128 * 4;
+  if (P.NE > 0) f |= tc::EPI_SMEM;
   if (smem > 227 * 1024) {
     snprintf(err, errn, "tc_run_conv(%s): shared memory budget exceeded (%zu bytes)", L.name.c_str(), smem);
     return 1;
@@ -261,14 +296,6 @@ inline int tc_run_conv(vcd_plan* p, const Layer& L, bool dgrad, const void* in, 
   const int ctas_per_sm = (occ2 && smem <= 110 * 1024 && P.tmem_cols <= 256) ? 2 : 1;
   const int max_ctas = p->num_sms * ctas_per_sm;
   const int grid = P.total_tiles < max_ctas ? P.total_tiles : max_ctas;
-  // epilogue feature set -> instantiation (a superset is always valid: unused operands are null-checked or zero)
-  int f = (e.mask ? tc::EPI_MASK : 0) | (e.res_t ? tc::EPI_RES : 0) | (e.res2 ? tc::EPI_RES2 : 0) | (e.out_raw ? tc::EPI_RAW : 0);
-  if (f & (tc::EPI_RES2 | tc::EPI_RAW)) {
-    if (f & tc::EPI_RES) f |= tc::EPI_RES2 | tc::EPI_RAW;      // running-sum variants: {RES,RES2,RAW} (+MASK)
-  }
-  if (f == (tc::EPI_RAW | tc::EPI_RES2)) f = tc::EPI_RES | tc::EPI_RES2 | tc::EPI_RAW;
-  const bool known = f == 0 || f == 1 || f == 2 || f == 3 || f == 6 || f == 7 || f == 8 || f == 14 || f == 15;
-  if (!known) f = 15;
   if (blk_elems(B, g.creal, Lout) >= (1ull << 31)) {  // the epilogue addresses its operands with 32-bit element offsets
     snprintf(err, errn, "tc_run_conv(%s): output tensor of %zu elements exceeds the 2^31-element limit of the tensor-core path",
              L.name.c_str(), blk_elems(B, g.creal, Lout));

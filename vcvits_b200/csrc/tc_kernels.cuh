@@ -233,6 +233,9 @@ struct ConvParams {
   int acc_bufs;           // 2: accumulators double-buffered (epilogue overlaps the next tile's MMAs); 1: MT*BN > 256
   uint32_t tmem_cols;
   int pdl_late;           // 1: release the stream successor after this CTA's last MMAs are issued (default: at its last tile's loads)
+  int NE;                 // EPI_SMEM: stages of the epilogue-operand ring (mask / residual tiles fetched by the bulk-copy engine)
+  int e_ops;              // operands per stage (mask, residual)
+  uint32_t e_stage_bytes; // e_ops * MT * (BN/8) * 128 rows * 16 B
   unsigned long long* trace;  // debug: %globaltimer stamps of CTA 0 (null = off)
 };
 
@@ -245,7 +248,11 @@ __device__ __forceinline__ void ktrace(unsigned long long* buf, int slot) {
 }
 
 // Compile-time epilogue features: unused operand paths (and their registers) vanish from the specialisation.
-enum : int { EPI_MASK = 1, EPI_RES = 2, EPI_RES2 = 4, EPI_RAW = 8 };
+// EPI_SMEM: the bf16 epilogue operands (mask, residual) of a tile are staged in shared memory by a producer warp
+// (one 2 KB bulk copy per channel group and 128-row tile, several tiles ahead) instead of being loaded from global
+// memory by the epilogue threads: the epilogue of the <= 64-channel layers is bound by the latency of those loads and
+// by their 64-bit address arithmetic, not by a pipe (profiles/r01_ncu_conv_c32_full_summary.md).
+enum : int { EPI_MASK = 1, EPI_RES = 2, EPI_RES2 = 4, EPI_RAW = 8, EPI_SMEM = 16 };
 
 struct EpiLoads {
   uint4 mask, rest;
@@ -264,8 +271,10 @@ __device__ __forceinline__ void unpack8(const uint4& raw, float (&f)[8]) {
 template <int F>
 __device__ __forceinline__ void epi_prefetch(const Epilogue& e, uint32_t o, bool valid, EpiLoads& L) {
   if (!valid) return;
-  if constexpr (F & EPI_MASK) L.mask = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(e.mask) + o));
-  if constexpr (F & EPI_RES) L.rest = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(e.res_t) + o));
+  if constexpr (!(F & EPI_SMEM)) {
+    if constexpr (F & EPI_MASK) L.mask = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(e.mask) + o));
+    if constexpr (F & EPI_RES) L.rest = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(e.res_t) + o));
+  }
   if constexpr (F & EPI_RES2) {
     if (e.res2) {
       L.r2a = __ldg(reinterpret_cast<const float4*>(e.res2 + o));
@@ -345,20 +354,24 @@ conv_kernel(const ConvParams P) {
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
   uint8_t* a_smem = smem;
   uint8_t* w_smem = a_smem + static_cast<size_t>(P.NA) * a_stage_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(w_smem + w_region_bytes);
+  uint8_t* e_smem = w_smem + w_region_bytes;                                     // EPI_SMEM: NE stages of epilogue operands
+  uint64_t* bars = reinterpret_cast<uint64_t*>(e_smem + static_cast<size_t>(P.NE) * P.e_stage_bytes);
   uint64_t* fullA = bars;
   uint64_t* emptyA = fullA + P.NA;
   uint64_t* fullW = emptyA + P.NA;      // ring mode: NW entries; resident mode: entry 0 = "weights loaded"
   uint64_t* emptyW = fullW + 8;
   uint64_t* acc_full = emptyW + 8;
   uint64_t* acc_empty = acc_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  uint64_t* fullE = acc_empty + 2;
+  uint64_t* emptyE = fullE + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(emptyE + 4);
   float* bias_s = reinterpret_cast<float*>(tmem_slot + 4);   // [2][128]: per-tile bias (+ per-batch bias), double-buffered
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < P.NA; ++i) { mbar_init(&fullA[i], 1); mbar_init(&emptyA[i], 1); }
     for (int i = 0; i < 8; ++i) { mbar_init(&fullW[i], 1); mbar_init(&emptyW[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 8); }
+    for (int i = 0; i < 4; ++i) { mbar_init(&fullE[i], 1); mbar_init(&emptyE[i], 8); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, P.tmem_cols);
@@ -413,6 +426,39 @@ conv_kernel(const ConvParams P) {
           bulk_load(w_smem + off, reinterpret_cast<const uint8_t*>(P.w) + off, min(65536u, total - off), &fullW[0]);
       }
       __syncwarp();
+      if constexpr (F & EPI_SMEM) {
+        // ===== epilogue-operand producer: the mask / residual tiles of every output tile, NE tiles ahead =====
+        // os == 1, p == 0, one column tile (host-checked): output row == accumulator row, and a (channel group, 128-row
+        // tile) of an operand is one contiguous 2 KB run of the row-padded layout.
+        const int groups = P.BN / 8;
+        const size_t cg_stride_e = static_cast<size_t>(padded_len(P.Lout)) * 8;
+        const bf16* ops[2] = {nullptr, nullptr};
+        int nops = 0;
+        if constexpr (F & EPI_MASK) ops[nops++] = reinterpret_cast<const bf16*>(P.e.mask);
+        if constexpr (F & EPI_RES) ops[nops++] = reinterpret_cast<const bf16*>(P.e.res_t);
+        Pipe pe;
+        pdl_wait();
+        for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+          int b, mg;
+          P.d_mgroups.divmod(tile, b, mg);
+          int mt_live = P.MT;
+          while (mt_live > 1 && (mg * P.MT + mt_live - 1) * 128 >= P.Lq) --mt_live;
+          mbar_wait(&emptyE[pe.stage], pe.phase ^ 1);
+          uint8_t* stage = e_smem + static_cast<size_t>(pe.stage) * P.e_stage_bytes;
+          if (elect_one()) {
+            mbar_expect_tx(&fullE[pe.stage], static_cast<uint32_t>(nops * mt_live * groups) * 2048u);
+            for (int op = 0; op < nops; ++op) {
+              const bf16* src0 = ops[op] + blk_row(b, 0, mg * P.MT * 128, P.g.creal, P.Lout);
+              for (int mt = 0; mt < mt_live; ++mt)
+                for (int cg = 0; cg < groups; ++cg)
+                  bulk_load(stage + ((static_cast<size_t>(op) * P.MT + mt) * groups + cg) * 2048, src0 + cg * cg_stride_e + static_cast<size_t>(mt) * 128 * 8,
+                            2048u, &fullE[pe.stage]);
+            }
+          }
+          __syncwarp();
+          pe.advance(P.NE);
+        }
+      }
     } else {
       Pipe pw;
       const size_t tap_stride_g = static_cast<size_t>(P.g.K / 8) * P.BN * 8;
@@ -638,6 +684,11 @@ conv_kernel(const ConvParams P) {
         epi_prefetch<F>(e, un.o, un.valid, fill[0]);
         epi_prefetch<F>(e, un.o + chunk_stride, un.valid, fill[1]);
       }
+      int e_stage = 0;
+      if constexpr (F & EPI_SMEM) {
+        e_stage = it % P.NE;
+        if (first) mbar_wait(&fullE[e_stage], static_cast<uint32_t>(it / P.NE) & 1u);
+      }
       if (first) {
         mbar_wait(&acc_full[buf], use_n & 1);
         tc_fence_after();
@@ -651,6 +702,19 @@ conv_kernel(const ConvParams P) {
           float v[8];
 #pragma unroll
           for (int n = 0; n < 8; ++n) v[n] = acc[h * 8 + n];
+          if constexpr (F & EPI_SMEM) {   // this row's 16 bytes of each staged operand: [op][mt][channel group][128 rows][16 B]
+            const int mt = u >> P.units_shift;
+            const int cg = ((u - (mt << P.units_shift)) << 1) + h;
+            const int groups = P.BN >> 3;
+            const uint8_t* ep = e_smem + static_cast<size_t>(e_stage) * P.e_stage_bytes +
+                                (static_cast<size_t>(mt * groups + cg) * 128 + row_in_tile) * 16;
+            const size_t op_stride = static_cast<size_t>(P.MT) * groups * 2048;
+            if constexpr (F & EPI_MASK) {
+              use[h].mask = *reinterpret_cast<const uint4*>(ep);
+              ep += op_stride;
+            }
+            if constexpr (F & EPI_RES) use[h].rest = *reinterpret_cast<const uint4*>(ep);
+          }
           epi_finish<F>(e, P.g, tcur.b, uc.ro, uc.ch + h * 8, uc.o + h * chunk_stride, use[h],
                         has_bias ? bias_s + (bias_once ? 0 : (it & 1) * 128) + (uc.ch - tcur.ch_tile) + h * 8 : nullptr, plain_out,
                         s_pos, s_neg, v);
@@ -660,6 +724,9 @@ conv_kernel(const ConvParams P) {
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&acc_empty[buf]);
+        if constexpr (F & EPI_SMEM) {
+          if (lane == 0) mbar_arrive(&emptyE[e_stage]);
+        }
         if (warp == 2 && lane == 0 && it < 4) ktrace(P.trace, 16 + it);   // epilogue of tile `it` done
       }
       tile = n_tile; it = n_it; u = n_u;

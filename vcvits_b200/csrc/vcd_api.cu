@@ -358,19 +358,59 @@ extern "C" int vcd_plan_create(const vcd_config* cfg, vcd_plan** out_plan) {
     if (L.p_g >= 0) p->is_weight_g[L.p_g] = 1;
 
   // ---- fold job tables ----
-  {
+  // layers handled by the bandwidth-shaped fold kernels (fold_fast.cuh): both operand formats on the tensor-core path,
+  // whole taps per upsample phase (k % u == 0), rows in groups of 8
+  static const int fast_fold = tc_env_int("VCD_FAST_FOLD", 1);
+  auto fast_shape = [&](const Layer& L) {
+    const ParamInfo& pv = p->params[L.p_w];
+    return fast_fold && L.k % L.u == 0 && pv.shape[0] % 8 == 0 && pv.shape[1] % 8 == 0 && (pv.numel / pv.shape[0]) % 4 == 0;
+  };
+  auto fast_pack_ok = [&](const Layer& L) { return fast_shape(L) && L.tc_ok_fwd && L.tc_ok_dgr; };
+  for (int bf = 0; bf < 2; ++bf) {
     std::vector<NormJob> nj;
     int blk = 0;
     for (const Layer& L : p->layers) {
-      if (!L.wn) continue;
+      if (!L.wn || (bf && fast_pack_ok(L))) continue;
       const ParamInfo& pv = p->params[L.p_w];
       NormJob j{L.p_w, static_cast<int>(pv.shape[0]), static_cast<int>(pv.numel / pv.shape[0]), L.norm_off, blk};
       blk += j.rows;
       nj.push_back(j);
     }
-    p->n_norm_jobs = static_cast<int>(nj.size());
-    p->n_norm_blocks = blk;
-    TRY(upload_jobs(nj, &p->d_norm_jobs));
+    if (!bf) {
+      p->n_norm_jobs = static_cast<int>(nj.size());
+      p->n_norm_blocks = blk;
+      TRY(upload_jobs(nj, &p->d_norm_jobs));
+    } else {
+      p->n_norm_jobs_bf16 = static_cast<int>(nj.size());
+      p->n_norm_blocks_bf16 = blk;
+      TRY(upload_jobs(nj, &p->d_norm_jobs_bf16));
+    }
+  }
+  {
+    std::vector<FastPackJob> fj;
+    int blk = 0;
+    for (const Layer& L : p->layers) {
+      if (!fast_pack_ok(L)) continue;
+      const ParamInfo& pv = p->params[L.p_w];
+      FastPackJob j{};
+      j.p_w = L.p_w; j.p_g = L.p_g; j.norm_off = L.wn ? L.norm_off : 0;
+      j.rows = static_cast<int>(pv.shape[0]); j.inner = static_cast<int>(pv.shape[1]); j.k = L.k; j.u = L.u;
+      j.is_convt = L.kind == LK_CONVT ? 1 : 0;
+      // format R = "row is the GEMM column": Conv1d forward / ConvTranspose1d data gradient
+      j.nt_r = j.is_convt ? L.nt_dgr : L.nt_fwd;
+      j.nt_c = j.is_convt ? L.nt_fwd : L.nt_dgr;
+      j.dst_r = j.is_convt ? L.tc_dgr : L.tc_fwd;
+      j.dst_c = j.is_convt ? L.tc_fwd : L.tc_dgr;
+      j.first_block = blk;
+      blk += j.rows / kFoldRows;
+      p->fast_pack_smem = std::max(p->fast_pack_smem, sizeof(float) * kFoldRows * (static_cast<size_t>(j.inner) * fold_ks(j.k) + 1));
+      fj.push_back(j);
+    }
+    p->n_fast_pack_jobs = static_cast<int>(fj.size());
+    p->n_fast_pack_blocks = blk;
+    TRY(upload_jobs(fj, &p->d_fast_pack));
+    if (p->fast_pack_smem > 200 * 1024) return fail("internal: fast fold tile of %zu bytes", p->fast_pack_smem);
+    if (blk) CU_TRY(cudaFuncSetAttribute(wn_pack_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(p->fast_pack_smem)));
   }
   for (int mode = 0; mode < 2; ++mode) {
     std::vector<PackJob> pj;
@@ -391,6 +431,7 @@ extern "C" int vcd_plan_create(const vcd_config* cfg, vcd_plan** out_plan) {
       pj.push_back(j);
     };
     for (const Layer& L : p->layers) {
+      if (mode == VCD_MODE_BF16 && fast_pack_ok(L)) continue;   // written by wn_pack_fast_kernel
       const bool tcf = mode == VCD_MODE_BF16 && L.tc_ok_fwd, tcd = mode == VCD_MODE_BF16 && L.tc_ok_dgr;
       push(L, false, tcf ? FMT_TC : FMT_F32);
       push(L, true, tcd ? FMT_TC : FMT_F32);
@@ -400,6 +441,7 @@ extern "C" int vcd_plan_create(const vcd_config* cfg, vcd_plan** out_plan) {
     TRY(upload_jobs(pj, &p->d_pack_jobs[mode]));
   }
   // ---- unfold job tables (per segment) ----
+  size_t unfold_smem_max = 0;
   for (int seg = 0; seg <= S; ++seg) {
     std::vector<UnfoldJob> uj;
     int blk = 0;
@@ -435,7 +477,40 @@ extern "C" int vcd_plan_create(const vcd_config* cfg, vcd_plan** out_plan) {
     sj.njobs = static_cast<int>(uj.size());
     sj.nblocks = blk;
     TRY(upload_jobs(uj, &sj.d_jobs));
+    // the same jobs for wn_unfold_fast_kernel (8 rows per block, 1024 elements per copy block)
+    bool all_fast = true;
+    for (const Layer& L : p->layers)
+      if (L.segment == seg && !fast_shape(L)) all_fast = false;
+    if (all_fast) {
+      std::vector<FastUnfoldJob> fj;
+      int fblk = 0;
+      for (size_t n = 0; n < uj.size(); ++n) {
+        const UnfoldJob& o = uj[n];
+        FastUnfoldJob j{};
+        j.kind = o.kind; j.p_w = o.p_w; j.p_g = o.p_g; j.norm_off = o.norm_off; j.src_off = o.src_off; j.numel = o.numel;
+        j.first_block = fblk;
+        if (o.kind == 1) {
+          fblk += static_cast<int>((o.numel + 1023) / 1024);
+        } else {
+          const ParamInfo& pv = p->params[o.p_w];
+          j.rows = o.rows; j.inner = static_cast<int>(pv.shape[1]); j.k = o.map.k;
+          j.is_convt = o.map.src == SRC_CONVT_FWD ? 1 : 0;
+          j.u = j.is_convt ? o.map.u : 1;
+          j.K = o.K; j.N = o.N;
+          fblk += j.rows / kFoldRows;
+          sj.fast_smem = std::max(sj.fast_smem, sizeof(float) * kFoldRows * (static_cast<size_t>(j.inner) * fold_ks(j.k) + 1));
+        }
+        if (static_cast<int>(n) + 1 == sj.lead_jobs) { sj.fast_lead_jobs = sj.lead_jobs; sj.fast_lead_blocks = fblk; }
+        fj.push_back(j);
+      }
+      sj.fast_njobs = static_cast<int>(fj.size());
+      sj.fast_nblocks = fblk;
+      TRY(upload_jobs(fj, &sj.d_fast));
+      unfold_smem_max = std::max(unfold_smem_max, sj.fast_smem);
+    }
   }
+  if (unfold_smem_max > 200 * 1024) return fail("internal: fast unfold tile of %zu bytes", unfold_smem_max);
+  if (unfold_smem_max) CU_TRY(cudaFuncSetAttribute(wn_unfold_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(unfold_smem_max)));
   for (int i = 0; i < vcd_plan::kMaxAux; ++i) CU_TRY(cudaStreamCreateWithFlags(&p->aux[i], cudaStreamNonBlocking));
   CU_TRY(cudaStreamCreateWithFlags(&p->own, cudaStreamNonBlocking));
   CU_TRY(cudaEventCreateWithFlags(&p->hop_in, cudaEventDisableTiming));
@@ -451,7 +526,8 @@ extern "C" void vcd_plan_destroy(vcd_plan* p) {
   cudaFree(p->d_f32); cudaFree(p->d_bf16); cudaFree(p->d_norms); cudaFree(p->d_gscratch);
   cudaFree(p->d_params); cudaFree(p->d_dparams); cudaFree(p->d_norm_jobs);
   cudaFree(p->d_pack_jobs[0]); cudaFree(p->d_pack_jobs[1]);
-  for (auto& s : p->segments) cudaFree(s.d_jobs);
+  for (auto& s : p->segments) { cudaFree(s.d_jobs); cudaFree(s.d_fast); }
+  cudaFree(p->d_fast_pack); cudaFree(p->d_norm_jobs_bf16);
   for (auto& kv : p->graphs) cudaGraphExecDestroy(kv.second);
   for (auto& kv : p->pad_tables) cudaFree(kv.second);
   if (p->own) cudaStreamDestroy(p->own);
@@ -684,13 +760,30 @@ extern "C" int vcd_fold_weights(vcd_plan* p, int mode, const float* const* param
   }
   PhaseScope ph__("fold", stream);
   ProfScope ps__(PC_FOLD, 0, 4.0 * p->n_f32, stream);
-  if (p->n_norm_blocks) {
-    wn_norm_kernel<<<p->n_norm_blocks, 128, 0, stream>>>(p->d_norm_jobs, p->n_norm_jobs, p->d_params, p->d_norms);
+  // the float4 row loads of the fast kernel need 16-byte aligned parameter tensors (true for separately allocated
+  // tensors; a parameter that is a view into a flat buffer may not be): fall back to the generic tables otherwise
+  bool fast = mode == VCD_MODE_BF16 && p->n_fast_pack_blocks > 0;
+  for (size_t i = 0; fast && i < np; ++i)
+    if (reinterpret_cast<uintptr_t>(params[i]) & 15) fast = false;
+  if (mode == VCD_MODE_BF16 && p->n_fast_pack_blocks > 0 && !fast)
+    return fail("vcd_fold_weights: parameter tensors must be 16-byte aligned");
+  const bool bf = mode == VCD_MODE_BF16;
+  const int nblk = bf ? p->n_norm_blocks_bf16 : p->n_norm_blocks;
+  if (nblk) {
+    wn_norm_kernel<<<nblk, 128, 0, stream>>>(bf ? p->d_norm_jobs_bf16 : p->d_norm_jobs, bf ? p->n_norm_jobs_bf16 : p->n_norm_jobs,
+                                             p->d_params, p->d_norms);
     LAUNCH_CHECK("wn_norm_kernel");
   }
-  wn_pack_kernel<<<p->n_pack_blocks[mode], 256, 0, stream>>>(p->d_pack_jobs[mode], p->n_pack_jobs[mode],
-                                                              p->d_params, p->d_norms, p->d_f32, p->d_bf16);
-  LAUNCH_CHECK("wn_pack_kernel");
+  if (fast) {
+    wn_pack_fast_kernel<<<p->n_fast_pack_blocks, 256, p->fast_pack_smem, stream>>>(p->d_fast_pack, p->n_fast_pack_jobs, p->d_params,
+                                                                                  p->d_norms, p->d_bf16);
+    LAUNCH_CHECK("wn_pack_fast_kernel");
+  }
+  if (p->n_pack_blocks[mode]) {
+    wn_pack_kernel<<<p->n_pack_blocks[mode], 256, 0, stream>>>(p->d_pack_jobs[mode], p->n_pack_jobs[mode],
+                                                                p->d_params, p->d_norms, p->d_f32, p->d_bf16);
+    LAUNCH_CHECK("wn_pack_kernel");
+  }
   p->folded[mode] = true;
   p->folded[1 - mode] = false;   // the fp32 arena is shared between the modes (bf16 mode stores bf16-rounded values in it)
   return 0;
@@ -1005,8 +1098,8 @@ extern "C" int vcd_forward(vcd_plan* p, int mode, const float* x, int64_t xs_b, 
   Lcur = T * p->hop;  // `core` is skipped on a graph replay: do not rely on its side effects
   {  // conv_post + tanh
     const int C = p->stages[S - 1].cout;
-    dim3 grid((Lcur + 255) / 256, B);
-    const size_t smem = sizeof(float) * C * 7;
+    dim3 grid((Lcur + kPostOut - 1) / kPostOut, B);
+    const size_t smem = sizeof(float) * C * 8;
     ProfScope ps__(PC_POST, 2.0 * C * 7 * B * Lcur, static_cast<double>(B) * Lcur * (C * esize(mode) + 4), stream);
     if (f32) conv_post_fwd_kernel<float><<<grid, 256, smem, stream>>>(static_cast<const float*>(P(w.a[S])), p->h_params[p->p_post_w], y, C, Lcur);
     else conv_post_fwd_kernel<bf16><<<grid, 256, smem, stream>>>(static_cast<const bf16*>(P(w.a[S])), p->h_params[p->p_post_w], y, C, Lcur);
@@ -1099,8 +1192,13 @@ extern "C" int vcd_backward(vcd_plan* p, int mode, const float* dy, const float*
                                                               nullptr, static_cast<bf16*>(P(w.Gi[slot])), C, L);
       }
       LAUNCH_CHECK("conv_post_dgrad_kernel");
-      if (sj.lead_blocks > 0) {
-        wn_unfold_kernel<<<sj.lead_blocks, 256, 0, wst>>>(sj.d_jobs, sj.lead_jobs, p->d_params, p->d_dparams, p->d_norms, p->d_gscratch, 0);
+      if (sj.fast_nblocks > 0 && sj.fast_lead_blocks > 0) {
+        wn_unfold_fast_kernel<<<sj.fast_lead_blocks, 256, sj.fast_smem, wst>>>(sj.d_fast, sj.fast_lead_jobs, p->d_params, p->d_dparams,
+                                                                              p->d_norms, p->d_gscratch, 0, p->grad_scale);
+        LAUNCH_CHECK("wn_unfold_fast_kernel");
+      } else if (sj.lead_blocks > 0) {
+        wn_unfold_kernel<<<sj.lead_blocks, 256, 0, wst>>>(sj.d_jobs, sj.lead_jobs, p->d_params, p->d_dparams, p->d_norms, p->d_gscratch, 0,
+                                                          p->grad_scale);
         LAUNCH_CHECK("wn_unfold_kernel");
       }
     }
@@ -1213,17 +1311,26 @@ extern "C" int vcd_backward(vcd_plan* p, int mode, const float* dy, const float*
     // join the side streams, then the weight-norm backward of this segment's parameters
     for (int k = 0; k < 4; ++k)
       if (side_used[k]) c.order(c.side(k), stream);
-    if (sj.nblocks > sj.lead_blocks) {  // (the jobs ahead of the first layer ran with conv_post's weight gradient)
-      ProfScope ps__(PC_FOLD, 0, 8.0 * (sj.scratch_end - sj.scratch_begin), stream);
+    if (sj.fast_nblocks > sj.fast_lead_blocks) {  // (the jobs ahead of the first layer ran with conv_post's weight gradient)
+      ProfScope ps__(PC_FOLD, 0, 12.0 * (sj.scratch_end - sj.scratch_begin), stream);   // dWp read + v read + gradient write
+      wn_unfold_fast_kernel<<<sj.fast_nblocks - sj.fast_lead_blocks, 256, sj.fast_smem, stream>>>(
+          sj.d_fast + sj.fast_lead_jobs, sj.fast_njobs - sj.fast_lead_jobs, p->d_params, p->d_dparams, p->d_norms, p->d_gscratch,
+          sj.fast_lead_blocks, p->grad_scale);
+      LAUNCH_CHECK("wn_unfold_fast_kernel");
+    } else if (sj.fast_nblocks == 0 && sj.nblocks > sj.lead_blocks) {
+      ProfScope ps__(PC_FOLD, 0, 12.0 * (sj.scratch_end - sj.scratch_begin), stream);   // dWp read + v read + gradient write
       wn_unfold_kernel<<<sj.nblocks - sj.lead_blocks, 256, 0, stream>>>(sj.d_jobs + sj.lead_jobs, sj.njobs - sj.lead_jobs, p->d_params,
-                                                                       p->d_dparams, p->d_norms, p->d_gscratch, sj.lead_blocks);
+                                                                       p->d_dparams, p->d_norms, p->d_gscratch, sj.lead_blocks, p->grad_scale);
       LAUNCH_CHECK("wn_unfold_kernel");
     }
     return 0;
     };
     {
       PhaseScope ph__(("backward segment " + std::to_string(seg)).c_str(), stream);
-      TRY(run_graphed(p, GraphKey{1 + seg, mode, B, T, 1, gvec ? 1 : 0, dx ? 1 : 0, ws, p->params_version}, stream, core));
+      uint32_t scale_bits;
+      memcpy(&scale_bits, &p->grad_scale, sizeof(scale_bits));   // baked into the captured unfold launch
+      TRY(run_graphed(p, GraphKey{1 + seg, mode, B, T, 1, gvec ? 1 : 0, dx ? 1 : 0, ws, p->params_version ^ (static_cast<uint64_t>(scale_bits) << 32)},
+                      stream, core));
     }
     if (post_forked) c.order(wst, stream);
     if (next_seg >= 0) c.order(zst, stream);
@@ -1238,7 +1345,7 @@ extern "C" int vcd_backward(vcd_plan* p, int mode, const float* dy, const float*
         cond_bwd_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(
             PF(w.dcb), have_g ? p->h_params[p->p_cond_w] : nullptr, gvec, p->h_dparams[L.p_b],
             have_g ? p->h_dparams[p->p_cond_b] : nullptr, have_g ? p->h_dparams[p->p_cond_w] : nullptr,
-            B, C0, std::max(G, 1));
+            B, C0, std::max(G, 1), p->grad_scale);
         LAUNCH_CHECK("cond_bwd_kernel");
         if (have_g && dg) {
           cond_dg_kernel<<<dim3((G + 31) / 32, B), 256, 0, stream>>>(PF(w.dcb), p->h_params[p->p_cond_w], dg, C0, G);
@@ -1355,6 +1462,12 @@ extern "C" int vcd_debug_ws_tensor(const vcd_plan* p, int mode, int B, int T, in
 
 // Debug / test hook: choose, for plans created AFTER this call, which directions of bf16 mode run on the tcgen05
 // kernels (1) or on the FFMA kernels with the same bf16 operands (0); a negative value leaves a flag unchanged.
+extern "C" int vcd_set_gradient_scale(vcd_plan* p, float scale) {
+  if (!p) return fail("vcd_set_gradient_scale: null plan");
+  p->grad_scale = scale;
+  return 0;
+}
+
 extern "C" int vcd_debug_tc_paths(int fwd, int dgrad, int wgrad) {
   int* f = tc_path_flags();
   if (fwd >= 0) f[0] = fwd != 0;

@@ -17,8 +17,12 @@ import torch.distributed as dist
 class SegmentReducer:
     """Issues one asynchronous all-reduce per finished gradient segment; ``finish()`` waits and averages."""
 
-    def __init__(self, flat: torch.Tensor, ranges: Sequence[Tuple[int, int]], group: Optional[dist.ProcessGroup]):
+    def __init__(self, flat: torch.Tensor, ranges: Sequence[Tuple[int, int]], group: Optional[dist.ProcessGroup],
+                 prescaled: bool = False):
+        """``prescaled``: the gradients were already multiplied by 1/world where they were produced
+        (``vcd_set_gradient_scale``), so the SUM all-reduce is the average and ``finish`` only waits."""
         self.flat = flat
+        self.prescaled = prescaled
         self.ranges = list(ranges)
         self.group = group
         self.world = dist.get_world_size(group) if group is not None else 1
@@ -42,4 +46,5 @@ class SegmentReducer:
         for w in self.works:
             w.wait()
         self.works = []
-        self.flat.mul_(1.0 / self.world)
+        if not self.prescaled:
+            self.flat.mul_(1.0 / self.world)

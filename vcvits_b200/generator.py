@@ -19,6 +19,7 @@ import warnings
 from typing import List, Optional, Sequence
 
 import torch
+import torch.distributed as dist
 from torch import nn
 
 from . import _lib
@@ -170,10 +171,13 @@ class _DecoderFunction(torch.autograd.Function):
                                         dg.data_ptr() if dg is not None else None,
                                         ptrs, ctx.ws.data_ptr(), ctx.ws_bytes, B, T, mask, stream), "vcd_backward")
 
-        if module._grad_sync_group is None:
+        world = dist.get_world_size(module._grad_sync_group) if module._grad_sync_group is not None else 1
+        # 1/world is applied where the gradients are written (weight-norm backward), so the all-reduce is a plain SUM
+        _lib.check(lib.vcd_set_gradient_scale(plan, 1.0 / world), "vcd_set_gradient_scale")
+        if module._grad_sync_group is None or world == 1:
             run(0xFFFFFFFF)
         else:
-            reducer = SegmentReducer(flat, module._segment_ranges, module._grad_sync_group)
+            reducer = SegmentReducer(flat, module._segment_ranges, module._grad_sync_group, prescaled=True)
             for seg in range(module._num_segments):
                 run(1 << seg)
                 # gradients of this segment are final: all-reduce them on NCCL's stream while the next segment's
