@@ -116,6 +116,22 @@ int vcd_backward(vcd_plan* plan, int mode, const float* dy_dev, const float* y_d
                  float* dx_dev, float* dg_dev, float* const* dparams_dev_ptrs, void* ws_dev, size_t ws_bytes,
                  int B, int T, uint32_t segment_mask, void* stream);
 
+/* the training-time segment gather in front of the decoder,
+ *     z_slice, ids = commons.rand_slice_segments(z, lengths, segment_size)   (vits/commons.py:48-64; call sites
+ *     synthesizer_tts.py:138, synthesizer_svc.py:86)
+ * folded into the decoder's input load: `z_dev` is the FULL-length latent [B, initial_channel, T_full] (element
+ * strides as for vcd_forward), `starts_dev` a device array of B int64 first frames (ids_slice), T the segment length.
+ * Equivalent to vcd_forward on slice_segments(z, starts, T) without materialising the slice.  vcd_backward_sliced
+ * returns the gradient w.r.t. the full-length latent ([B, initial_channel, T_full] contiguous: zero outside each
+ * item's segment -- the scatter-add that autograd derives from the per-item copies of slice_segments). */
+int vcd_forward_sliced(vcd_plan* plan, int mode, const float* z_dev, int64_t zs_b, int64_t zs_c, int64_t zs_t,
+                       const int64_t* starts_dev, const float* g_dev, float* y_dev, void* ws_dev, size_t ws_bytes, int B,
+                       int T, int save_for_backward, void* stream);
+int vcd_backward_sliced(vcd_plan* plan, int mode, const float* dy_dev, const float* y_dev, const float* g_dev,
+                        float* dz_dev, int64_t T_full, const int64_t* starts_dev, float* dg_dev,
+                        float* const* dparams_dev_ptrs, void* ws_dev, size_t ws_bytes, int B, int T, uint32_t segment_mask,
+                        void* stream);
+
 /* Data-parallel training: every PARAMETER gradient written by vcd_backward is multiplied by `scale` (not dx / dg).
  * With scale = 1 / world_size a plain SUM all-reduce of the gradient buffers yields the DDP average
  * (train.py:99-100) without a separate scaling pass.  Default 1. */

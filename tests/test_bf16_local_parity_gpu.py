@@ -10,8 +10,9 @@ stored operands (teacher forcing, oracle/bf16_emulation.py).  One comparison = o
 fused epilogue, forward or data gradient); the 233 parameter gradients, dz and dg are then compared with what
 autograd derives from those stored operands (= every weight-gradient launch + the weight-norm backward).
 
-Tolerances: stored tensors rel-L2 <= 2e-3 and max-abs <= one bf16 ulp of the tensor's absmax; parameter gradients
-rel-L2 <= 2e-3 per tensor (the measured values are printed; they sit one to two orders below).
+Tolerances: stored tensors rel-L2 <= 1e-3 and max-abs <= one bf16 ulp of the tensor's absmax; parameter gradients
+rel-L2 <= 5e-4 per tensor.  Measured on B200 (round 2): stored tensors <= 2.5e-4 (a few flipped roundings out of millions
+of elements), gradients <= 7e-6 (configs[1]), <= 2.5e-5 (configs[2]), <= 2.1e-5 (2 x 938 frames).
 """
 import pytest
 import torch
@@ -22,8 +23,8 @@ from tests.helpers import b200_step_with_stored, rel_l2
 
 pytestmark = pytest.mark.gpu
 
-STORED_REL = 2e-3
-GRAD_REL = 2e-3
+STORED_REL = 1e-3
+GRAD_REL = 5e-4
 
 
 def _local_parity(cfg, B, T, dtype, seed, gain=1.2, expect_tc=True):

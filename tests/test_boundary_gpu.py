@@ -167,3 +167,28 @@ def test_gradient_sync_equals_single_process_full_batch():
             assert rel_l2(out[r][n], full[n]) <= 1e-5, (r, n)
     for n in full:
         assert torch.equal(out[0][n], out[1][n]), n
+
+
+def test_sliced_forward_equals_slice_segments_then_decode():
+    """rand_slice_segments' gather folded into the decoder input load (commons.py:48-64).  Same
+    waveform bit for bit, same parameter gradients, and dz = the scatter autograd derives from slice_segments."""
+    from oracle import synth_parts as S
+    m, _ = _small("fp32")
+    torch.manual_seed(2)
+    z = torch.randn(3, 64, 50, device="cuda", requires_grad=True)
+    g = torch.randn(3, 16, 1, device="cuda")
+    ids = torch.tensor([0, 17, 38], device="cuda")
+    dy = torch.randn(3, 1, 12 * 16, device="cuda")
+    y_ref = m(S.slice_segments(z, ids, 12), g)
+    y_ref.backward(dy)
+    dz_ref, grads_ref = z.grad.clone(), [p.grad.clone() for p in m.parameters()]
+    z.grad = None
+    m.zero_grad(set_to_none=True)
+    y = m.forward_sliced(z, ids, 12, g)
+    assert torch.equal(y, y_ref)
+    y.backward(dy)
+    assert z.grad.shape == z.shape and torch.equal(z.grad, dz_ref)
+    for p, r in zip(m.parameters(), grads_ref):      # split partials combine with fp32 atomics: equal up to summation order
+        assert rel_l2(p.grad.cpu(), r.cpu()) <= 1e-5
+    with pytest.raises(ValueError):
+        m.forward_sliced(z, ids[:2], 12, g)

@@ -93,6 +93,11 @@ _SIGNATURES = {
                               C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "vcd_backward": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                _FLOATPP, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_uint32, C.c_void_p]),
+    "vcd_forward_sliced": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p,
+                                     C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "vcd_backward_sliced": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                                      C.c_void_p, C.c_void_p, _FLOATPP, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_uint32,
+                                      C.c_void_p]),
     "vcd_set_gradient_scale": (C.c_int, [C.c_void_p, C.c_float]),
     "vcd_num_backward_segments": (C.c_int, [C.c_void_p]),
     "vcd_segment_params": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.c_int]),

@@ -229,30 +229,36 @@ pad_zero_kernel(const PadJob* __restrict__ jobs, int njobs, char* __restrict__ w
 // -------------------------------------------------------------------------------------------------
 // Boundary layout changes.
 // -------------------------------------------------------------------------------------------------
-// x: fp32 [B, C, L] with element strides -> blocked T.  grid = (ceil(L/128), C/8, B), block = 128.
+// x: fp32 [B, C, *] with element strides -> blocked T of length L.  grid = (ceil(L/128), C/8, B), block = 128.
+// `starts` (optional, device): per-item first frame -- the segment gather of commons.slice_segments /
+// rand_slice_segments (vits/commons.py:48-64) folded into the decoder's input load.
 template <typename T>
 __global__ void __launch_bounds__(128)
 ncl_to_blocked_kernel(const float* __restrict__ x, long long sb, long long sc, long long st,
-                      T* __restrict__ out, int C, int L) {
+                      T* __restrict__ out, int C, int L, const long long* __restrict__ starts) {
   const int t = blockIdx.x * 128 + threadIdx.x;
   if (t >= L) return;
   const int cg = blockIdx.y, b = blockIdx.z;
+  const long long t_src = t + (starts ? starts[b] : 0);
   float v[8];
 #pragma unroll
-  for (int n = 0; n < 8; ++n) v[n] = __ldg(x + b * sb + (cg * 8 + n) * sc + t * st);
+  for (int n = 0; n < 8; ++n) v[n] = __ldg(x + b * sb + (cg * 8 + n) * sc + t_src * st);
   store8<T>(out + blk_off(b, cg * 8, t, C, L), v);
 }
 
-// blocked fp32 -> contiguous fp32 [B, C, L].
+// blocked fp32 of length L -> contiguous fp32 [B, C, Lfull] at frame offset starts[b] (the scatter that is the backward
+// of the segment gather; the caller zero-fills `out` when Lfull > L).
 __global__ void __launch_bounds__(128)
-blocked_to_ncl_kernel(const float* __restrict__ in, float* __restrict__ out, int C, int L) {
+blocked_to_ncl_kernel(const float* __restrict__ in, float* __restrict__ out, int C, int L, long long Lfull,
+                      const long long* __restrict__ starts) {
   const int t = blockIdx.x * 128 + threadIdx.x;
   if (t >= L) return;
   const int cg = blockIdx.y, b = blockIdx.z;
+  const long long t_dst = t + (starts ? starts[b] : 0);
   float v[8];
   load8<float>(in + blk_off(b, cg * 8, t, C, L), v);
 #pragma unroll
-  for (int n = 0; n < 8; ++n) out[(static_cast<size_t>(b) * C + cg * 8 + n) * L + t] = v[n];
+  for (int n = 0; n < 8; ++n) out[(static_cast<size_t>(b) * C + cg * 8 + n) * Lfull + t_dst] = v[n];
 }
 
 // -------------------------------------------------------------------------------------------------

@@ -94,9 +94,9 @@ inline bool tc_make_rows_map(CUtensorMap* map, const void* base, int B, int C, i
 
 // Epilogue-specialised instantiations of the convolution kernel.  P == nullptr: only raise the dynamic shared
 // memory limit of instantiation `f` (plan creation); otherwise launch it.
-template <int F>
+template <int F, int UW = 16>
 inline cudaError_t tc_conv_launch_one(const tc::ConvParams* P, int grid, size_t smem, cudaStream_t stream, bool pdl) {
-  if (!P) return cudaFuncSetAttribute(tc::conv_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (!P) return cudaFuncSetAttribute(tc::conv_kernel<F, UW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   // programmatic dependent launch: the prologue (barrier init, TMEM allocation, weight loads) overlaps the tail of the
   // previous kernel of the stream; the kernel's activation / epilogue-operand readers call griddepcontrol.wait
   cudaLaunchConfig_t cfg{};
@@ -109,10 +109,16 @@ inline cudaError_t tc_conv_launch_one(const tc::ConvParams* P, int grid, size_t 
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, tc::conv_kernel<F>, *P);
+  return cudaLaunchKernelEx(&cfg, tc::conv_kernel<F, UW>, *P);
 }
+// f: epilogue feature set (tc::EPI_*); bit 5 (32) selects the 32-column epilogue units
+constexpr int kUw32 = 32;
 inline cudaError_t tc_conv_dispatch(int f, const tc::ConvParams* P, int grid, size_t smem, cudaStream_t stream, bool pdl) {
   switch (f) {
+    case kUw32 | 0: return tc_conv_launch_one<0, 32>(P, grid, smem, stream, pdl);
+    case kUw32 | 17: return tc_conv_launch_one<17, 32>(P, grid, smem, stream, pdl);
+    case kUw32 | 18: return tc_conv_launch_one<18, 32>(P, grid, smem, stream, pdl);
+    case kUw32 | 19: return tc_conv_launch_one<19, 32>(P, grid, smem, stream, pdl);
     case 0: return tc_conv_launch_one<0>(P, grid, smem, stream, pdl);
     case 1: return tc_conv_launch_one<1>(P, grid, smem, stream, pdl);
     case 2: return tc_conv_launch_one<2>(P, grid, smem, stream, pdl);
@@ -133,7 +139,7 @@ inline cudaError_t tc_conv_dispatch(int f, const tc::ConvParams* P, int grid, si
 
 inline int tc_plan_init(vcd_plan* p) {
   cudaError_t e = cudaSuccess;
-  for (int f = 0; f < 32 && e == cudaSuccess; ++f) e = tc_conv_dispatch(f, nullptr, 0, 0, 0, false);
+  for (int f = 0; f < 64 && e == cudaSuccess; ++f) e = tc_conv_dispatch(f, nullptr, 0, 0, 0, false);
   if (e != cudaSuccess) return 1;
   e = cudaFuncSetAttribute(tc::wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   if (e != cudaSuccess) return 1;
@@ -183,8 +189,9 @@ inline int tc_run_conv(vcd_plan* p, const Layer& L, bool dgrad, const void* in, 
     if (total < best) { best = total; MT = cand; bufs = cb; }
   }
   {
-    static const int force_mt = tc_env_int("VCD_CONV_MT", 0);
-    if (force_mt > 0 && force_mt * P.BN <= 512 && force_mt <= mtiles) { MT = force_mt; bufs = 2 * MT * P.BN <= 512 ? 2 : 1; }
+    static const int force_mt = tc_env_int("VCD_CONV_MT", 0), force_mt_small = tc_env_int("VCD_CONV_MT_SMALL", 0);
+    const int fm = can_reside && force_mt_small > 0 ? force_mt_small : force_mt;
+    if (fm > 0 && fm * P.BN <= 512 && fm <= mtiles) { MT = fm; bufs = 2 * MT * P.BN <= 512 ? 2 : 1; }
   }
   // epilogue feature set -> instantiation (a superset is always valid: unused operands are null-checked or zero)
   int f = (e.mask ? tc::EPI_MASK : 0) | (e.res_t ? tc::EPI_RES : 0) | (e.res2 ? tc::EPI_RES2 : 0) | (e.out_raw ? tc::EPI_RAW : 0);
@@ -249,7 +256,7 @@ inline int tc_run_conv(vcd_plan* p, const Layer& L, bool dgrad, const void* in, 
       const size_t e_stage = static_cast<size_t>(e_nops) * MT * P.BN * 256;
       int ne = ne_want;
       while (ne >= 2 && used + ne * e_stage > budget) --ne;
-      if (ne >= 2) { P.NE = ne > 4 ? 4 : ne; P.e_ops = e_nops; P.e_stage_bytes = static_cast<uint32_t>(e_stage); used += P.NE * e_stage; }
+      if (ne >= 2) { P.NE = ne > 8 ? 8 : ne; P.e_ops = e_nops; P.e_stage_bytes = static_cast<uint32_t>(e_stage); used += P.NE * e_stage; }
     }
     while (P.NA < na_small && used + a_stage <= budget && (P.NA + 1) * a_stage <= 96 * 1024) { ++P.NA; used += a_stage; }
   } else {
@@ -274,8 +281,12 @@ inline int tc_run_conv(vcd_plan* p, const Layer& L, bool dgrad, const void* in, 
   }
   break;
   }
-  const size_t smem = 128 + P.NA * a_stage + w_region + static_cast<size_t>(P.NE) * P.e_stage_bytes + (2 * P.NA + 16 + 4 + 8) * 8 + 16 + 2 * 128 * 4;
+  const size_t smem = 128 + P.NA * a_stage + w_region + static_cast<size_t>(P.NE) * P.e_stage_bytes + (2 * P.NA + 16 + 4 + 16) * 8 + 16 + 2 * 128 * 4;
   if (P.NE > 0) f |= tc::EPI_SMEM;
+  // 32-column epilogue units: resident-weight (<= 64-channel) layers whose epilogue has no global operands; both warps
+  // of a TMEM lane quadrant need at least one unit per tile
+  static const int uw32_on = tc_env_int("VCD_CONV_UW32", 1);
+  const bool uw32 = uw32_on && P.w_resident && (f == 0 || f == 17 || f == 18 || f == 19) && P.BN % 32 == 0 && MT * P.BN >= 64;
   if (smem > 227 * 1024) {
     snprintf(err, errn, "tc_run_conv(%s): shared memory budget exceeded (%zu bytes)", L.name.c_str(), smem);
     return 1;
@@ -309,7 +320,7 @@ inline int tc_run_conv(vcd_plan* p, const Layer& L, bool dgrad, const void* in, 
   // only the forward chain uses it by default.
   static const int pdl_mask = tc_env_int("VCD_PDL", 1), pdl_late_mask = tc_env_int("VCD_PDL_LATE", 2);
   P.pdl_late = (pdl_late_mask & (dgrad ? 2 : 1)) != 0 ? 1 : 0;
-  const cudaError_t ce = tc_conv_dispatch(f, &P, grid, smem, stream, (pdl_mask & (dgrad ? 2 : 1)) != 0);
+  const cudaError_t ce = tc_conv_dispatch(f | (uw32 ? kUw32 : 0), &P, grid, smem, stream, (pdl_mask & (dgrad ? 2 : 1)) != 0);
   launches.fetch_add(1, std::memory_order_relaxed);
   if (ce != cudaSuccess) {
     snprintf(err, errn, "launch of tc::conv_kernel(%s) failed: %s", L.name.c_str(), cudaGetErrorString(ce));

@@ -309,8 +309,13 @@ __device__ __forceinline__ void epi_finish(const Epilogue& e, const ConvGeo& g, 
   if constexpr (F & EPI_RES) {
     float t[8];
     unpack8(L.rest, t);
+    if (e.res_inv == 1.f) {   // backward: the identity path of `x = xt + x` adds the gradient as is
 #pragma unroll
-    for (int n = 0; n < 8; ++n) v[n] += (t[n] > 0.f ? t[n] : t[n] * e.res_inv);
+      for (int n = 0; n < 8; ++n) v[n] += t[n];
+    } else {                  // forward: residual stream recovered from the stored leaky_relu(x)
+#pragma unroll
+      for (int n = 0; n < 8; ++n) v[n] += (t[n] > 0.f ? t[n] : t[n] * e.res_inv);
+    }
   }
   if constexpr (F & EPI_RES2) {
     v[0] += L.r2a.x; v[1] += L.r2a.y; v[2] += L.r2a.z; v[3] += L.r2a.w;
@@ -322,9 +327,9 @@ __device__ __forceinline__ void epi_finish(const Epilogue& e, const ConvGeo& g, 
   if (e.out_t) {
     if (!plain_out) {
 #pragma unroll
-      for (int n = 0; n < 8; ++n) {
+      for (int n = 0; n < 8; ++n) {   // leaky_relu with 0 < slope <= 1 is max(x, slope * x)
         const float x = v[n] * e.tscale;
-        v[n] = x > 0.f ? x : x * e.act_slope;
+        v[n] = fmaxf(x, x * e.act_slope);
       }
     }
     if (e.zu > 0) {
@@ -336,7 +341,11 @@ __device__ __forceinline__ void epi_finish(const Epilogue& e, const ConvGeo& g, 
   }
 }
 
-template <int F>
+// UW: accumulator columns an epilogue warp handles per step (16 | 32).  The epilogue of the <= 64-channel layers is bound
+// by instruction issue; one 32-column TMEM load per step halves the per-step bookkeeping (tile / unit decode, barrier
+// checks, pipeline state).  UW = 32 is only instantiated for the variants without global epilogue operands (none, or all
+// staged in shared memory) -- the register prefetch buffers of the other variants would double.
+template <int F, int UW = 16>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_kernel(const ConvParams P) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -363,15 +372,15 @@ conv_kernel(const ConvParams P) {
   uint64_t* acc_full = emptyW + 8;
   uint64_t* acc_empty = acc_full + 2;
   uint64_t* fullE = acc_empty + 2;
-  uint64_t* emptyE = fullE + 4;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(emptyE + 4);
+  uint64_t* emptyE = fullE + 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(emptyE + 8);
   float* bias_s = reinterpret_cast<float*>(tmem_slot + 4);   // [2][128]: per-tile bias (+ per-batch bias), double-buffered
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < P.NA; ++i) { mbar_init(&fullA[i], 1); mbar_init(&emptyA[i], 1); }
     for (int i = 0; i < 8; ++i) { mbar_init(&fullW[i], 1); mbar_init(&emptyW[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 8); }
-    for (int i = 0; i < 4; ++i) { mbar_init(&fullE[i], 1); mbar_init(&emptyE[i], 8); }
+    for (int i = 0; i < 8; ++i) { mbar_init(&fullE[i], 1); mbar_init(&emptyE[i], 8); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, P.tmem_cols);
@@ -602,7 +611,11 @@ conv_kernel(const ConvParams P) {
     const int half = (warp - 2) >> 2;        // two warps per quadrant interleave over 16-column units
     const int row_in_tile = quad * 32 + lane;
     const Epilogue& e = P.e;
-    const int units_per_mt = P.BN / 16;
+    static_assert(UW == 16 || UW == 32, "unit width");
+    static_assert(UW == 16 || F == 0 || ((F & EPI_SMEM) && !(F & (EPI_RES2 | EPI_RAW))), "UW = 32 needs operand-free or smem-staged epilogues");
+    constexpr int NG = UW / 8;                                   // 8-channel groups per unit
+    const int ushift = P.units_shift - (UW == 32 ? 1 : 0);      // log2(BN / UW)
+    const int units_per_mt = P.BN / UW;
     const int n_units = P.MT * units_per_mt;
     const uint32_t chunk_stride = static_cast<uint32_t>(padded_len(P.Lout)) * 8;  // next 8-channel group, same row (elements)
     const uint32_t b_stride = static_cast<uint32_t>(P.g.creal >> 3) * chunk_stride;   // next batch item
@@ -625,14 +638,14 @@ conv_kernel(const ConvParams P) {
     struct UnitC { int ro, ch; bool valid; uint32_t o; uint32_t taddr; };
     auto unit_coords = [&](const TileC& t, int u) {
       UnitC c;
-      const int mt = u >> P.units_shift, c16 = u - (mt << P.units_shift);
+      const int mt = u >> ushift, cu = u - (mt << ushift);
       const int q = t.q_first + mt * 128;
       c.ro = q * P.g.os + t.r_phase - P.g.p;
       c.valid = q < P.Lq && c.ro >= 0 && c.ro < P.Lout;
-      c.ch = t.ch_tile + c16 * 16;
+      c.ch = t.ch_tile + cu * UW;
       c.o = static_cast<uint32_t>(t.b) * b_stride + static_cast<uint32_t>(c.ch >> 3) * chunk_stride +
             static_cast<uint32_t>((c.valid ? c.ro : 0) + kPadL) * 8u;
-      c.taddr = t.t_lane + static_cast<uint32_t>(mt * P.BN + c16 * 16);
+      c.taddr = t.t_lane + static_cast<uint32_t>(mt * P.BN + cu * UW);
       return c;
     };
 
@@ -642,15 +655,15 @@ conv_kernel(const ConvParams P) {
     // critical path.  The two operand buffers alternate by code duplication (step(A, B); step(B, A)): a register
     // copy `cur = nxt` would wait for the just-issued loads and serialise the pipeline again.
     pdl_wait();   // masks / residuals / running sums may be the stream predecessor's output
-    EpiLoads bufA[2], bufB[2];
+    EpiLoads bufA[NG], bufB[NG];
     UnitC uc{};
     TileC tcur = tile_coords(blockIdx.x, 0);
     int tile = blockIdx.x, it = 0, u = half;
     const int grid = static_cast<int>(gridDim.x);
     if (tile < P.total_tiles) {
       uc = unit_coords(tcur, u);
-      epi_prefetch<F>(e, uc.o, uc.valid, bufA[0]);
-      epi_prefetch<F>(e, uc.o + chunk_stride, uc.valid, bufA[1]);
+#pragma unroll
+      for (int h = 0; h < NG; ++h) epi_prefetch<F>(e, uc.o + h * chunk_stride, uc.valid, bufA[h]);
     }
     const bool has_bias = e.bias != nullptr || e.bias2 != nullptr;
     // one column tile and no per-batch bias: the bias vector is the same for every tile of the launch -- stage it once
@@ -660,7 +673,7 @@ conv_kernel(const ConvParams P) {
       if (et < P.BN) bias_s[et] = __ldg(e.bias + et);
       asm volatile("bar.sync 1, 256;" ::: "memory");
     }
-    auto step = [&](EpiLoads (&use)[2], EpiLoads (&fill)[2]) {
+    auto step = [&](EpiLoads (&use)[NG], EpiLoads (&fill)[NG]) {
       const int buf = P.acc_bufs == 2 ? (it & 1) : 0;
       const int use_n = P.acc_bufs == 2 ? (it >> 1) : it;
       const bool first = u == half;                      // first unit of this warp in the tile
@@ -681,8 +694,8 @@ conv_kernel(const ConvParams P) {
       if (n_tile < P.total_tiles) {
         if (last) tnext = tile_coords(n_tile, n_it);
         un = unit_coords(tnext, n_u);
-        epi_prefetch<F>(e, un.o, un.valid, fill[0]);
-        epi_prefetch<F>(e, un.o + chunk_stride, un.valid, fill[1]);
+#pragma unroll
+        for (int h = 0; h < NG; ++h) epi_prefetch<F>(e, un.o + h * chunk_stride, un.valid, fill[h]);
       }
       int e_stage = 0;
       if constexpr (F & EPI_SMEM) {
@@ -694,17 +707,18 @@ conv_kernel(const ConvParams P) {
         tc_fence_after();
         if (warp == 2 && lane == 0 && it < 4) ktrace(P.trace, 12 + it);   // accumulators of tile `it` complete
       }
-      float acc[16];
-      tmem_ld16(uc.taddr, acc);
+      float acc[UW];
+      if constexpr (UW == 16) tmem_ld16(uc.taddr, acc);
+      else tmem_ld32(uc.taddr, acc);
       if (uc.valid) {
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
+        for (int h = 0; h < NG; ++h) {
           float v[8];
 #pragma unroll
           for (int n = 0; n < 8; ++n) v[n] = acc[h * 8 + n];
           if constexpr (F & EPI_SMEM) {   // this row's 16 bytes of each staged operand: [op][mt][channel group][128 rows][16 B]
-            const int mt = u >> P.units_shift;
-            const int cg = ((u - (mt << P.units_shift)) << 1) + h;
+            const int mt = u >> ushift;
+            const int cg = (u - (mt << ushift)) * NG + h;
             const int groups = P.BN >> 3;
             const uint8_t* ep = e_smem + static_cast<size_t>(e_stage) * P.e_stage_bytes +
                                 (static_cast<size_t>(mt * groups + cg) * 128 + row_in_tile) * 16;

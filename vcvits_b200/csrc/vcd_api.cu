@@ -363,7 +363,8 @@ extern "C" int vcd_plan_create(const vcd_config* cfg, vcd_plan** out_plan) {
   static const int fast_fold = tc_env_int("VCD_FAST_FOLD", 1);
   auto fast_shape = [&](const Layer& L) {
     const ParamInfo& pv = p->params[L.p_w];
-    return fast_fold && L.k % L.u == 0 && pv.shape[0] % 8 == 0 && pv.shape[1] % 8 == 0 && (pv.numel / pv.shape[0]) % 4 == 0;
+    return fast_fold && L.k % L.u == 0 && pv.shape[0] % 8 == 0 && pv.shape[1] % 8 == 0 && (pv.numel / pv.shape[0]) % 4 == 0 &&
+           fold_kshift(L.k) >= 0 && ((L.k & 1) || L.k % 4 == 0);
   };
   auto fast_pack_ok = [&](const Layer& L) { return fast_shape(L) && L.tc_ok_fwd && L.tc_ok_dgr; };
   for (int bf = 0; bf < 2; ++bf) {
@@ -396,6 +397,7 @@ extern "C" int vcd_plan_create(const vcd_config* cfg, vcd_plan** out_plan) {
       j.p_w = L.p_w; j.p_g = L.p_g; j.norm_off = L.wn ? L.norm_off : 0;
       j.rows = static_cast<int>(pv.shape[0]); j.inner = static_cast<int>(pv.shape[1]); j.k = L.k; j.u = L.u;
       j.is_convt = L.kind == LK_CONVT ? 1 : 0;
+      j.kshift = fold_kshift(L.k);
       // format R = "row is the GEMM column": Conv1d forward / ConvTranspose1d data gradient
       j.nt_r = j.is_convt ? L.nt_dgr : L.nt_fwd;
       j.nt_c = j.is_convt ? L.nt_fwd : L.nt_dgr;
@@ -403,7 +405,7 @@ extern "C" int vcd_plan_create(const vcd_config* cfg, vcd_plan** out_plan) {
       j.dst_c = j.is_convt ? L.tc_fwd : L.tc_dgr;
       j.first_block = blk;
       blk += j.rows / kFoldRows;
-      p->fast_pack_smem = std::max(p->fast_pack_smem, sizeof(float) * kFoldRows * (static_cast<size_t>(j.inner) * fold_ks(j.k) + 1));
+      p->fast_pack_smem = std::max(p->fast_pack_smem, sizeof(float) * kFoldRows * static_cast<size_t>(fold_srow(j.inner, j.k)));
       fj.push_back(j);
     }
     p->n_fast_pack_jobs = static_cast<int>(fj.size());
@@ -490,15 +492,16 @@ extern "C" int vcd_plan_create(const vcd_config* cfg, vcd_plan** out_plan) {
         j.kind = o.kind; j.p_w = o.p_w; j.p_g = o.p_g; j.norm_off = o.norm_off; j.src_off = o.src_off; j.numel = o.numel;
         j.first_block = fblk;
         if (o.kind == 1) {
-          fblk += static_cast<int>((o.numel + 1023) / 1024);
+          fblk += static_cast<int>((o.numel + 2047) / 2048);
         } else {
           const ParamInfo& pv = p->params[o.p_w];
           j.rows = o.rows; j.inner = static_cast<int>(pv.shape[1]); j.k = o.map.k;
           j.is_convt = o.map.src == SRC_CONVT_FWD ? 1 : 0;
           j.u = j.is_convt ? o.map.u : 1;
+          j.kshift = fold_kshift(j.k);
           j.K = o.K; j.N = o.N;
           fblk += j.rows / kFoldRows;
-          sj.fast_smem = std::max(sj.fast_smem, sizeof(float) * kFoldRows * (static_cast<size_t>(j.inner) * fold_ks(j.k) + 1));
+          sj.fast_smem = std::max(sj.fast_smem, sizeof(float) * kFoldRows * static_cast<size_t>(fold_srow(j.inner, j.k)));
         }
         if (static_cast<int>(n) + 1 == sj.lead_jobs) { sj.fast_lead_jobs = sj.lead_jobs; sj.fast_lead_blocks = fblk; }
         fj.push_back(j);
@@ -775,7 +778,7 @@ extern "C" int vcd_fold_weights(vcd_plan* p, int mode, const float* const* param
     LAUNCH_CHECK("wn_norm_kernel");
   }
   if (fast) {
-    wn_pack_fast_kernel<<<p->n_fast_pack_blocks, 256, p->fast_pack_smem, stream>>>(p->d_fast_pack, p->n_fast_pack_jobs, p->d_params,
+    wn_pack_fast_kernel<<<p->n_fast_pack_blocks, kFoldThreads, p->fast_pack_smem, stream>>>(p->d_fast_pack, p->n_fast_pack_jobs, p->d_params,
                                                                                   p->d_norms, p->d_bf16);
     LAUNCH_CHECK("wn_pack_fast_kernel");
   }
@@ -985,9 +988,26 @@ constexpr float kFinalSlope = 0.01f;    // F.leaky_relu default before conv_post
 // ---------------------------------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------------------------------
+static int forward_impl(vcd_plan* p, int mode, const float* x, int64_t xs_b, int64_t xs_c, int64_t xs_t,
+                        const int64_t* starts, const float* gvec, float* y, void* ws, size_t ws_bytes, int B, int T, int save_,
+                        void* stream_);
+
 extern "C" int vcd_forward(vcd_plan* p, int mode, const float* x, int64_t xs_b, int64_t xs_c, int64_t xs_t,
                            const float* gvec, float* y, void* ws, size_t ws_bytes, int B, int T, int save_,
                            void* stream_) {
+  return forward_impl(p, mode, x, xs_b, xs_c, xs_t, nullptr, gvec, y, ws, ws_bytes, B, T, save_, stream_);
+}
+
+extern "C" int vcd_forward_sliced(vcd_plan* p, int mode, const float* z, int64_t zs_b, int64_t zs_c, int64_t zs_t,
+                                  const int64_t* starts_dev, const float* gvec, float* y, void* ws, size_t ws_bytes, int B,
+                                  int T, int save_, void* stream_) {
+  if (!starts_dev) return fail("vcd_forward_sliced: null starts");
+  return forward_impl(p, mode, z, zs_b, zs_c, zs_t, starts_dev, gvec, y, ws, ws_bytes, B, T, save_, stream_);
+}
+
+static int forward_impl(vcd_plan* p, int mode, const float* x, int64_t xs_b, int64_t xs_c, int64_t xs_t,
+                        const int64_t* starts, const float* gvec, float* y, void* ws, size_t ws_bytes, int B, int T, int save_,
+                        void* stream_) {
   const bool save = save_ != 0;
   TRY(check_common(p, mode, B, T, ws, ws_bytes, save));
   if (!x || !y) return fail("vcd_forward: null x or y");
@@ -1007,8 +1027,9 @@ extern "C" int vcd_forward(vcd_plan* p, int mode, const float* x, int64_t xs_b, 
   {  // latent -> blocked layout
     ProfScope ps__(PC_MISC, 0, 0, stream);
     dim3 grid((T + 127) / 128, Cin0 / 8, B);
-    if (f32) ncl_to_blocked_kernel<float><<<grid, 128, 0, stream>>>(x, xs_b, xs_c, xs_t, static_cast<float*>(P(w.xin)), Cin0, T);
-    else ncl_to_blocked_kernel<bf16><<<grid, 128, 0, stream>>>(x, xs_b, xs_c, xs_t, static_cast<bf16*>(P(w.xin)), Cin0, T);
+    const long long* st0 = reinterpret_cast<const long long*>(starts);
+    if (f32) ncl_to_blocked_kernel<float><<<grid, 128, 0, stream>>>(x, xs_b, xs_c, xs_t, static_cast<float*>(P(w.xin)), Cin0, T, st0);
+    else ncl_to_blocked_kernel<bf16><<<grid, 128, 0, stream>>>(x, xs_b, xs_c, xs_t, static_cast<bf16*>(P(w.xin)), Cin0, T, st0);
     LAUNCH_CHECK("ncl_to_blocked_kernel");
   }
   if (gvec) {
@@ -1111,9 +1132,26 @@ extern "C" int vcd_forward(vcd_plan* p, int mode, const float* x, int64_t xs_b, 
 // ---------------------------------------------------------------------------------------------------
 // backward
 // ---------------------------------------------------------------------------------------------------
+static int backward_impl(vcd_plan* p, int mode, const float* dy, const float* y, const float* gvec, float* dx, int64_t T_full,
+                         const int64_t* starts, float* dg, float* const* dparams, void* ws, size_t ws_bytes, int B, int T,
+                         uint32_t segment_mask, void* stream_);
+
 extern "C" int vcd_backward(vcd_plan* p, int mode, const float* dy, const float* y, const float* gvec, float* dx,
                             float* dg, float* const* dparams, void* ws, size_t ws_bytes, int B, int T,
                             uint32_t segment_mask, void* stream_) {
+  return backward_impl(p, mode, dy, y, gvec, dx, T, nullptr, dg, dparams, ws, ws_bytes, B, T, segment_mask, stream_);
+}
+
+extern "C" int vcd_backward_sliced(vcd_plan* p, int mode, const float* dy, const float* y, const float* gvec, float* dz,
+                                   int64_t T_full, const int64_t* starts_dev, float* dg, float* const* dparams, void* ws,
+                                   size_t ws_bytes, int B, int T, uint32_t segment_mask, void* stream_) {
+  if (!starts_dev || T_full < T) return fail("vcd_backward_sliced: null starts or T_full < T");
+  return backward_impl(p, mode, dy, y, gvec, dz, T_full, starts_dev, dg, dparams, ws, ws_bytes, B, T, segment_mask, stream_);
+}
+
+static int backward_impl(vcd_plan* p, int mode, const float* dy, const float* y, const float* gvec, float* dx, int64_t T_full,
+                         const int64_t* starts, float* dg, float* const* dparams, void* ws, size_t ws_bytes, int B, int T,
+                         uint32_t segment_mask, void* stream_) {
   TRY(check_common(p, mode, B, T, ws, ws_bytes, true));
   if (!dy || !y || !dparams) return fail("vcd_backward: null dy, y or dparams");
   const WsLayout w = make_layout(p, mode, B, T, true);
@@ -1193,7 +1231,7 @@ extern "C" int vcd_backward(vcd_plan* p, int mode, const float* dy, const float*
       }
       LAUNCH_CHECK("conv_post_dgrad_kernel");
       if (sj.fast_nblocks > 0 && sj.fast_lead_blocks > 0) {
-        wn_unfold_fast_kernel<<<sj.fast_lead_blocks, 256, sj.fast_smem, wst>>>(sj.d_fast, sj.fast_lead_jobs, p->d_params, p->d_dparams,
+        wn_unfold_fast_kernel<<<sj.fast_lead_blocks, kFoldThreads, sj.fast_smem, wst>>>(sj.d_fast, sj.fast_lead_jobs, p->d_params, p->d_dparams,
                                                                               p->d_norms, p->d_gscratch, 0, p->grad_scale);
         LAUNCH_CHECK("wn_unfold_fast_kernel");
       } else if (sj.lead_blocks > 0) {
@@ -1313,7 +1351,7 @@ extern "C" int vcd_backward(vcd_plan* p, int mode, const float* dy, const float*
       if (side_used[k]) c.order(c.side(k), stream);
     if (sj.fast_nblocks > sj.fast_lead_blocks) {  // (the jobs ahead of the first layer ran with conv_post's weight gradient)
       ProfScope ps__(PC_FOLD, 0, 12.0 * (sj.scratch_end - sj.scratch_begin), stream);   // dWp read + v read + gradient write
-      wn_unfold_fast_kernel<<<sj.fast_nblocks - sj.fast_lead_blocks, 256, sj.fast_smem, stream>>>(
+      wn_unfold_fast_kernel<<<sj.fast_nblocks - sj.fast_lead_blocks, kFoldThreads, sj.fast_smem, stream>>>(
           sj.d_fast + sj.fast_lead_jobs, sj.fast_njobs - sj.fast_lead_jobs, p->d_params, p->d_dparams, p->d_norms, p->d_gscratch,
           sj.fast_lead_blocks, p->grad_scale);
       LAUNCH_CHECK("wn_unfold_fast_kernel");
@@ -1360,7 +1398,9 @@ extern "C" int vcd_backward(vcd_plan* p, int mode, const float* dy, const float*
       if (dx) {
         ProfScope ps__(PC_MISC, 0, 0, stream);
         dim3 grid((T + 127) / 128, Cin0 / 8, B);
-        blocked_to_ncl_kernel<<<grid, 128, 0, stream>>>(PF(w.dxb), dx, Cin0, T);
+        // sliced call: the gradient w.r.t. the full-length latent is zero outside each item's segment
+        if (starts) CU_TRY(cudaMemsetAsync(dx, 0, sizeof(float) * static_cast<size_t>(B) * Cin0 * T_full, stream));
+        blocked_to_ncl_kernel<<<grid, 128, 0, stream>>>(PF(w.dxb), dx, Cin0, T, T_full, reinterpret_cast<const long long*>(starts));
         LAUNCH_CHECK("blocked_to_ncl_kernel");
       }
     }

@@ -102,9 +102,12 @@ class _DecoderFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, module: "Generator", need_grad: bool, x: torch.Tensor, g: Optional[torch.Tensor],
-                *params: torch.Tensor):
+                starts: Optional[torch.Tensor], seg_frames: int, *params: torch.Tensor):
         lib = _lib.load()
         B, _, T = x.shape
+        T_full = T
+        if starts is not None:   # sliced call: x is the full-length latent, the decoder runs on [starts, starts + seg_frames)
+            T = int(seg_frames)
         plan = module._plan_for(x.device)
         mode = module._mode
         module._fold_if_needed(params, force=need_grad)
@@ -116,11 +119,18 @@ class _DecoderFunction(torch.autograd.Function):
         ws_bytes = lib.vcd_workspace_bytes(plan, mode, B, T, 1 if need_grad else 0)
         ws = module._take_workspace(ws_bytes, x.device) if need_grad else module._workspace(ws_bytes, x.device, cache=True)
         y = torch.empty((B, 1, T * module.hop), dtype=torch.float32, device=x.device)
-        _lib.check(lib.vcd_forward(plan, mode, xf.data_ptr(), xf.stride(0), xf.stride(1), xf.stride(2),
-                                   gf.data_ptr() if gf is not None else None, y.data_ptr(), ws.data_ptr(),
-                                   ws_bytes, B, T, 1 if need_grad else 0, stream), "vcd_forward")
+        if starts is None:
+            _lib.check(lib.vcd_forward(plan, mode, xf.data_ptr(), xf.stride(0), xf.stride(1), xf.stride(2),
+                                       gf.data_ptr() if gf is not None else None, y.data_ptr(), ws.data_ptr(),
+                                       ws_bytes, B, T, 1 if need_grad else 0, stream), "vcd_forward")
+        else:
+            _lib.check(lib.vcd_forward_sliced(plan, mode, xf.data_ptr(), xf.stride(0), xf.stride(1), xf.stride(2),
+                                              starts.data_ptr(), gf.data_ptr() if gf is not None else None, y.data_ptr(),
+                                              ws.data_ptr(), ws_bytes, B, T, 1 if need_grad else 0, stream),
+                       "vcd_forward_sliced")
         if need_grad:
             ctx.module = module
+            ctx.starts, ctx.T_full = starts, T_full
             ctx.fold_serial = module._fold_serial
             ctx.ws = ws
             ctx.ws_bytes = ws_bytes
@@ -158,18 +168,27 @@ class _DecoderFunction(torch.autograd.Function):
         stream = torch.cuda.current_stream(dev).cuda_stream
         dy = dy.contiguous().float()
         need_dx, need_dg = ctx.needs_input_grad[2], ctx.has_g and ctx.needs_input_grad[3]
-        dx = torch.empty((B, module.initial_channel, T), dtype=torch.float32, device=dev) if need_dx else None
+        starts, T_full = ctx.starts, ctx.T_full
+        dx = torch.empty((B, module.initial_channel, T_full), dtype=torch.float32, device=dev) if need_dx else None
         dg = torch.empty((B, module.gin_channels), dtype=torch.float32, device=dev) if need_dg else None
         flat = torch.empty(module._flat_numel, dtype=torch.float32, device=dev)
         views = module._grad_views(flat)
         ptrs = (C.c_void_p * len(views))(*[v.data_ptr() if p is not None else None
                                            for v, p in zip(views, module._ordered_params())])
         def run(mask):
-            _lib.check(lib.vcd_backward(plan, module._mode, dy.data_ptr(), y.data_ptr(),
-                                        gf.data_ptr() if gf is not None else None,
-                                        dx.data_ptr() if dx is not None else None,
-                                        dg.data_ptr() if dg is not None else None,
-                                        ptrs, ctx.ws.data_ptr(), ctx.ws_bytes, B, T, mask, stream), "vcd_backward")
+            if starts is None:
+                _lib.check(lib.vcd_backward(plan, module._mode, dy.data_ptr(), y.data_ptr(),
+                                            gf.data_ptr() if gf is not None else None,
+                                            dx.data_ptr() if dx is not None else None,
+                                            dg.data_ptr() if dg is not None else None,
+                                            ptrs, ctx.ws.data_ptr(), ctx.ws_bytes, B, T, mask, stream), "vcd_backward")
+            else:
+                _lib.check(lib.vcd_backward_sliced(plan, module._mode, dy.data_ptr(), y.data_ptr(),
+                                                   gf.data_ptr() if gf is not None else None,
+                                                   dx.data_ptr() if dx is not None else None, T_full, starts.data_ptr(),
+                                                   dg.data_ptr() if dg is not None else None,
+                                                   ptrs, ctx.ws.data_ptr(), ctx.ws_bytes, B, T, mask, stream),
+                           "vcd_backward_sliced")
 
         world = dist.get_world_size(module._grad_sync_group) if module._grad_sync_group is not None else 1
         # 1/world is applied where the gradients are written (weight-norm backward), so the all-reduce is a plain SUM
@@ -189,7 +208,7 @@ class _DecoderFunction(torch.autograd.Function):
         grads = [v if (p is not None and p.requires_grad) else None for v, p in zip(views, module._ordered_params())]
         gx = dx.to(ctx.x_dtype) if dx is not None else None
         gg = dg.reshape(ctx.g_shape).to(ctx.g_dtype) if dg is not None else None
-        return (None, None, gx, gg, *grads)
+        return (None, None, gx, gg, None, None, *grads)
 
 
 class Generator(nn.Module):
@@ -468,7 +487,22 @@ class Generator(nn.Module):
         return out
 
     # ------------------------------------------------------------------ forward
-    def forward(self, x: torch.Tensor, g: Optional[torch.Tensor] = None) -> torch.Tensor:
+    def forward_sliced(self, z: torch.Tensor, ids_str: torch.Tensor, segment_size: int,
+                       g: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """``self(commons.slice_segments(z, ids_str, segment_size), g)`` without materialising the slice: the per-item
+        segment gather of ``rand_slice_segments`` (vits/commons.py:48-64; synthesizer_tts.py:138-140,
+        synthesizer_svc.py:86-87) happens inside the decoder's input load, and backward scatters the latent gradient
+        into a zero-filled full-length tensor.  ``z``: [B, C, T_full]; ``ids_str``: [B] integer start frames."""
+        if ids_str.dim() != 1 or ids_str.shape[0] != z.shape[0]:
+            raise ValueError(f"expected ids_str of shape [{z.shape[0]}], got {tuple(ids_str.shape)}")
+        segment_size = int(segment_size)
+        if segment_size < 1 or segment_size > z.shape[2]:
+            raise ValueError(f"segment_size {segment_size} does not fit a latent of {z.shape[2]} frames")
+        starts = ids_str.to(device=z.device, dtype=torch.int64).contiguous()
+        return self.forward(z, g, _starts=starts, _segment=segment_size)
+
+    def forward(self, x: torch.Tensor, g: Optional[torch.Tensor] = None, *, _starts: Optional[torch.Tensor] = None,
+                _segment: int = 0) -> torch.Tensor:
         if not x.is_cuda:
             raise RuntimeError("vcvits_b200.Generator runs only on CUDA (sm_100a); there is no CPU fallback")
         if x.dim() != 3 or x.shape[1] != self.initial_channel:
@@ -486,7 +520,7 @@ class Generator(nn.Module):
                                                      or any(p is not None and p.requires_grad for p in params))
             # Lightning AMP (train.py:104-106) calls this inside autocast: the decoder computes in its own mode
             with torch.autocast(device_type="cuda", enabled=False):
-                return _DecoderFunction.apply(self, need_grad, x, g, *params)
+                return _DecoderFunction.apply(self, need_grad, x, g, _starts, _segment, *params)
 
     def synthesize_host(self, x_host: torch.Tensor, g_host: Optional[torch.Tensor] = None,
                         device: Optional[torch.device] = None) -> torch.Tensor:
