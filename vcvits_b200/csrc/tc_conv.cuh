@@ -94,9 +94,9 @@ inline bool tc_make_rows_map(CUtensorMap* map, const void* base, int B, int C, i
 
 // Epilogue-specialised instantiations of the convolution kernel.  P == nullptr: only raise the dynamic shared
 // memory limit of instantiation `f` (plan creation); otherwise launch it.
-template <int F, int UW = 16>
+template <int F, int UW = 16, bool LEAN = false>
 inline cudaError_t tc_conv_launch_one(const tc::ConvParams* P, int grid, size_t smem, cudaStream_t stream, bool pdl) {
-  if (!P) return cudaFuncSetAttribute(tc::conv_kernel<F, UW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (!P) return cudaFuncSetAttribute(tc::conv_kernel<F, UW, LEAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   // programmatic dependent launch: the prologue (barrier init, TMEM allocation, weight loads) overlaps the tail of the
   // previous kernel of the stream; the kernel's activation / epilogue-operand readers call griddepcontrol.wait
   cudaLaunchConfig_t cfg{};
@@ -109,12 +109,20 @@ inline cudaError_t tc_conv_launch_one(const tc::ConvParams* P, int grid, size_t 
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, tc::conv_kernel<F, UW>, *P);
+  return cudaLaunchKernelEx(&cfg, tc::conv_kernel<F, UW, LEAN>, *P);
 }
 // f: epilogue feature set (tc::EPI_*); bit 5 (32) selects the 32-column epilogue units
-constexpr int kUw32 = 32;
+constexpr int kUw32 = 32, kLean = 64;
 inline cudaError_t tc_conv_dispatch(int f, const tc::ConvParams* P, int grid, size_t smem, cudaStream_t stream, bool pdl) {
   switch (f) {
+    case kLean | 0: return tc_conv_launch_one<0, 16, true>(P, grid, smem, stream, pdl);
+    case kLean | 17: return tc_conv_launch_one<17, 16, true>(P, grid, smem, stream, pdl);
+    case kLean | 18: return tc_conv_launch_one<18, 16, true>(P, grid, smem, stream, pdl);
+    case kLean | 19: return tc_conv_launch_one<19, 16, true>(P, grid, smem, stream, pdl);
+    case kLean | kUw32 | 0: return tc_conv_launch_one<0, 32, true>(P, grid, smem, stream, pdl);
+    case kLean | kUw32 | 17: return tc_conv_launch_one<17, 32, true>(P, grid, smem, stream, pdl);
+    case kLean | kUw32 | 18: return tc_conv_launch_one<18, 32, true>(P, grid, smem, stream, pdl);
+    case kLean | kUw32 | 19: return tc_conv_launch_one<19, 32, true>(P, grid, smem, stream, pdl);
     case kUw32 | 0: return tc_conv_launch_one<0, 32>(P, grid, smem, stream, pdl);
     case kUw32 | 17: return tc_conv_launch_one<17, 32>(P, grid, smem, stream, pdl);
     case kUw32 | 18: return tc_conv_launch_one<18, 32>(P, grid, smem, stream, pdl);
@@ -139,7 +147,7 @@ inline cudaError_t tc_conv_dispatch(int f, const tc::ConvParams* P, int grid, si
 
 inline int tc_plan_init(vcd_plan* p) {
   cudaError_t e = cudaSuccess;
-  for (int f = 0; f < 64 && e == cudaSuccess; ++f) e = tc_conv_dispatch(f, nullptr, 0, 0, 0, false);
+  for (int f = 0; f < 128 && e == cudaSuccess; ++f) e = tc_conv_dispatch(f, nullptr, 0, 0, 0, false);
   if (e != cudaSuccess) return 1;
   e = cudaFuncSetAttribute(tc::wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   if (e != cudaSuccess) return 1;
@@ -213,8 +221,13 @@ inline int tc_run_conv(vcd_plan* p, const Layer& L, bool dgrad, const void* in, 
   P.NE = 0; P.e_ops = 0; P.e_stage_bytes = 0;
   const int kb0 = P.KB;
   size_t a_stage = 0, w_region = 0;
+  // Streamed-weight (>= 128-channel) launches own one tile per CTA at training shapes, so a second accumulator buffer
+  // buys nothing there; a CTA that keeps to half of the SM's shared memory and TMEM lets a CTA of another ResBlock
+  // branch (or weight-gradient kernel) share the SM, whose epilogue / prologue then overlaps this one's MMAs.
+  static const int bufs1_big = tc_env_int("VCD_CONV_BUFS1_BIG", 0);
   for (;; MT /= 2) {  // a row-tile count whose rings do not fit the shared-memory budget falls back to the next smaller one
   bufs = 2 * MT * P.BN <= 512 ? 2 : 1;
+  if (bufs1_big && !can_reside && MT * P.BN <= 256) bufs = 1;
   P.KB = kb0;
   P.MT = MT;
   P.acc_bufs = bufs;
@@ -236,8 +249,8 @@ inline int tc_run_conv(vcd_plan* p, const Layer& L, bool dgrad, const void* in, 
   a_stage = static_cast<size_t>(MT) * (P.KB / 8) * P.RA * 16;
   const size_t w_tap = static_cast<size_t>(P.KB / 8) * P.BN * 16;
   const size_t w_all = w_tap * g.taps * (g.K / P.KB);
-  static const int smem_kb = tc_env_int("VCD_CONV_SMEM_KB", 220);
-  const size_t budget = static_cast<size_t>(smem_kb) * 1024;
+  static const int smem_kb = tc_env_int("VCD_CONV_SMEM_KB", 220), smem_kb_big = tc_env_int("VCD_CONV_SMEM_KB_BIG", 0);
+  const size_t budget = static_cast<size_t>(!can_reside && smem_kb_big > 0 ? smem_kb_big : smem_kb) * 1024;
   P.NA = (g.K / P.KB) > 1 ? 3 : 2;
   {
     static const int force_na = tc_env_int("VCD_CONV_NA", 0);
@@ -320,7 +333,12 @@ inline int tc_run_conv(vcd_plan* p, const Layer& L, bool dgrad, const void* in, 
   // only the forward chain uses it by default.
   static const int pdl_mask = tc_env_int("VCD_PDL", 1), pdl_late_mask = tc_env_int("VCD_PDL_LATE", 2);
   P.pdl_late = (pdl_late_mask & (dgrad ? 2 : 1)) != 0 ? 1 : 0;
-  const cudaError_t ce = tc_conv_dispatch(f | (uw32 ? kUw32 : 0), &P, grid, smem, stream, (pdl_mask & (dgrad ? 2 : 1)) != 0);
+  // lean epilogue: plain geometry, launch-constant bias, operand-free or smem-staged epilogue, both warps of a quadrant busy
+  static const int lean_on = tc_env_int("VCD_CONV_LEAN", 1);
+  const bool lean = lean_on && P.w_resident && (f == 0 || f == 17 || f == 18 || f == 19) && g.os == 1 && g.p == 0 && g.creal == g.N &&
+                    P.n_tiles_n == 1 && e.bias2 == nullptr && e.zu == 0 && (MT * P.BN) / (uw32 ? 32 : 16) >= 2;
+  const cudaError_t ce = tc_conv_dispatch(f | (uw32 ? kUw32 : 0) | (lean ? kLean : 0), &P, grid, smem, stream,
+                                          (pdl_mask & (dgrad ? 2 : 1)) != 0);
   launches.fetch_add(1, std::memory_order_relaxed);
   if (ce != cudaSuccess) {
     snprintf(err, errn, "launch of tc::conv_kernel(%s) failed: %s", L.name.c_str(), cudaGetErrorString(ce));

@@ -345,7 +345,14 @@ __device__ __forceinline__ void epi_finish(const Epilogue& e, const ConvGeo& g, 
 // by instruction issue; one 32-column TMEM load per step halves the per-step bookkeeping (tile / unit decode, barrier
 // checks, pipeline state).  UW = 32 is only instantiated for the variants without global epilogue operands (none, or all
 // staged in shared memory) -- the register prefetch buffers of the other variants would double.
-template <int F, int UW = 16>
+// LEAN: epilogue role for the plain convolution geometry of the resident-weight (<= 64-channel) ResBlock layers (os == 1,
+// p == 0, one column tile, launch-constant bias, no global epilogue operands: F == 0 or EPI_SMEM without running sums).
+// The generic epilogue decodes (tile -> batch item, row group, scatter phase) with three multiplier divisions and
+// re-derives every offset per 16-column unit; the compiler places that warp-uniform arithmetic on the uniform datapath,
+// whose long dependent chains (~100 UIMAD / USEL / LDCU per unit) cost more than the arithmetic of a 128 x 32 tile
+// (in-kernel trace: 0.67 us per tile of which 0.13 us MMA).  Here the tile walk is incremental (b, row group advance by
+// the grid stride), offsets are one IMAD per unit, and a warp sweeps all its units of a tile in one straight loop.
+template <int F, int UW = 16, bool LEAN = false>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_kernel(const ConvParams P) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -595,16 +602,100 @@ conv_kernel(const ConvParams P) {
     if (kk_per_block == 4) {
       if (P.MT == 1) issue_tiles(integral_constant<int, 4>{}, integral_constant<int, 1>{});
       else if (P.MT == 2) issue_tiles(integral_constant<int, 4>{}, integral_constant<int, 2>{});
+      else if (P.MT == 4) issue_tiles(integral_constant<int, 4>{}, integral_constant<int, 4>{});
       else issue_tiles(integral_constant<int, 4>{}, integral_constant<int, 0>{});
     } else if (kk_per_block == 2) {
       if (P.MT == 1) issue_tiles(integral_constant<int, 2>{}, integral_constant<int, 1>{});
       else if (P.MT == 2) issue_tiles(integral_constant<int, 2>{}, integral_constant<int, 2>{});
+      else if (P.MT == 4) issue_tiles(integral_constant<int, 2>{}, integral_constant<int, 4>{});
       else issue_tiles(integral_constant<int, 2>{}, integral_constant<int, 0>{});
     } else {
       issue_tiles(integral_constant<int, 1>{}, integral_constant<int, 0>{});
     }
     if (P.pdl_late) pdl_launch();
     if (lane == 0) ktrace(P.trace, 5);
+  } else if (LEAN && warp >= 2 && warp <= 9) {
+    // ===================== epilogue warps, plain geometry (see LEAN above) =====================
+    if constexpr (LEAN) {
+      static_assert(F == 0 || ((F & EPI_SMEM) && !(F & (EPI_RES2 | EPI_RAW))), "LEAN needs operand-free or smem-staged epilogues");
+      constexpr int NG = UW / 8;
+      const int quad = warp & 3, half = (warp - 2) >> 2;
+      const int row_in_tile = quad * 32 + lane;
+      const Epilogue& e = P.e;
+      const int ushift = P.units_shift - (UW == 32 ? 1 : 0);
+      const int n_units = P.MT << ushift;
+      const int groups = P.BN >> 3;
+      const uint32_t chunk_stride = static_cast<uint32_t>(padded_len(P.Lout)) * 8;
+      const uint32_t b_stride = static_cast<uint32_t>(P.g.creal >> 3) * chunk_stride;
+      const uint32_t tile_rows8 = static_cast<uint32_t>(P.MT) * 128u * 8u;
+      const bool plain_out = e.tscale == 1.f && e.act_slope == 1.f;
+      const float s_pos = e.scale, s_neg = e.mask_slope * e.scale;
+      const bool has_bias = e.bias != nullptr;
+      const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+      const uint32_t op_stride = static_cast<uint32_t>(P.MT) * groups * 2048u;
+      const int grid = static_cast<int>(gridDim.x);
+      if (has_bias) {     // launch-constant bias vector (host-checked: one column tile, no per-batch bias)
+        const int et = static_cast<int>(threadIdx.x) - 64;
+        if (et < P.BN) bias_s[et] = __ldg(e.bias + et);
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+      }
+      int b, mg;
+      P.d_mgroups.divmod(static_cast<int>(blockIdx.x), b, mg);
+      pdl_wait();
+      int it = 0;
+      for (int tile = blockIdx.x; tile < P.total_tiles; tile += grid, ++it) {
+        const int buf = P.acc_bufs == 2 ? (it & 1) : 0;
+        const int use_n = P.acc_bufs == 2 ? (it >> 1) : it;
+        const int q0 = mg * P.MT * 128 + row_in_tile;
+        const uint32_t tile_o = static_cast<uint32_t>(b) * b_stride + static_cast<uint32_t>(mg) * tile_rows8 +
+                                static_cast<uint32_t>(row_in_tile + kPadL) * 8u;
+        const uint32_t t_tile = t_lane + static_cast<uint32_t>(buf * P.MT * P.BN);
+        int e_stage = 0;
+        const uint8_t* e_base = nullptr;
+        if constexpr (F & EPI_SMEM) {
+          e_stage = it % P.NE;
+          mbar_wait(&fullE[e_stage], static_cast<uint32_t>(it / P.NE) & 1u);
+          e_base = e_smem + static_cast<size_t>(e_stage) * P.e_stage_bytes + static_cast<uint32_t>(row_in_tile) * 16u;
+        }
+        mbar_wait(&acc_full[buf], use_n & 1);
+        tc_fence_after();
+        for (int u = half; u < n_units; u += 2) {
+          const int mt = u >> ushift, cu = u - (mt << ushift);
+          float acc[UW];
+          const uint32_t taddr = t_tile + static_cast<uint32_t>(mt * P.BN + cu * UW);
+          if constexpr (UW == 16) tmem_ld16(taddr, acc);
+          else tmem_ld32(taddr, acc);
+          if (q0 + mt * 128 < P.Lq) {
+            const uint32_t o = tile_o + static_cast<uint32_t>(mt) * 1024u + static_cast<uint32_t>(cu * NG) * chunk_stride;
+#pragma unroll
+            for (int h = 0; h < NG; ++h) {
+              float v[8];
+#pragma unroll
+              for (int n = 0; n < 8; ++n) v[n] = acc[h * 8 + n];
+              EpiLoads L;
+              if constexpr (F & EPI_SMEM) {
+                const uint8_t* ep = e_base + static_cast<uint32_t>(mt * groups + cu * NG + h) * 2048u;
+                if constexpr (F & EPI_MASK) {
+                  L.mask = *reinterpret_cast<const uint4*>(ep);
+                  ep += op_stride;
+                }
+                if constexpr (F & EPI_RES) L.rest = *reinterpret_cast<const uint4*>(ep);
+              }
+              epi_finish<F>(e, P.g, 0, 0, 0, o + static_cast<uint32_t>(h) * chunk_stride, L,
+                            has_bias ? bias_s + cu * UW + h * 8 : nullptr, plain_out, s_pos, s_neg, v);
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(&acc_empty[buf]);
+          if constexpr (F & EPI_SMEM) mbar_arrive(&emptyE[e_stage]);
+        }
+        mg += grid;
+        while (mg >= P.n_mgroups) { mg -= P.n_mgroups; ++b; }
+      }
+    }
   } else if (warp >= 2 && warp <= 9) {
     // ===================== epilogue warps =====================
     const int quad = warp & 3;               // TMEM lane quadrant this warp may access
