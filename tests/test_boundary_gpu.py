@@ -192,3 +192,51 @@ def test_sliced_forward_equals_slice_segments_then_decode():
         assert rel_l2(p.grad.cpu(), r.cpu()) <= 1e-5
     with pytest.raises(ValueError):
         m.forward_sliced(z, ids[:2], 12, g)
+
+
+def test_fused_parameter_gradients_match_autograd_leaves():
+    """b5: the default backward writes every parameter's ``.grad`` itself (one flat buffer) instead of returning 233
+    tensors to autograd; same values as the classic leaf-per-parameter path, ``+=`` when a gradient already exists,
+    nothing for frozen parameters, and ``torch.autograd.grad`` w.r.t. parameters through the classic path."""
+    m, _ = _small("fp32")
+    torch.manual_seed(4)
+    x = torch.randn(2, 64, 20, device="cuda", requires_grad=True)
+    g = torch.randn(2, 16, 1, device="cuda", requires_grad=True)
+    dy = torch.randn(2, 1, 320, device="cuda")
+    assert m.fused_param_grads
+    m(x, g).backward(dy)
+    fused = [p.grad.clone() for p in m.parameters()]
+    dx_f, dg_f = x.grad.clone(), g.grad.clone()
+    assert all(p.grad.shape == p.shape and p.grad.is_contiguous() for p in m.parameters())
+    # accumulate into existing gradients (no zero_grad in between): exactly twice the gradient
+    m(x, g).backward(dy)
+    for p, r in zip(m.parameters(), fused):
+        assert rel_l2(p.grad.cpu(), (2 * r).cpu()) <= 1e-5
+    # classic path
+    m.zero_grad(set_to_none=True)
+    x.grad = g.grad = None
+    m.fused_param_grads = False
+    m(x, g).backward(dy)
+    for p, r in zip(m.parameters(), fused):
+        assert rel_l2(p.grad.cpu(), r.cpu()) <= 1e-5
+    assert rel_l2(x.grad.cpu(), dx_f.cpu()) <= 1e-5 and rel_l2(g.grad.cpu(), dg_f.cpu()) <= 1e-5
+    some = [m.conv_pre.weight, m.ups[0].weight_g]
+    got = torch.autograd.grad(m(x, g), some, dy)
+    assert rel_l2(got[0].cpu(), m.conv_pre.weight.grad.cpu()) <= 1e-5
+    # frozen parameters: no gradient, the rest unchanged; latents only: no parameter gradient at all
+    m.fused_param_grads = True
+    m.zero_grad(set_to_none=True)
+    m.conv_pre.weight.requires_grad_(False)
+    m(x, g).backward(dy)
+    assert m.conv_pre.weight.grad is None and m.conv_pre.bias.grad is not None
+    for p in m.parameters():
+        p.requires_grad_(False)
+    m.zero_grad(set_to_none=True)
+    x.grad = None
+    m(x, g).backward(dy)
+    assert all(p.grad is None for p in m.parameters())
+    assert rel_l2(x.grad.cpu(), dx_f.cpu()) <= 1e-5
+    # inference under no_grad still works with the fused default
+    with torch.no_grad():
+        y = m(x, g)
+    assert not y.requires_grad

@@ -844,6 +844,9 @@ double layer_flops(const Layer& L, int B, int Lfwd_in) {
 int run_conv(const Ctx& c, cudaStream_t st, const Layer& L, bool dgrad, const void* in, int Lin, int Lq, int Lout,
              Epilogue e, double flops) {
   const ConvGeo& g = dgrad ? L.dgr : L.fwd;
+  // timing experiments only (results are wrong): bit 0 skips forward, bit 1 data-gradient, bit 2 weight-gradient launches
+  static const int dbg_skip = tc_env_int("VCD_DEBUG_SKIP", 0);
+  if (dbg_skip & (dgrad ? 2 : 1)) return 0;
   if (c.mode == VCD_MODE_BF16 && (dgrad ? L.tc_ok_dgr : L.tc_ok_fwd)) {
     ProfScope ps__(PC_TC_CONV, flops, 0, st, (L.name + (dgrad ? ":dgrad" : ":fwd")).c_str());
     return tc_run_conv(c.p, L, dgrad, in, c.B, Lin, Lq, Lout, e, st, g_launches, g_err, sizeof(g_err));
@@ -860,6 +863,8 @@ int run_wgrad(const Ctx& c, cudaStream_t st, const Layer& L, const void* in, con
               bool tail = false) {
   const ConvGeo& g = L.wgr;
   float* dwp = c.p->d_gscratch + L.dwp;
+  static const int dbg_skip = tc_env_int("VCD_DEBUG_SKIP", 0);
+  if (dbg_skip & 4) return 0;
   if (c.mode == VCD_MODE_BF16 && L.tc_ok_wgr) {
     ProfScope ps__(PC_TC_WGRAD, flops, 0, st, (L.name + ":wgrad").c_str());
     // the bias gradient (column sums of dout) is produced by the same kernel
