@@ -114,7 +114,7 @@ struct vcd_plan {
   std::vector<vcd::SegmentJobs> segments;
 
   // auxiliary streams / events for intra-step concurrency (ResBlock branches, weight-gradient kernels)
-  static constexpr int kMaxAux = 14, kMaxEvents = 256;   // 7 branch + 4 weight-gradient side streams + 3 helpers
+  static constexpr int kMaxAux = 14, kMaxEvents = 1024;   // 7 branch + 4 weight-gradient side streams + 3 helpers
   cudaStream_t aux[kMaxAux] = {};
   cudaStream_t own = nullptr;              // stands in for the legacy default stream (not capturable)
   cudaEvent_t hop_in = nullptr, hop_out = nullptr;

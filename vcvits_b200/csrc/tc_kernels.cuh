@@ -232,6 +232,8 @@ struct ConvParams {
   int minshift;           // min over taps of j*step (<= 0)
   int acc_bufs;           // 2: accumulators double-buffered (epilogue overlaps the next tile's MMAs); 1: MT*BN > 256
   uint32_t tmem_cols;
+  int rot;                // ring mode: rotate the (K block, tap group) order by the row-group index, so that the CTAs of a
+                          // launch do not all pull the same weight chunk from the same L2 slices at the same time
   int pdl_late;           // 1: release the stream successor after this CTA's last MMAs are issued (default: at its last tile's loads)
   int NE;                 // EPI_SMEM: stages of the epilogue-operand ring (mask / residual tiles fetched by the bulk-copy engine)
   int e_ops;              // operands per stage (mask, residual)
@@ -366,6 +368,7 @@ conv_kernel(const ConvParams P) {
   const uint32_t w_tap_bytes = static_cast<uint32_t>(P.KB / 8) * P.BN * 16;   // one tap of one K block
   const int kblocks = P.g.K / P.KB;
   const int kk_per_block = P.KB / 16;
+  const int ngroups_w = (P.g.taps + P.TPS - 1) / P.TPS;   // weight stages per K block (ring mode)
   const uint32_t w_region_bytes = P.w_resident ? w_tap_bytes * P.g.taps * kblocks : w_tap_bytes * P.TPS * P.NW;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
   uint8_t* a_smem = smem;
@@ -416,7 +419,10 @@ conv_kernel(const ConvParams P) {
       // 128-row tiles that start beyond the last output row are not loaded (their accumulators are never stored)
       int mt_live = P.MT;
       while (mt_live > 1 && (mg * P.MT + mt_live - 1) * 128 >= P.Lq) --mt_live;
-      for (int kb = 0; kb < kblocks; ++kb) {
+      const int rot_k = P.rot ? (P.d_tiles_n.quot(tile) / ngroups_w) % kblocks : 0;
+      for (int kbi = 0; kbi < kblocks; ++kbi) {
+        int kb = kbi + rot_k;
+        if (kb >= kblocks) kb -= kblocks;
         mbar_wait(&emptyA[pa.stage], pa.phase ^ 1);
         uint8_t* stage = a_smem + static_cast<size_t>(pa.stage) * a_stage_bytes;
         const bf16* src0 = P.in + blk_row(b, kb * cgs, row0, P.g.K, P.Lin);
@@ -428,7 +434,7 @@ conv_kernel(const ConvParams P) {
                         cg_bytes, &fullA[pa.stage]);
         }
         __syncwarp();
-        if (tile == static_cast<int>(blockIdx.x) && kb == 0 && lane == 0) ktrace(P.trace, 2);
+        if (tile == static_cast<int>(blockIdx.x) && kbi == 0 && lane == 0) ktrace(P.trace, 2);
         pa.advance(P.NA);
       }
     }
@@ -479,9 +485,16 @@ conv_kernel(const ConvParams P) {
       Pipe pw;
       const size_t tap_stride_g = static_cast<size_t>(P.g.K / 8) * P.BN * 8;
       for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
-        const int nt = tile - P.d_tiles_n.quot(tile) * P.n_tiles_n;
-        for (int kb = 0; kb < kblocks; ++kb) {
-          for (int j0 = 0; j0 < P.g.taps; j0 += P.TPS) {
+        const int rest = P.d_tiles_n.quot(tile);
+        const int nt = tile - rest * P.n_tiles_n;
+        const int rot_j = P.rot ? rest % ngroups_w : 0, rot_k = P.rot ? (rest / ngroups_w) % kblocks : 0;
+        for (int kbi = 0; kbi < kblocks; ++kbi) {
+          int kb = kbi + rot_k;
+          if (kb >= kblocks) kb -= kblocks;
+          for (int gi = 0; gi < ngroups_w; ++gi) {
+            int grp = gi + rot_j;
+            if (grp >= ngroups_w) grp -= ngroups_w;
+            const int j0 = grp * P.TPS;
             const int nj = min(P.TPS, P.g.taps - j0);
             mbar_wait(&emptyW[pw.stage], pw.phase ^ 1);
             uint8_t* dst = w_smem + static_cast<size_t>(pw.stage) * P.TPS * w_tap_bytes;
@@ -535,26 +548,35 @@ conv_kernel(const ConvParams P) {
         mbar_wait(&acc_empty[buf], (use & 1) ^ 1);
         tc_fence_after();
         const uint32_t d_tile = tmem_base + static_cast<uint32_t>(buf * P.MT * P.BN);
-        for (int kb = 0; kb < kblocks; ++kb) {
+        const int rest = P.d_tiles_n.quot(tile);
+        const int rot_j = P.rot ? rest % ngroups_w : 0;          // (host: rot only with streamed weights)
+        const int rot_k = P.rot ? (rest / ngroups_w) % kblocks : 0;
+        const int ngroups = P.w_resident ? 1 : ngroups_w;
+        for (int kbi = 0; kbi < kblocks; ++kbi) {
+          int kb = kbi + rot_k;
+          if (kb >= kblocks) kb -= kblocks;
           mbar_wait(&fullA[pa.stage], pa.phase);
           tc_fence_after();
-          if (it == 0 && kb == 0 && lane == 0) ktrace(P.trace, 4);
+          if (it == 0 && kbi == 0 && lane == 0) ktrace(P.trace, 4);
           const uint32_t a_stage_lo = static_cast<uint32_t>(a_desc0) + (smem_u32(a_smem + static_cast<size_t>(pa.stage) * a_stage_bytes) >> 4);
-          uint32_t a_tap = a_stage_lo + static_cast<uint32_t>(-P.minshift);
-          int j = 0;
-          while (j < taps) {
-            int nj;
+          for (int gi = 0; gi < ngroups; ++gi) {
+            int nj, j0;
             uint32_t w_lo;
             if (P.w_resident) {
               nj = taps;
+              j0 = 0;
               w_lo = w_res_lo + static_cast<uint32_t>(kb) * w_tap16;
             } else {
-              nj = min(P.TPS, taps - j);
+              int grp = gi + rot_j;
+              if (grp >= ngroups_w) grp -= ngroups_w;
+              j0 = grp * P.TPS;
+              nj = min(P.TPS, taps - j0);
               mbar_wait(&fullW[pw.stage], pw.phase);
               tc_fence_after();
               w_lo = static_cast<uint32_t>(w_desc0) + (smem_u32(w_smem + static_cast<size_t>(pw.stage) * P.TPS * w_tap_bytes) >> 4);
             }
-            uint32_t first = (kb | j) != 0 ? 1u : 0u;    // accumulate flag of the first MMA of this tap
+            uint32_t a_tap = a_stage_lo + static_cast<uint32_t>(-P.minshift) + static_cast<uint32_t>(j0) * a_step;
+            uint32_t first = (kbi | gi) != 0 ? 1u : 0u;    // accumulate flag of the first MMA of this tap group
 #pragma unroll 1
             for (int jj = 0; jj < nj; ++jj) {
               if constexpr (MTC > 0) {
@@ -585,7 +607,6 @@ conv_kernel(const ConvParams P) {
               w_lo += tap_stride16;
               a_tap += a_step;
             }
-            j += nj;
             if (!P.w_resident) {
               if (elect_one()) umma_commit(&emptyW[pw.stage]);
               pw.advance(P.NW);

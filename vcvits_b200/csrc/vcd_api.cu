@@ -581,9 +581,13 @@ struct WsLayout {
   std::vector<size_t> a;
   std::vector<StageWs> st;
   size_t sum[2] = {0, 0};                   // fp32 running sums over ResBlock branches (fwd) / branch gradients (bwd)
-  size_t Gi[2] = {0, 0};                    // T: gradient w.r.t. a stage output (ping-pong across stages)
-  std::vector<std::vector<size_t>> Gt, dm;  // T [branch][pair]: residual-stream gradient / mid gradient
-  size_t duz = 0;                           // T: phase-packed gradient w.r.t. the upsample output
+  size_t Gi[3] = {0, 0, 0};                 // T: gradient w.r.t. the output of stage i lives in Gi[i % 3] (three sets: the
+                                            // trailing weight-gradient kernels of segment s-1 still read theirs while segment s writes)
+  // T [stage parity][branch][pair]: residual-stream gradient / mid gradient.  Two sets, alternating between consecutive
+  // stages: the weight-gradient kernels of a backward segment trail behind the next segment's data-gradient chain
+  // (they read these tensors), so a segment must not overwrite its predecessor's set.
+  std::vector<std::vector<size_t>> Gt[2], dm[2];
+  size_t duz[2] = {0, 0};                   // T: phase-packed gradient w.r.t. the upsample output (same alternation)
   size_t d0 = 0, dxb = 0;
   size_t total = 0;
   // pad-row zeroing jobs: forward phase 0 = boundary tensors, phase 1+i = stage i; backward phase = segment
@@ -664,30 +668,39 @@ WsLayout make_layout(const vcd_plan* p, int mode, int B, int T, bool save) {
   w.sum[0] = alloc(4 * emax);
   w.sum[1] = alloc(4 * emax);
   if (save) {
-    w.Gi[0] = alloc(es * emax);
-    w.Gi[1] = alloc(es * emax);
-    w.Gt.assign(NB, std::vector<size_t>(npairs, 0));
-    w.dm.assign(NB, std::vector<size_t>(npairs, 0));
-    for (int j = 0; j < NB; ++j)
-      for (int q = 0; q < npairs; ++q) {
-        if (q > 0) w.Gt[j][q] = alloc(es * emax);
-        if (p->cfg.resblock == 1) w.dm[j][q] = alloc(es * emax);
+    for (int t = 0; t < 3; ++t) w.Gi[t] = alloc(es * emax);
+    for (int par = 0; par < 2; ++par) {
+      // set `par` serves the stages i with (i & 1) == par
+      size_t em = 0, zm = 0;
+      for (int i = par; i < S; i += 2) {
+        const Layer& U = p->layers[p->stages[i].up_layer];
+        em = std::max(em, E[i]);
+        zm = std::max(zm, blk_elems(B, U.wgr.N, Ls[i] + U.fwd.taps - 1));
       }
-    w.duz = alloc(es * zmax);
+      w.Gt[par].assign(NB, std::vector<size_t>(npairs, 0));
+      w.dm[par].assign(NB, std::vector<size_t>(npairs, 0));
+      if (em == 0) continue;
+      for (int j = 0; j < NB; ++j)
+        for (int q = 0; q < npairs; ++q) {
+          if (q > 0) w.Gt[par][j][q] = alloc(es * em);
+          if (p->cfg.resblock == 1) w.dm[par][j][q] = alloc(es * em);
+        }
+      w.duz[par] = alloc(es * zm);
+    }
     w.d0 = alloc(es * blk_elems(B, C0, T));
     w.dxb = alloc(4 * blk_elems(B, Cin0, T));
     // backward pads: segment s works on stage i = S-1-s and produces the stage gradient consumed by segment s+1
-    pad(w.pad_fwd[S], w.Gi[(S - 1) & 1], p->stages[S - 1].cout, Ls[S]);  // written by conv_post's backward
+    pad(w.pad_fwd[S], w.Gi[(S - 1) % 3], p->stages[S - 1].cout, Ls[S]);  // written by conv_post's backward
     pad(w.pad_fwd[0], w.d0, C0, T);
     for (int seg = 0; seg < S; ++seg) {
       const int i = S - 1 - seg;
       const int C = p->stages[i].cout, L = Ls[i + 1];
       for (int j = 0; j < NB; ++j)
         for (int q = 0; q < npairs; ++q) {
-          if (q > 0) pad(w.pad_bwd[seg], w.Gt[j][q], C, L);
-          if (p->cfg.resblock == 1) pad(w.pad_bwd[seg], w.dm[j][q], C, L);
+          if (q > 0) pad(w.pad_bwd[seg], w.Gt[i & 1][j][q], C, L);
+          if (p->cfg.resblock == 1) pad(w.pad_bwd[seg], w.dm[i & 1][j][q], C, L);
         }
-      if (i > 0) pad(w.pad_bwd[seg], w.Gi[(i - 1) & 1], p->stages[i - 1].cout, Ls[i]);
+      if (i > 0) pad(w.pad_bwd[seg], w.Gi[(i - 1) % 3], p->stages[i - 1].cout, Ls[i]);
     }
   }
   w.total = top;
@@ -1198,27 +1211,25 @@ static int backward_impl(vcd_plan* p, int mode, const float* dy, const float* y,
       CU_TRY(cudaMemsetAsync(p->d_gscratch + z.scratch_begin, 0, (z.scratch_end - z.scratch_begin) * sizeof(float), st));
     return 0;
   };
-  bool first_seg = true;
-  for (int seg = 0; seg <= S; ++seg) {
-    if (!(segment_mask & (1u << seg))) continue;
+  // Whole-backward mode (every segment requested in one call): ONE captured graph in which the data-gradient chain runs
+  // through all stages without waiting for the weight gradients; the weight-gradient kernels of a segment and its
+  // weight-norm backward trail behind on the side streams / the unfold stream while the next segment's chain already
+  // runs (per-segment calls join them at every segment end: ~0.15 ms of idle chain per segment on base.json).
+  const uint32_t all_mask = (1u << (S + 1)) - 1;
+  static const int whole_on = tc_env_int("VCD_BWD_WHOLE", 1);
+  const bool whole = whole_on && !c.serial && (segment_mask & all_mask) == all_mask;
+  cudaStream_t ust = c.serial ? stream : p->aux[vcd_plan::kMaxAux - 3];   // weight-norm backward of trailing segments
+  std::vector<cudaEvent_t> join_ev(S + 1, nullptr);   // whole mode: weight gradients of segment s complete
+  bool post_forked = false;
+  auto pre_part = [&](int seg) -> int {
     const SegmentJobs& sj = p->segments[seg];
-    if (first_seg) TRY(zero_scratch(seg, stream));   // later segments: zeroed beside the previous segment (below)
-    first_seg = false;
-    int next_seg = -1;
-    for (int k = seg + 1; k <= S; ++k)
-      if (segment_mask & (1u << k)) { next_seg = k; break; }
-    if (next_seg >= 0) {
-      c.order(stream, zst);
-      TRY(zero_scratch(next_seg, zst));
-    }
-    bool post_forked = false;
     if (seg == 0) {  // conv_post + tanh backward -> gradient w.r.t. the last stage output
       const int C = p->stages[S - 1].cout, L = Ls[S];
       const int splits = std::max(1, std::min(64, L / 2048));
       dim3 gw(C / 8, B, splits);
       dim3 gd((L + 127) / 128, C / 8, B);
       const float* wpost = p->h_params[p->p_post_w];
-      const int slot = (S - 1) & 1;
+      const int slot = (S - 1) % 3;
       ProfScope ps__(PC_POST, 4.0 * C * 7 * B * L, static_cast<double>(B) * L * (C * 3 * es + 16), stream);
       // weight gradient (+ its copy into the caller's tensor) beside the data-gradient chain
       c.order(stream, wst);
@@ -1245,7 +1256,10 @@ static int backward_impl(vcd_plan* p, int mode, const float* dy, const float* y,
         LAUNCH_CHECK("wn_unfold_kernel");
       }
     }
-    auto core = [&]() -> int {
+    return 0;
+  };
+  auto core = [&](int seg) -> int {
+    const SegmentJobs& sj = p->segments[seg];
     int side_rr = 0;
     bool side_used[4] = {false, false, false, false};
     // weight-gradient kernels run on side streams: they only need their two operands, never feed the
@@ -1256,6 +1270,8 @@ static int backward_impl(vcd_plan* p, int mode, const float* dy, const float* y,
       if (!c.serial) { c.wait(s, ready); side_used[k] = true; }
       return s;
     };
+    // whole mode: this segment reuses the gradient workspaces of segment seg-2, whose weight gradients may still trail
+    if (whole && seg >= 2 && join_ev[seg - 2]) c.wait(stream, join_ev[seg - 2]);
     if (seg < S) {
       const int i = S - 1 - seg;
       const StageDesc& sd = p->stages[i];
@@ -1263,9 +1279,9 @@ static int backward_impl(vcd_plan* p, int mode, const float* dy, const float* y,
       const int L = Ls[i + 1], Lprev = Ls[i];
       const Layer& U = p->layers[sd.up_layer];
       const int Lz = Lprev + U.fwd.taps - 1;  // rows of the phase-packed gradient
-      const void* Gi = P(w.Gi[i & 1]);
+      const void* Gi = P(w.Gi[i % 3]);
       // unwritten edge slots (and the pad rows) of the phase-packed tensor must read as zero
-      CU_TRY(cudaMemsetAsync(P(w.duz), 0, es * blk_elems(B, U.wgr.N, Lz), stream));
+      CU_TRY(cudaMemsetAsync(P(w.duz[i & 1]), 0, es * blk_elems(B, U.wgr.N, Lz), stream));
       TRY(launch_pads(p, w.pad_bwd[seg], mode, B, T, true, seg, true, c.ws, stream));
       cudaEvent_t ev0 = c.serial ? nullptr : c.record(stream);
       for (int j = 1; j < NB; ++j) if (!c.serial) c.wait(c.branch(j), ev0);
@@ -1284,9 +1300,9 @@ static int backward_impl(vcd_plan* p, int mode, const float* dy, const float* y,
             Epilogue e = epi();
             e.mask = P(sw.ma[j][q]);
             e.mask_slope = kSlope;
-            e.out_t = P(w.dm[j][q]);
+            e.out_t = P(w.dm[i & 1][j][q]);
             TRY(run_conv(c, sjs, L2, true, Gt_cur, L, L, L, e, layer_flops(L2, B, L)));
-            d_first = P(w.dm[j][q]);
+            d_first = P(w.dm[i & 1][j][q]);
             ev_first = c.serial ? nullptr : c.record(sjs);
           }
           const Layer& L1 = p->layers[sd.convs[j][q][0]];
@@ -1296,8 +1312,8 @@ static int backward_impl(vcd_plan* p, int mode, const float* dy, const float* y,
           e.mask_slope = kSlope;
           e.res_t = Gt_cur;  // identity path of `x = xt + x`
           if (q > 0) {
-            e.out_t = P(w.Gt[j][q]);
-            Gt_cur = P(w.Gt[j][q]);
+            e.out_t = P(w.Gt[i & 1][j][q]);
+            Gt_cur = P(w.Gt[i & 1][j][q]);
           } else {
             if (j > 0) {
               e.res2 = PF(w.sum[(j - 1) & 1]);
@@ -1306,7 +1322,7 @@ static int backward_impl(vcd_plan* p, int mode, const float* dy, const float* y,
             if (j < NB - 1) {
               e.out_raw = PF(w.sum[j & 1]);
             } else {  // sum over branches, written phase-packed for the upsample conv's backward GEMMs
-              e.out_t = P(w.duz);
+              e.out_t = P(w.duz[i & 1]);
               e.zu = sd.u; e.zp = U.pad; e.zLq = Lz;
             }
           }
@@ -1321,17 +1337,17 @@ static int backward_impl(vcd_plan* p, int mode, const float* dy, const float* y,
       // upsample conv: weight/bias gradients (side stream) and data gradient, fused with the lrelu mask and the
       // 1/NB of the previous stage's branch mean
       cudaEvent_t ev_du = c.serial ? nullptr : c.record(stream);
-      TRY(run_wgrad(c, side_after(ev_du), U, P(w.a[i]), P(w.duz), Lprev, Lz, layer_flops(U, B, Lprev), true));
+      TRY(run_wgrad(c, side_after(ev_du), U, P(w.a[i]), P(w.duz[i & 1]), Lprev, Lz, layer_flops(U, B, Lprev), true));
       Epilogue e = epi();
       e.mask = P(w.a[i]);
       e.mask_slope = kSlope;
       if (i > 0) {
         e.scale = 1.f / NB;
-        e.out_t = P(w.Gi[(i - 1) & 1]);
+        e.out_t = P(w.Gi[(i - 1) % 3]);
       } else {
         e.out_t = P(w.d0);
       }
-      TRY(run_conv(c, stream, U, true, P(w.duz), Lz, Lprev, Lprev, e, layer_flops(U, B, Lprev)));
+      TRY(run_conv(c, stream, U, true, P(w.duz[i & 1]), Lz, Lprev, Lprev, e, layer_flops(U, B, Lprev)));
     } else {  // conv_pre: weight gradient, per-batch column sums (bias / cond gradients), data gradient
       const Layer& L = p->layers[p->l_pre];
       cudaEvent_t ev0 = c.serial ? nullptr : c.record(stream);
@@ -1351,32 +1367,27 @@ static int backward_impl(vcd_plan* p, int mode, const float* dy, const float* y,
         TRY(run_conv(c, stream, L, true, P(w.d0), T, T, T, e, layer_flops(L, B, T)));
       }
     }
-    // join the side streams, then the weight-norm backward of this segment's parameters
+    // join the side streams, then the weight-norm backward of this segment's parameters (whole mode: on the unfold
+    // stream, behind the chain)
+    cudaStream_t fst = whole ? ust : stream;
     for (int k = 0; k < 4; ++k)
-      if (side_used[k]) c.order(c.side(k), stream);
+      if (side_used[k]) c.order(c.side(k), fst);
+    if (whole) join_ev[seg] = c.record(fst);
     if (sj.fast_nblocks > sj.fast_lead_blocks) {  // (the jobs ahead of the first layer ran with conv_post's weight gradient)
-      ProfScope ps__(PC_FOLD, 0, 12.0 * (sj.scratch_end - sj.scratch_begin), stream);   // dWp read + v read + gradient write
-      wn_unfold_fast_kernel<<<sj.fast_nblocks - sj.fast_lead_blocks, kFoldThreads, sj.fast_smem, stream>>>(
+      ProfScope ps__(PC_FOLD, 0, 12.0 * (sj.scratch_end - sj.scratch_begin), fst);   // dWp read + v read + gradient write
+      wn_unfold_fast_kernel<<<sj.fast_nblocks - sj.fast_lead_blocks, kFoldThreads, sj.fast_smem, fst>>>(
           sj.d_fast + sj.fast_lead_jobs, sj.fast_njobs - sj.fast_lead_jobs, p->d_params, p->d_dparams, p->d_norms, p->d_gscratch,
           sj.fast_lead_blocks, p->grad_scale);
       LAUNCH_CHECK("wn_unfold_fast_kernel");
     } else if (sj.fast_nblocks == 0 && sj.nblocks > sj.lead_blocks) {
-      ProfScope ps__(PC_FOLD, 0, 12.0 * (sj.scratch_end - sj.scratch_begin), stream);   // dWp read + v read + gradient write
-      wn_unfold_kernel<<<sj.nblocks - sj.lead_blocks, 256, 0, stream>>>(sj.d_jobs + sj.lead_jobs, sj.njobs - sj.lead_jobs, p->d_params,
+      ProfScope ps__(PC_FOLD, 0, 12.0 * (sj.scratch_end - sj.scratch_begin), fst);   // dWp read + v read + gradient write
+      wn_unfold_kernel<<<sj.nblocks - sj.lead_blocks, 256, 0, fst>>>(sj.d_jobs + sj.lead_jobs, sj.njobs - sj.lead_jobs, p->d_params,
                                                                        p->d_dparams, p->d_norms, p->d_gscratch, sj.lead_blocks, p->grad_scale);
       LAUNCH_CHECK("wn_unfold_kernel");
     }
     return 0;
-    };
-    {
-      PhaseScope ph__(("backward segment " + std::to_string(seg)).c_str(), stream);
-      uint32_t scale_bits;
-      memcpy(&scale_bits, &p->grad_scale, sizeof(scale_bits));   // baked into the captured unfold launch
-      TRY(run_graphed(p, GraphKey{1 + seg, mode, B, T, 1, gvec ? 1 : 0, dx ? 1 : 0, ws, p->params_version ^ (static_cast<uint64_t>(scale_bits) << 32)},
-                      stream, core));
-    }
-    if (post_forked) c.order(wst, stream);
-    if (next_seg >= 0) c.order(zst, stream);
+  };
+  auto post_part = [&](int seg) -> int {
     if (seg == S) {  // kernels that touch caller-owned tensors: cond / conv_pre.bias gradients, dg, dx
       const Layer& L = p->layers[p->l_pre];
       {
@@ -1409,6 +1420,47 @@ static int backward_impl(vcd_plan* p, int mode, const float* dy, const float* y,
         LAUNCH_CHECK("blocked_to_ncl_kernel");
       }
     }
+    return 0;
+  };
+  uint32_t scale_bits;
+  memcpy(&scale_bits, &p->grad_scale, sizeof(scale_bits));   // baked into the captured unfold launches
+  const uint64_t gver = p->params_version ^ (static_cast<uint64_t>(scale_bits) << 32);
+  if (whole) {
+    for (int seg = 0; seg <= S; ++seg) TRY(zero_scratch(seg, stream));
+    TRY(pre_part(0));
+    {
+      PhaseScope ph__("backward (all segments)", stream);
+      TRY(run_graphed(p, GraphKey{1 + 64, mode, B, T, 1, gvec ? 1 : 0, dx ? 1 : 0, ws, gver}, stream, [&]() -> int {
+        for (int seg = 0; seg <= S; ++seg) TRY(core(seg));
+        c.order(ust, stream);   // the last trailing weight-norm backward
+        return 0;
+      }));
+    }
+    if (post_forked) c.order(wst, stream);
+    TRY(post_part(S));
+    return 0;
+  }
+  bool first_seg = true;
+  for (int seg = 0; seg <= S; ++seg) {
+    if (!(segment_mask & (1u << seg))) continue;
+    if (first_seg) TRY(zero_scratch(seg, stream));   // later segments: zeroed beside the previous segment (below)
+    first_seg = false;
+    int next_seg = -1;
+    for (int k = seg + 1; k <= S; ++k)
+      if (segment_mask & (1u << k)) { next_seg = k; break; }
+    if (next_seg >= 0) {
+      c.order(stream, zst);
+      TRY(zero_scratch(next_seg, zst));
+    }
+    post_forked = false;
+    TRY(pre_part(seg));
+    {
+      PhaseScope ph__(("backward segment " + std::to_string(seg)).c_str(), stream);
+      TRY(run_graphed(p, GraphKey{1 + seg, mode, B, T, 1, gvec ? 1 : 0, dx ? 1 : 0, ws, gver}, stream, [&]() -> int { return core(seg); }));
+    }
+    if (post_forked) c.order(wst, stream);
+    if (next_seg >= 0) c.order(zst, stream);
+    TRY(post_part(seg));
   }
   return 0;
 }
@@ -1482,14 +1534,14 @@ extern "C" int vcd_debug_ws_tensor(const vcd_plan* p, int mode, int B, int T, in
   else if (!strcmp(name, "d0")) { off = w.d0; *C = p->cfg.upsample_initial_channel; *L = T; found = save != 0; }
   else if (sscanf(name, "ma%d.%d.%d", &i, &j, &q) == 3) { if (bq_ok() && p->cfg.resblock == 1) { off = w.st[i].ma[j][q]; found = true; } }
   else if (sscanf(name, "xa%d.%d.%d", &i, &j, &q) == 3) { if (bq_ok() && q < npairs - 1) { off = w.st[i].xa[j][q]; found = true; } }
-  else if (sscanf(name, "Gt%d.%d.%d", &i, &j, &q) == 3) { if (bq_ok() && q > 0 && save) { off = w.Gt[j][q]; found = true; } }
-  else if (sscanf(name, "dm%d.%d.%d", &i, &j, &q) == 3) { if (bq_ok() && save && p->cfg.resblock == 1) { off = w.dm[j][q]; found = true; } }
+  else if (sscanf(name, "Gt%d.%d.%d", &i, &j, &q) == 3) { if (bq_ok() && q > 0 && save) { off = w.Gt[i & 1][j][q]; found = true; } }
+  else if (sscanf(name, "dm%d.%d.%d", &i, &j, &q) == 3) { if (bq_ok() && save && p->cfg.resblock == 1) { off = w.dm[i & 1][j][q]; found = true; } }
   else if (sscanf(name, "ua%d", &i) == 1) { if (stage_ok()) { off = w.st[i].ua; found = true; } }
-  else if (sscanf(name, "Gi%d", &i) == 1) { if (stage_ok() && save) { off = w.Gi[i & 1]; found = true; } }
+  else if (sscanf(name, "Gi%d", &i) == 1) { if (stage_ok() && save) { off = w.Gi[i % 3]; found = true; } }
   else if (sscanf(name, "duz%d", &i) == 1) {
     if (stage_ok() && save) {
       const Layer& U = p->layers[p->stages[i].up_layer];
-      *offset = w.duz; *C = U.wgr.N; *L = Ls[i] + U.fwd.taps - 1;
+      *offset = w.duz[i & 1]; *C = U.wgr.N; *L = Ls[i] + U.fwd.taps - 1;
       return 0;
     }
   }
