@@ -137,6 +137,15 @@ int vcd_backward_sliced(vcd_plan* plan, int mode, const float* dy_dev, const flo
  * (train.py:99-100) without a separate scaling pass.  Default 1. */
 int vcd_set_gradient_scale(vcd_plan* plan, float scale);
 
+/* When vcd_backward runs every segment in ONE call (segment_mask = ~0u) the data-gradient chain runs through all stages
+ * while the weight gradients / weight-norm backward of finished segments trail behind it; the library then records one
+ * event per segment ("its gradients are final").  vcd_stream_wait_segment makes `stream` wait for segment `segment`, so a
+ * caller can overlap that segment's gradient all-reduce (the DDP reducer of train.py:99-100) with the rest of backward
+ * without splitting the call.  vcd_segment_events_valid: 1 if the last vcd_backward recorded the events (it does not under
+ * the per-launch profiler or VCD_SERIAL=1). */
+int vcd_segment_events_valid(const vcd_plan* plan);
+int vcd_stream_wait_segment(vcd_plan* plan, int segment, void* stream);
+
 /* Backward segments, in execution order: segment 0 = conv_post + last upsample stage, ...,
  * last segment = conv_pre + cond.  vcd_segment_params lists the parameter indices finalised by a segment. */
 int vcd_num_backward_segments(const vcd_plan* plan);

@@ -118,6 +118,11 @@ struct vcd_plan {
   cudaStream_t aux[kMaxAux] = {};
   cudaStream_t own = nullptr;              // stands in for the legacy default stream (not capturable)
   cudaEvent_t hop_in = nullptr, hop_out = nullptr;
+  // whole-backward mode: "gradients of segment i are final" (recorded inside the captured graph as external events) and
+  // "conv_post's weight gradient is final" (segment 0, outside the graph); valid after a whole-mode vcd_backward
+  cudaEvent_t seg_done[VCD_MAX_UPSAMPLES + 2] = {};
+  cudaEvent_t post_done = nullptr;
+  bool seg_events_valid = false;
   cudaEvent_t events[kMaxEvents] = {};
   int next_event = 0;
 

@@ -94,9 +94,9 @@ inline bool tc_make_rows_map(CUtensorMap* map, const void* base, int B, int C, i
 
 // Epilogue-specialised instantiations of the convolution kernel.  P == nullptr: only raise the dynamic shared
 // memory limit of instantiation `f` (plan creation); otherwise launch it.
-template <int F, int UW = 16, bool LEAN = false>
+template <int F, int UW = 16, bool LEAN = false, bool WG = false>
 inline cudaError_t tc_conv_launch_one(const tc::ConvParams* P, int grid, size_t smem, cudaStream_t stream, bool pdl) {
-  if (!P) return cudaFuncSetAttribute(tc::conv_kernel<F, UW, LEAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (!P) return cudaFuncSetAttribute(tc::conv_kernel<F, UW, LEAN, WG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   // programmatic dependent launch: the prologue (barrier init, TMEM allocation, weight loads) overlaps the tail of the
   // previous kernel of the stream; the kernel's activation / epilogue-operand readers call griddepcontrol.wait
   cudaLaunchConfig_t cfg{};
@@ -109,12 +109,16 @@ inline cudaError_t tc_conv_launch_one(const tc::ConvParams* P, int grid, size_t 
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, tc::conv_kernel<F, UW, LEAN>, *P);
+  return cudaLaunchKernelEx(&cfg, tc::conv_kernel<F, UW, LEAN, WG>, *P);
 }
 // f: epilogue feature set (tc::EPI_*); bit 5 (32) selects the 32-column epilogue units
-constexpr int kUw32 = 32, kLean = 64;
+constexpr int kUw32 = 32, kLean = 64, kWg = 128;   // kWg: fused weight gradient (data-gradient launches, lean + mask staged)
 inline cudaError_t tc_conv_dispatch(int f, const tc::ConvParams* P, int grid, size_t smem, cudaStream_t stream, bool pdl) {
   switch (f) {
+    case kWg | kLean | 17: return tc_conv_launch_one<17, 16, true, true>(P, grid, smem, stream, pdl);
+    case kWg | kLean | 19: return tc_conv_launch_one<19, 16, true, true>(P, grid, smem, stream, pdl);
+    case kWg | kLean | kUw32 | 17: return tc_conv_launch_one<17, 32, true, true>(P, grid, smem, stream, pdl);
+    case kWg | kLean | kUw32 | 19: return tc_conv_launch_one<19, 32, true, true>(P, grid, smem, stream, pdl);
     case kLean | 0: return tc_conv_launch_one<0, 16, true>(P, grid, smem, stream, pdl);
     case kLean | 17: return tc_conv_launch_one<17, 16, true>(P, grid, smem, stream, pdl);
     case kLean | 18: return tc_conv_launch_one<18, 16, true>(P, grid, smem, stream, pdl);
@@ -147,7 +151,7 @@ inline cudaError_t tc_conv_dispatch(int f, const tc::ConvParams* P, int grid, si
 
 inline int tc_plan_init(vcd_plan* p) {
   cudaError_t e = cudaSuccess;
-  for (int f = 0; f < 128 && e == cudaSuccess; ++f) e = tc_conv_dispatch(f, nullptr, 0, 0, 0, false);
+  for (int f = 0; f < 256 && e == cudaSuccess; ++f) e = tc_conv_dispatch(f, nullptr, 0, 0, 0, false);
   if (e != cudaSuccess) return 1;
   e = cudaFuncSetAttribute(tc::wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   if (e != cudaSuccess) return 1;
@@ -158,8 +162,16 @@ inline int tc_plan_init(vcd_plan* p) {
   return 0;
 }
 
+// Request to accumulate the layer's weight (+ bias) gradient inside its data-gradient launch (see ConvParams::wg_*).
+struct WgFuse {
+  float* dwp = nullptr;     // [taps][cin][cout] fp32, zeroed by the caller
+  float* dbias = nullptr;   // [cout] or null
+  bool fused = false;       // out: the launch took it (else the caller runs the weight-gradient kernel)
+};
+
 inline int tc_run_conv(vcd_plan* p, const Layer& L, bool dgrad, const void* in, int B, int Lin, int Lq, int Lout,
-                       const Epilogue& e, cudaStream_t stream, std::atomic<uint64_t>& launches, char* err, size_t errn) {
+                       const Epilogue& e, cudaStream_t stream, std::atomic<uint64_t>& launches, char* err, size_t errn,
+                       WgFuse* wg = nullptr) {
   const ConvGeo& g = dgrad ? L.dgr : L.fwd;
   tc::ConvParams P{};
   P.g = g;
@@ -294,7 +306,7 @@ inline int tc_run_conv(vcd_plan* p, const Layer& L, bool dgrad, const void* in, 
   }
   break;
   }
-  const size_t smem = 128 + P.NA * a_stage + w_region + static_cast<size_t>(P.NE) * P.e_stage_bytes + (2 * P.NA + 16 + 4 + 16) * 8 + 16 + 2 * 128 * 4;
+  size_t smem = 128 + P.NA * a_stage + w_region + static_cast<size_t>(P.NE) * P.e_stage_bytes + (2 * P.NA + 16 + 4 + 16) * 8 + 16 + 2 * 128 * 4;
   if (P.NE > 0) f |= tc::EPI_SMEM;
   // 32-column epilogue units: resident-weight (<= 64-channel) layers whose epilogue has no global operands; both warps
   // of a TMEM lane quadrant need at least one unit per tile
@@ -341,7 +353,35 @@ inline int tc_run_conv(vcd_plan* p, const Layer& L, bool dgrad, const void* in, 
   static const int lean_on = tc_env_int("VCD_CONV_LEAN", 1);
   const bool lean = lean_on && P.w_resident && (f == 0 || f == 17 || f == 18 || f == 19) && g.os == 1 && g.p == 0 && g.creal == g.N &&
                     P.n_tiles_n == 1 && e.bias2 == nullptr && e.zu == 0 && (MT * P.BN) / (uw32 ? 32 : 16) >= 2;
-  const cudaError_t ce = tc_conv_dispatch(f | (uw32 ? kUw32 : 0) | (lean ? kLean : 0), &P, grid, smem, stream,
+  // Fused weight gradient (ConvParams::wg_*): lean data-gradient launch whose staged mask operand IS the layer's forward
+  // input, one 128-row tile per CTA tile, one K block, square <= 64-channel layer, odd tap count (free slot for the bias).
+  bool wg_on = false;
+  P.wg_dwp = nullptr; P.wg_dbias = nullptr; P.wg_r0 = P.wg_rstep = P.wg_rc = 0; P.wg_col0 = 0;
+  static const int wg_env = tc_env_int("VCD_WG_FUSE", 0);   // off: measured slower (see DESIGN.md, round-2 negative results)
+  if (wg != nullptr) wg->fused = false;
+  if (wg != nullptr && wg->dwp != nullptr && wg_env && dgrad && lean && (f & tc::EPI_MASK) && (f & tc::EPI_SMEM) && MT == 1 && P.KB == g.K &&
+      g.K == g.N && g.N == P.BN && g.K <= 64 && (g.taps & 1) && L.tc_ok_wgr) {
+    const ConvGeo& gw = L.wgr;
+    const int r0 = -gw.off0 - g.off0 - P.minshift, rstep = -gw.step, rc = -g.off0 - P.minshift;
+    bool ok = gw.taps == g.taps && gw.K == g.N && gw.N == g.K && gw.is == 1 && gw.os == 1 && rc >= 0 && rc + 128 <= P.RA;
+    for (int j = 0; ok && j < g.taps; ++j) ok = r0 + j * rstep >= 0 && r0 + j * rstep + 128 <= P.RA;
+    const uint32_t col0 = static_cast<uint32_t>(P.acc_bufs * MT * P.BN);
+    const uint32_t need = col0 + static_cast<uint32_t>(((g.taps + 2) / 2) * P.BN);
+    ok = ok && need <= 512 && P.NA * a_stage + w_region >= 8 * 32 * 36 * sizeof(float);   // (write-out scratch aliases the rings)
+    const size_t extra = 2048 + 128 + (g.K < 64 ? 8 * 1024 : 0);   // ones tile; slack: the M = 64 operand over a 32-channel tile
+    ok = ok && smem + extra <= 227 * 1024;
+    if (ok) {
+      wg_on = true;
+      smem += extra;
+      P.wg_dwp = wg->dwp; P.wg_dbias = wg->dbias;
+      P.wg_r0 = r0; P.wg_rstep = rstep; P.wg_rc = rc; P.wg_col0 = col0;
+      uint32_t cols = 32;
+      while (cols < need) cols <<= 1;
+      P.tmem_cols = cols;
+      wg->fused = true;
+    }
+  }
+  const cudaError_t ce = tc_conv_dispatch(f | (uw32 ? kUw32 : 0) | (lean ? kLean : 0) | (wg_on ? kWg : 0), &P, grid, smem, stream,
                                           (pdl_mask & (dgrad ? 2 : 1)) != 0);
   launches.fetch_add(1, std::memory_order_relaxed);
   if (ce != cudaSuccess) {

@@ -238,6 +238,15 @@ struct ConvParams {
   int NE;                 // EPI_SMEM: stages of the epilogue-operand ring (mask / residual tiles fetched by the bulk-copy engine)
   int e_ops;              // operands per stage (mask, residual)
   uint32_t e_stage_bytes; // e_ops * MT * (BN/8) * 128 rows * 16 B
+  // WG instantiations (data-gradient launches of the <= 64-channel ResBlock layers): the layer's WEIGHT gradient is
+  // accumulated by the same CTA.  Both of its operands are already in shared memory -- the gradient tile with its tap
+  // halo (this kernel's A operand) and the layer's forward input (staged as the leaky-ReLU mask operand) -- so the
+  // separate weight-gradient launch and its second pass over the two tensors disappear.
+  float* wg_dwp;          // [taps][cin][cout] fp32 accumulated with reductions (zeroed by the caller)
+  float* wg_dbias;        // [cout] bias gradient (column sums of the gradient tile), or null
+  int wg_r0, wg_rstep;    // row of the A region that pairs with input row 0 of the tile for tap 0, and its step per tap
+  int wg_rc;              // row of the A region that is output row 0 of the tile (bias gradient)
+  uint32_t wg_col0;       // first TMEM column of the weight-gradient accumulators
   unsigned long long* trace;  // debug: %globaltimer stamps of CTA 0 (null = off)
 };
 
@@ -354,9 +363,10 @@ __device__ __forceinline__ void epi_finish(const Epilogue& e, const ConvGeo& g, 
 // whose long dependent chains (~100 UIMAD / USEL / LDCU per unit) cost more than the arithmetic of a 128 x 32 tile
 // (in-kernel trace: 0.67 us per tile of which 0.13 us MMA).  Here the tile walk is incremental (b, row group advance by
 // the grid stride), offsets are one IMAD per unit, and a warp sweeps all its units of a tile in one straight loop.
-template <int F, int UW = 16, bool LEAN = false>
+template <int F, int UW = 16, bool LEAN = false, bool WG = false>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_kernel(const ConvParams P) {
+  static_assert(!WG || (LEAN && (F & EPI_SMEM) && (F & EPI_MASK)), "WG rides on the lean, smem-staged data-gradient epilogues");
   extern __shared__ __align__(128) uint8_t smem_raw[];
   // shfl-broadcast warp index: provably warp-uniform, so role branches are uniform and the compiler may use the
   // uniform datapath (UR registers) for descriptor / address arithmetic inside them
@@ -385,13 +395,20 @@ conv_kernel(const ConvParams P) {
   uint64_t* emptyE = fullE + 8;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(emptyE + 8);
   float* bias_s = reinterpret_cast<float*>(tmem_slot + 4);   // [2][128]: per-tile bias (+ per-batch bias), double-buffered
+  // WG: [8 channel groups][16 rows][16 B] of bf16 ones -- the A operand whose product with the gradient tile is its column sum
+  uint8_t* ones_s = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(bias_s + 256) + 127) & ~uintptr_t(127));
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < P.NA; ++i) { mbar_init(&fullA[i], 1); mbar_init(&emptyA[i], 1); }
     for (int i = 0; i < 8; ++i) { mbar_init(&fullW[i], 1); mbar_init(&emptyW[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 8); }
-    for (int i = 0; i < 8; ++i) { mbar_init(&fullE[i], 1); mbar_init(&emptyE[i], 8); }
+    for (int i = 0; i < 8; ++i) { mbar_init(&fullE[i], 1); mbar_init(&emptyE[i], WG ? 9 : 8); }   // WG: + the MMA warp's commit
     fence_barrier_init();
+  }
+  if constexpr (WG) {
+    if (threadIdx.x >= 64 && threadIdx.x < 64 + 128)
+      reinterpret_cast<uint4*>(ones_s)[threadIdx.x - 64] = make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);
+    fence_proxy_async();
   }
   if (warp == 1) tmem_alloc(tmem_slot, P.tmem_cols);
   tc_fence_before();
@@ -612,11 +629,61 @@ conv_kernel(const ConvParams P) {
               pw.advance(P.NW);
             }
           }
-          if (elect_one()) umma_commit(&emptyA[pa.stage]);
+          if constexpr (WG) {
+            // (host: one K block, one 128-row tile per CTA tile)  The epilogue may start on the data gradient now; the
+            // weight-gradient MMAs of this tile follow in the tensor pipe.
+            if (elect_one()) umma_commit(&acc_full[buf]);
+            const int es = it % P.NE;
+            mbar_wait(&fullE[es], static_cast<uint32_t>(it / P.NE) & 1u);
+            tc_fence_after();
+            // MN-major operands (time rows are the contraction): A = the layer's forward input [cin][rows] from the staged
+            // mask operand ([group][128 rows][16 B]), B = the gradient tile [cout][rows] from the activation ring, displaced
+            // by the tap.  M = 64: accumulator slots pair up on the lane halves of a column block (see wgrad_kernel).
+            const uint32_t idesc_w = make_idesc(64, P.g.K, 1, 1);   // (host: K == N == BN <= 64)
+            const uint64_t x_desc = make_desc(smem_u32(e_smem + static_cast<size_t>(es) * P.e_stage_bytes), 128, 2048);
+            const uint64_t g_desc = make_desc(smem_u32(a_smem + static_cast<size_t>(pa.stage) * a_stage_bytes), 128, a_lbo);
+            const uint32_t x_lo = static_cast<uint32_t>(x_desc), x_hi = static_cast<uint32_t>(x_desc >> 32);
+            const uint32_t g_hi = static_cast<uint32_t>(g_desc >> 32);
+            const uint32_t acc0 = it != 0 ? 1u : 0u;
+            uint32_t g_lo = static_cast<uint32_t>(g_desc) + static_cast<uint32_t>(P.wg_r0);
+            const uint32_t wg_base = tmem_base + P.wg_col0;
+#pragma unroll 1
+            for (int j = 0; j < taps; ++j) {
+              const uint32_t d_w = wg_base + static_cast<uint32_t>((j >> 1) * P.BN) + (static_cast<uint32_t>((j & 1) * 16) << 16);
+              if (elect_one()) {
+#pragma unroll
+                for (int kk = 0; kk < 8; ++kk)
+                  umma_bf16_split(d_w, x_lo + 16u * kk, x_hi, g_lo + 16u * kk, g_hi, idesc_w, kk == 0 ? acc0 : 1u);
+              }
+              g_lo += static_cast<uint32_t>(P.wg_rstep);
+            }
+            if (P.wg_dbias != nullptr) {   // bias gradient: ones x gradient tile -> column sums in slot `taps` (taps is odd: a free lane half)
+              const uint32_t d_b = wg_base + static_cast<uint32_t>((taps >> 1) * P.BN) + (static_cast<uint32_t>((taps & 1) * 16) << 16);
+              const uint64_t o_desc = make_desc(smem_u32(ones_s), 128, 256);
+              const uint32_t gb_lo = static_cast<uint32_t>(g_desc) + static_cast<uint32_t>(P.wg_rc);
+              if (elect_one()) {
+#pragma unroll
+                for (int kk = 0; kk < 8; ++kk)
+                  umma_bf16_split(d_b, static_cast<uint32_t>(o_desc), static_cast<uint32_t>(o_desc >> 32), gb_lo + 16u * kk, g_hi, idesc_w,
+                                  kk == 0 ? acc0 : 1u);
+              }
+            }
+            if (elect_one()) {
+              umma_commit(&emptyE[es]);
+              umma_commit(&emptyA[pa.stage]);
+            }
+          } else {
+            if (elect_one()) umma_commit(&emptyA[pa.stage]);
+          }
           pa.advance(P.NA);
         }
-        if (elect_one()) umma_commit(&acc_full[buf]);
+        if constexpr (!WG) {
+          if (elect_one()) umma_commit(&acc_full[buf]);
+        }
         if (it < 4 && lane == 0) ktrace(P.trace, 8 + it);       // MMAs of tile `it` issued
+      }
+      if constexpr (WG) {
+        if (elect_one()) umma_commit(&fullW[1]);   // every weight-gradient MMA of this CTA has completed
       }
     };
     using std::integral_constant;
@@ -715,6 +782,60 @@ conv_kernel(const ConvParams P) {
         }
         mg += grid;
         while (mg >= P.n_mgroups) { mg -= P.n_mgroups; ++b; }
+      }
+      if constexpr (WG) {
+        // ---- weight-gradient accumulators -> global (fp32 reductions; the CTAs of the launch hold partial sums) ----
+        // Slot s (tap s; slot `taps` = bias gradient) lives at columns (s >> 1) * BN, lanes +16 * (s & 1) of every quadrant;
+        // row i of the 64-row D: lane i % 16 of quadrant i / 16.  Each 32-lane x 32-column block is transposed through a
+        // per-warp scratch (the drained activation ring) so one red.v4 covers 4 rows x 128 contiguous bytes.
+        mbar_wait(&fullW[1], 0);
+        tc_fence_after();
+        asm volatile("bar.sync 2, 256;" ::: "memory");   // every epilogue warp is done with the rings before they become scratch
+        float* scratch = reinterpret_cast<float*>(a_smem) + (warp - 2) * (32 * 36);
+        const int taps = P.g.taps;
+        const int nslots = taps + (P.wg_dbias != nullptr ? 1 : 0);
+        const int passes = (nslots + 1) >> 1;
+        const int K = P.g.N, N = P.g.K;   // weight gradient [tap][cin = this launch's output channels][cout = its contraction]
+        for (int ps = half; ps < passes; ps += 2) {
+          const int slot = 2 * ps + (lane >> 4);
+          const int row = quad * 16 + (lane & 15);
+          bool active = false;
+          const float* row_dst = P.wg_dwp;
+          if (slot < taps) {
+            active = row < K;
+            row_dst = P.wg_dwp + (static_cast<size_t>(slot) * K + (active ? row : 0)) * N;
+          } else if (slot == taps && P.wg_dbias != nullptr) {
+            active = row == 0;
+            row_dst = P.wg_dbias;
+          }
+          const unsigned long long row_ptr = reinterpret_cast<unsigned long long>(row_dst);
+          for (int c32 = 0; c32 < N / 32; ++c32) {
+            float acc[32];
+            tmem_ld32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + P.wg_col0 + static_cast<uint32_t>(ps * N + c32 * 32), acc);
+#pragma unroll
+            for (int n = 0; n < 32; n += 4)
+              *reinterpret_cast<float4*>(scratch + lane * 36 + n) = make_float4(acc[n], acc[n + 1], acc[n + 2], acc[n + 3]);
+            __syncwarp();
+            float4 v[8];
+            unsigned long long base[8];
+            int act[8];
+#pragma unroll
+            for (int i8 = 0; i8 < 8; ++i8) {
+              const int r = i8 * 4 + (lane >> 3);
+              v[i8] = *reinterpret_cast<const float4*>(scratch + r * 36 + (lane & 7) * 4);
+              base[i8] = __shfl_sync(0xffffffffu, row_ptr, r);
+              act[i8] = __shfl_sync(0xffffffffu, active ? 1 : 0, r);
+            }
+#pragma unroll
+            for (int i8 = 0; i8 < 8; ++i8) {
+              float* dst = reinterpret_cast<float*>(base[i8]) + c32 * 32 + (lane & 7) * 4;
+              if (act[i8])
+                asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v[i8].x), "f"(v[i8].y),
+                             "f"(v[i8].z), "f"(v[i8].w) : "memory");
+            }
+            __syncwarp();
+          }
+        }
       }
     }
   } else if (warp >= 2 && warp <= 9) {

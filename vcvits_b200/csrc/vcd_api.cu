@@ -518,6 +518,8 @@ extern "C" int vcd_plan_create(const vcd_config* cfg, vcd_plan** out_plan) {
   CU_TRY(cudaStreamCreateWithFlags(&p->own, cudaStreamNonBlocking));
   CU_TRY(cudaEventCreateWithFlags(&p->hop_in, cudaEventDisableTiming));
   CU_TRY(cudaEventCreateWithFlags(&p->hop_out, cudaEventDisableTiming));
+  for (auto& ev : p->seg_done) CU_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  CU_TRY(cudaEventCreateWithFlags(&p->post_done, cudaEventDisableTiming));
   for (int i = 0; i < vcd_plan::kMaxEvents; ++i) CU_TRY(cudaEventCreateWithFlags(&p->events[i], cudaEventDisableTiming));
   TRY(tc_plan_init(p));
   *out_plan = p;
@@ -536,6 +538,8 @@ extern "C" void vcd_plan_destroy(vcd_plan* p) {
   if (p->own) cudaStreamDestroy(p->own);
   if (p->hop_in) cudaEventDestroy(p->hop_in);
   if (p->hop_out) cudaEventDestroy(p->hop_out);
+  for (auto& ev : p->seg_done) if (ev) cudaEventDestroy(ev);
+  if (p->post_done) cudaEventDestroy(p->post_done);
   for (int i = 0; i < vcd_plan::kMaxAux; ++i) if (p->aux[i]) cudaStreamDestroy(p->aux[i]);
   for (int i = 0; i < vcd_plan::kMaxEvents; ++i) if (p->events[i]) cudaEventDestroy(p->events[i]);
   delete p;
@@ -855,14 +859,19 @@ double layer_flops(const Layer& L, int B, int Lfwd_in) {
 
 // One convolution (forward or data-gradient direction) of layer L on stream st.
 int run_conv(const Ctx& c, cudaStream_t st, const Layer& L, bool dgrad, const void* in, int Lin, int Lq, int Lout,
-             Epilogue e, double flops) {
+             Epilogue e, double flops, WgFuse* wg = nullptr) {
   const ConvGeo& g = dgrad ? L.dgr : L.fwd;
   // timing experiments only (results are wrong): bit 0 skips forward, bit 1 data-gradient, bit 2 weight-gradient launches
   static const int dbg_skip = tc_env_int("VCD_DEBUG_SKIP", 0);
   if (dbg_skip & (dgrad ? 2 : 1)) return 0;
   if (c.mode == VCD_MODE_BF16 && (dgrad ? L.tc_ok_dgr : L.tc_ok_fwd)) {
     ProfScope ps__(PC_TC_CONV, flops, 0, st, (L.name + (dgrad ? ":dgrad" : ":fwd")).c_str());
-    return tc_run_conv(c.p, L, dgrad, in, c.B, Lin, Lq, Lout, e, st, g_launches, g_err, sizeof(g_err));
+    const int rc = tc_run_conv(c.p, L, dgrad, in, c.B, Lin, Lq, Lout, e, st, g_launches, g_err, sizeof(g_err), wg);
+    if (wg && wg->fused && ps__.on) {   // the launch also produced the weight gradient: twice the algorithmic FLOPs
+      g_prof.back().flops *= 2.0;
+      g_prof.back().tag += "+wgrad";
+    }
+    return rc;
   }
   const float* w = c.p->d_f32 + (dgrad ? L.f32_dgr : L.f32_fwd);
   const std::string tag = L.name + (dgrad ? ":dgrad" : ":fwd");
@@ -1270,6 +1279,14 @@ static int backward_impl(vcd_plan* p, int mode, const float* dy, const float* y,
       if (!c.serial) { c.wait(s, ready); side_used[k] = true; }
       return s;
     };
+    auto wg_request = [&](const Layer& Lx) {
+      WgFuse r;
+      if (c.mode == VCD_MODE_BF16 && Lx.tc_ok_wgr && Lx.tc_ok_dgr) {
+        r.dwp = p->d_gscratch + Lx.dwp;
+        r.dbias = Lx.dbias >= 0 ? p->d_gscratch + Lx.dbias : nullptr;
+      }
+      return r;
+    };
     // whole mode: this segment reuses the gradient workspaces of segment seg-2, whose weight gradients may still trail
     if (whole && seg >= 2 && join_ev[seg - 2]) c.wait(stream, join_ev[seg - 2]);
     if (seg < S) {
@@ -1296,17 +1313,20 @@ static int backward_impl(vcd_plan* p, int mode, const float* dy, const float* y,
           cudaEvent_t ev_first = ev_cur;
           if (p->cfg.resblock == 1) {
             const Layer& L2 = p->layers[sd.convs[j][q][1]];
-            TRY(run_wgrad(c, side_after(ev_cur), L2, P(sw.ma[j][q]), Gt_cur, L, L, layer_flops(L2, B, L)));
             Epilogue e = epi();
             e.mask = P(sw.ma[j][q]);
             e.mask_slope = kSlope;
             e.out_t = P(w.dm[i & 1][j][q]);
-            TRY(run_conv(c, sjs, L2, true, Gt_cur, L, L, L, e, layer_flops(L2, B, L)));
+            // the weight gradient rides in the data-gradient launch when it can (its `in` operand is the mask operand)
+            WgFuse wg2 = wg_request(L2);
+            TRY(run_conv(c, sjs, L2, true, Gt_cur, L, L, L, e, layer_flops(L2, B, L), wg2.dwp ? &wg2 : nullptr));
+            if (!wg2.fused) TRY(run_wgrad(c, side_after(ev_cur), L2, P(sw.ma[j][q]), Gt_cur, L, L, layer_flops(L2, B, L)));
             d_first = P(w.dm[i & 1][j][q]);
             ev_first = c.serial ? nullptr : c.record(sjs);
           }
           const Layer& L1 = p->layers[sd.convs[j][q][0]];
-          TRY(run_wgrad(c, side_after(ev_first), L1, in_first, d_first, L, L, layer_flops(L1, B, L), q == 0 && j == NB - 1));
+          // (the first conv of a branch joins the running sum over branches: its epilogue is not a lean one, no fusion)
+          WgFuse wg1 = q > 0 ? wg_request(L1) : WgFuse{};
           Epilogue e = epi();
           e.mask = in_first;
           e.mask_slope = kSlope;
@@ -1326,7 +1346,9 @@ static int backward_impl(vcd_plan* p, int mode, const float* dy, const float* y,
               e.zu = sd.u; e.zp = U.pad; e.zLq = Lz;
             }
           }
-          TRY(run_conv(c, sjs, L1, true, d_first, L, L, L, e, layer_flops(L1, B, L)));
+          TRY(run_conv(c, sjs, L1, true, d_first, L, L, L, e, layer_flops(L1, B, L), wg1.dwp ? &wg1 : nullptr));
+          if (!wg1.fused)
+            TRY(run_wgrad(c, side_after(ev_first), L1, in_first, d_first, L, L, layer_flops(L1, B, L), q == 0 && j == NB - 1));
           if (!c.serial) {
             if (q > 0) ev_cur = c.record(sjs);
             else prev_final = c.record(sjs);
@@ -1385,6 +1407,11 @@ static int backward_impl(vcd_plan* p, int mode, const float* dy, const float* y,
                                                                        p->d_dparams, p->d_norms, p->d_gscratch, sj.lead_blocks, p->grad_scale);
       LAUNCH_CHECK("wn_unfold_kernel");
     }
+    if (whole) {   // gradients of this segment are final: visible to streams outside the captured graph
+      cudaStreamCaptureStatus cst = cudaStreamCaptureStatusNone;
+      cudaStreamIsCapturing(fst, &cst);
+      CU_TRY(cudaEventRecordWithFlags(p->seg_done[seg], fst, cst == cudaStreamCaptureStatusActive ? cudaEventRecordExternal : cudaEventRecordDefault));
+    }
     return 0;
   };
   auto post_part = [&](int seg) -> int {
@@ -1436,10 +1463,18 @@ static int backward_impl(vcd_plan* p, int mode, const float* dy, const float* y,
         return 0;
       }));
     }
-    if (post_forked) c.order(wst, stream);
+    if (post_forked) {
+      CU_TRY(cudaEventRecord(p->post_done, wst));
+      CU_TRY(cudaStreamWaitEvent(stream, p->post_done, 0));
+    } else {
+      CU_TRY(cudaEventRecord(p->post_done, stream));
+    }
     TRY(post_part(S));
+    CU_TRY(cudaEventRecord(p->seg_done[S], stream));   // the last segment's gradients include the kernels outside the graph
+    p->seg_events_valid = true;
     return 0;
   }
+  p->seg_events_valid = false;
   bool first_seg = true;
   for (int seg = 0; seg <= S; ++seg) {
     if (!(segment_mask & (1u << seg))) continue;
@@ -1562,6 +1597,19 @@ extern "C" int vcd_debug_ws_tensor(const vcd_plan* p, int mode, int B, int T, in
 extern "C" int vcd_set_gradient_scale(vcd_plan* p, float scale) {
   if (!p) return fail("vcd_set_gradient_scale: null plan");
   p->grad_scale = scale;
+  return 0;
+}
+
+// Whole-backward mode (vcd_backward with every segment requested, outside profiling): the gradients of segment `seg`
+// become final while later segments still run.  Makes `stream` wait for them (the caller then issues that segment's
+// gradient all-reduce on it).  vcd_segment_events_valid: 1 if the last vcd_backward recorded these events.
+extern "C" int vcd_segment_events_valid(const vcd_plan* p) { return p && p->seg_events_valid ? 1 : 0; }
+extern "C" int vcd_stream_wait_segment(vcd_plan* p, int seg, void* stream_) {
+  if (!p || seg < 0 || seg >= static_cast<int>(p->segments.size())) return fail("vcd_stream_wait_segment: bad plan or segment");
+  if (!p->seg_events_valid) return fail("vcd_stream_wait_segment: the last vcd_backward did not run in whole-backward mode");
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  CU_TRY(cudaStreamWaitEvent(st, p->seg_done[seg], 0));
+  if (seg == 0) CU_TRY(cudaStreamWaitEvent(st, p->post_done, 0));
   return 0;
 }
 

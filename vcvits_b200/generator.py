@@ -206,12 +206,20 @@ class _DecoderFunction(torch.autograd.Function):
         if module._grad_sync_group is None or world == 1:
             run(0xFFFFFFFF)
         else:
+            # ONE library call; the gradients of a segment are final (library event) while later segments still run: its
+            # all-reduce is issued behind that event on a side stream and overlaps the rest of backward (replaces the
+            # DDP reducer implied by train.py:99-100)
             reducer = SegmentReducer(flat, module._segment_ranges, module._grad_sync_group, prescaled=True)
-            for seg in range(module._num_segments):
-                run(1 << seg)
-                # gradients of this segment are final: all-reduce them on NCCL's stream while the next segment's
-                # kernels run (replaces the DDP reducer implied by train.py:99-100)
-                reducer.segment_done(seg)
+            run(0xFFFFFFFF)
+            if lib.vcd_segment_events_valid(plan):
+                comm = module._comm_stream(dev)
+                for seg in range(module._num_segments):
+                    _lib.check(lib.vcd_stream_wait_segment(plan, seg, comm.cuda_stream), "vcd_stream_wait_segment")
+                    with torch.cuda.stream(comm):
+                        reducer.segment_done(seg)
+            else:   # profiler / serial mode: everything is already enqueued in order on this stream
+                for seg in range(module._num_segments):
+                    reducer.segment_done(seg)
             reducer.finish()
         module._give_workspace(ctx.ws)
         ctx.ws = None
@@ -315,6 +323,7 @@ class Generator(nn.Module):
         # autograd leaves of this call (``torch.autograd.grad`` w.r.t. parameters, DistributedDataParallel hooks).
         self.fused_param_grads = True
         self._anchors = {}
+        self._comm_streams = {}
         self._grad_templates = None
         self._call_params = None
         self._names: Optional[List[str]] = None
@@ -479,6 +488,12 @@ class Generator(nn.Module):
         pieces = torch._C._nn.unflatten_dense_tensors(flat, self._grad_templates)
         return [pieces[k] for k, _ in self._flat_index]
 
+    def _comm_stream(self, device: torch.device) -> torch.cuda.Stream:
+        st = self._comm_streams.get(device)
+        if st is None:
+            st = self._comm_streams[device] = torch.cuda.Stream(device=device)
+        return st
+
     def _anchor_for(self, device: torch.device) -> torch.Tensor:
         a = self._anchors.get(device)
         if a is None:
@@ -624,6 +639,7 @@ class Generator(nn.Module):
         state["_ws_cache"] = {}
         state["_ws_pool"] = {}
         state["_anchors"] = {}
+        state["_comm_streams"] = {}
         state["_call_params"] = None
         state["_grad_templates"] = None
         state["_fold_key"] = None
