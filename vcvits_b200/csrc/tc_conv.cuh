@@ -9,6 +9,7 @@
 
 #include "plan.h"
 #include "tc_kernels.cuh"
+#include "tc_pair.cuh"
 
 namespace vcd {
 
@@ -154,6 +155,10 @@ inline int tc_plan_init(vcd_plan* p) {
   for (int f = 0; f < 256 && e == cudaSuccess; ++f) e = tc_conv_dispatch(f, nullptr, 0, 0, 0, false);
   if (e != cudaSuccess) return 1;
   e = cudaFuncSetAttribute(tc::wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (e != cudaSuccess) return 1;
+  e = cudaFuncSetAttribute(tc::pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (e != cudaSuccess) return 1;
+  e = cudaFuncSetAttribute(tc::pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   if (e != cudaSuccess) return 1;
   if (getenv("VCD_KTRACE")) {
     if (cudaMalloc(&p->d_trace, 64 * sizeof(unsigned long long)) != cudaSuccess) return 1;
@@ -386,6 +391,89 @@ inline int tc_run_conv(vcd_plan* p, const Layer& L, bool dgrad, const void* in, 
   launches.fetch_add(1, std::memory_order_relaxed);
   if (ce != cudaSuccess) {
     snprintf(err, errn, "launch of tc::conv_kernel(%s) failed: %s", L.name.c_str(), cudaGetErrorString(ce));
+    return 1;
+  }
+  return 0;
+}
+
+// Shared-memory bytes of the fused pair kernel for (C, taps, dil) with an NA-deep activation ring; 0 = not eligible.
+inline size_t tc_pair_smem(int C, int taps, int dil, int NA, int MT = 1) {
+  const int h1 = dil * (taps - 1) / 2;
+  const int RA = (MT * 128 + 2 * h1 + 7) / 8 * 8;
+  const size_t a_stage = static_cast<size_t>(C / 8) * RA * 16, w = static_cast<size_t>(taps) * (C / 8) * C * 16;
+  const size_t mid = static_cast<size_t>(C / 8) * (MT * 128 + tc::kMidSlack) * 16;
+  return 128 + NA * a_stage + 2 * w + 2 * mid + 32 * 8 + 16 + 2 * 64 * 4 + 128;
+}
+
+// Can the pair (L1 = dilated c1, L2 = c2 with dilation 1) of a ResBlock1 run as ONE fused forward launch?
+inline bool tc_pair_ok(const Layer& L1, const Layer& L2) {
+  static const int on = tc_env_int("VCD_PAIR", 1);
+  if (!on || !L1.tc_ok_fwd || !L2.tc_ok_fwd) return false;
+  if (L1.kind != LK_CONV || L2.kind != LK_CONV) return false;
+  const int C = L1.cin;
+  if (!(C == 32 || C == 64) || L1.cout != C || L2.cin != C || L2.cout != C) return false;
+  if (L1.k != L2.k || !(L1.k & 1) || L1.k < 3 || L1.k > 11 || L2.dil != 1 || L1.dil < 1) return false;
+  if (L1.p_b < 0 || L2.p_b < 0) return false;
+  const int h1 = L1.dil * (L1.k - 1) / 2, h2 = (L1.k - 1) / 2;
+  if (h1 + h2 > kPadL || 128 + h1 + h2 + 8 > kPadR) return false;   // the tile halo must stay inside the zero pads
+  if (L1.nt_fwd != C || L2.nt_fwd != C) return false;               // packed as one column tile: [tap][C/8][C][8]
+  return tc_pair_smem(C, L1.k, L1.dil, 2) <= 227 * 1024;
+}
+
+inline int tc_run_pair(vcd_plan* p, const Layer& L1, const Layer& L2, const void* in, void* mid_out, void* out, const float* bias1,
+                       const float* bias2, int B, int Lrows, float act_slope, float res_inv, cudaStream_t stream,
+                       std::atomic<uint64_t>& launches, char* err, size_t errn) {
+  tc::PairParams P{};
+  P.in = static_cast<const bf16*>(in);
+  P.w1 = p->d_bf16 + L1.tc_fwd;
+  P.w2 = p->d_bf16 + L2.tc_fwd;
+  P.bias1 = bias1; P.bias2 = bias2;
+  P.mid_out = static_cast<bf16*>(mid_out);
+  P.out = static_cast<bf16*>(out);
+  P.B = B; P.L = Lrows; P.C = L1.cin; P.taps = L1.k; P.dil = L1.dil;
+  P.h1 = L1.dil * (L1.k - 1) / 2; P.h2 = (L1.k - 1) / 2;
+  // MT 128-row MMA tiles per CTA tile: the largest that fits TMEM (4 * MT * C columns) and shared memory (two
+  // activation stages at least) while every SM still gets a few CTA tiles
+  static const int mt_env = tc_env_int("VCD_PAIR_MT", 0), na_want = tc_env_int("VCD_PAIR_NA", 3);
+  P.MT = 1;
+  for (int mt : {4, 2}) {
+    if (mt_env > 0 && mt != mt_env) continue;
+    if (4 * mt * P.C > 512 || tc_pair_smem(P.C, P.taps, P.dil, 2, mt) > 220 * 1024) continue;
+    const long long tiles = 1LL * B * ((Lrows + mt * 128 - P.taps) / (mt * 128 - (P.taps - 1)));
+    if (mt_env == 0 && tiles < 3LL * p->num_sms) continue;
+    P.MT = mt;
+    break;
+  }
+  P.R = P.MT * 128 - (L1.k - 1);
+  P.RA = (P.MT * 128 + 2 * P.h1 + 7) / 8 * 8;
+  P.NA = na_want < 2 ? 2 : (na_want > 8 ? 8 : na_want);
+  while (P.NA > 2 && tc_pair_smem(P.C, P.taps, P.dil, P.NA, P.MT) > 220 * 1024) --P.NA;
+  const size_t smem = tc_pair_smem(P.C, P.taps, P.dil, P.NA, P.MT);
+  if (smem > 227 * 1024) { snprintf(err, errn, "tc_run_pair(%s): shared memory budget exceeded", L1.name.c_str()); return 1; }
+  P.tiles_per_item = (Lrows + P.R - 1) / P.R;
+  P.total_tiles = P.tiles_per_item * B;
+  P.d_tiles.init(P.tiles_per_item);
+  P.act_slope = act_slope; P.res_inv = res_inv;
+  uint32_t cols = 32;
+  while (cols < static_cast<uint32_t>(4 * P.MT * P.C)) cols <<= 1;
+  P.tmem_cols = cols;
+  if (blk_elems(B, P.C, Lrows) >= (1ull << 31)) { snprintf(err, errn, "tc_run_pair(%s): tensor too large", L1.name.c_str()); return 1; }
+  const int grid = P.total_tiles < p->num_sms ? P.total_tiles : p->num_sms;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(static_cast<unsigned>(grid));
+  cfg.blockDim = dim3(tc::kPairThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  static const int pdl_mask = tc_env_int("VCD_PDL", 1);
+  cfg.numAttrs = (pdl_mask & 1) ? 1 : 0;
+  const cudaError_t ce = mid_out ? cudaLaunchKernelEx(&cfg, tc::pair_kernel<true>, P) : cudaLaunchKernelEx(&cfg, tc::pair_kernel<false>, P);
+  launches.fetch_add(1, std::memory_order_relaxed);
+  if (ce != cudaSuccess) {
+    snprintf(err, errn, "launch of tc::pair_kernel(%s) failed: %s", L1.name.c_str(), cudaGetErrorString(ce));
     return 1;
   }
   return 0;

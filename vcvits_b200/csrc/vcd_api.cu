@@ -1094,12 +1094,26 @@ static int forward_impl(vcd_plan* p, int mode, const float* x, int64_t xs_b, int
     // ResBlock branches run concurrently; the running sum over branches chains their last convolutions
     for (int j = 1; j < NB; ++j) c.order(stream, c.branch(j));
     cudaEvent_t prev_last = nullptr;
+    static const int dbg_skip_fwd = tc_env_int("VCD_DEBUG_SKIP", 0) & 1;
+    const bool pair_off = dbg_skip_fwd != 0;
     for (int j = 0; j < NB; ++j) {
       cudaStream_t sj = c.branch(j);
       const void* xin_t = P(sw.ua);
       for (int q = 0; q < npairs; ++q) {
         const bool last = q == npairs - 1;
         const void* conv_in = xin_t;
+        // <= 64-channel stages: both convolutions of a non-final pair in ONE launch (tc_pair.cuh); the final pair joins
+        // the running sum over branches and keeps its own epilogues
+        if (p->cfg.resblock == 1 && !last && mode == VCD_MODE_BF16 && !pair_off &&
+            tc_pair_ok(p->layers[sd.convs[j][q][0]], p->layers[sd.convs[j][q][1]])) {
+          const Layer& L1 = p->layers[sd.convs[j][q][0]];
+          const Layer& L2 = p->layers[sd.convs[j][q][1]];
+          ProfScope ps__(PC_TC_CONV, layer_flops(L1, B, Lcur) + layer_flops(L2, B, Lcur), 0, sj, (L1.name + "+" + L2.name + ":fwd").c_str());
+          TRY(tc_run_pair(p, L1, L2, xin_t, save ? P(sw.ma[j][q]) : nullptr, P(sw.xa[j][q]), p->h_params[L1.p_b], p->h_params[L2.p_b], B, Lcur,
+                          kSlope, kInvSlope, sj, g_launches, g_err, sizeof(g_err)));
+          xin_t = P(sw.xa[j][q]);
+          continue;
+        }
         if (p->cfg.resblock == 1) {
           const Layer& L1 = p->layers[sd.convs[j][q][0]];
           Epilogue e = epi();
