@@ -287,3 +287,31 @@ def test_many_distinct_shapes_recycle_the_graph_cache():
             again = m(xs[T], g)
             assert torch.equal(again, first[T]), T
     torch.cuda.synchronize()
+
+
+def test_batch_split_invariance_base_config_bf16():
+    """The decoder has no cross-sample operation (modules.py:203-216): one B=6 step must equal two B=3 steps on the same
+    utterances -- the waveform and dz bit for bit (no kernel's arithmetic may depend on the batch position of a tile),
+    parameter gradients up to the fp32 summation order of the weight-gradient partials."""
+    from vcvits_b200 import Generator
+    torch.manual_seed(11)
+    m = Generator(**O.BASE_CFG, mode="bf16").cuda()
+    gen = torch.Generator().manual_seed(3)
+    xs = torch.randn(6, 256, 20, generator=gen).cuda()
+    gs = torch.randn(6, 256, 1, generator=gen).cuda()
+    dys = torch.randn(6, 1, 20 * m.hop, generator=gen).cuda()
+
+    def step(sl):
+        m.zero_grad(set_to_none=True)
+        x = xs[sl].clone().requires_grad_(True)
+        y = m(x, gs[sl])
+        y.backward(dys[sl])
+        return y.detach().clone(), x.grad.clone(), [p.grad.double().clone() for p in m.parameters()]
+
+    yf, dxf, gf = step(slice(0, 6))
+    ya, dxa, ga = step(slice(0, 3))
+    yb, dxb, gb = step(slice(3, 6))
+    assert torch.equal(yf, torch.cat([ya, yb]))
+    assert torch.equal(dxf, torch.cat([dxa, dxb]))
+    for f, a, b in zip(gf, ga, gb):
+        assert float((a + b - f).norm()) <= 2e-5 * float(f.norm()) + 1e-12

@@ -45,4 +45,9 @@ num = den = 0.0
 for (n, p), (_, q) in zip(m.named_parameters(), single.named_parameters()):
     num += float((p.grad * world - q.grad).double().pow(2).sum()); den += float(q.grad.double().pow(2).sum())
 log("DDP vs single-GPU gradient rel-l2:", (num / den) ** 0.5)
+worst = sorted(((float((p.grad * world - q.grad).double().norm() / (q.grad.double().norm() + 1e-30)), n)
+                for (n, p), (_, q) in zip(m.named_parameters(), single.named_parameters())), reverse=True)[:8]
+if rank == 0:
+    for e, n in worst:
+        log(f"  {n:40s} rel-l2 {e:.3e}")
 dist.destroy_process_group()
