@@ -366,43 +366,55 @@ class Bench:
         return classes
 
     def rooflines(self, classes, workload):
+        """Per kernel class: the roofline that bounds it follows from its arithmetic intensity (algorithmic FLOPs / algorithmic
+        bytes, both accumulated per launch by the library) against the ridge of the MEASURED peaks (sustained bf16 / copy
+        bandwidth, MEASURED_PEAKS.json).  The headline `roofline` is the class with the largest share of the step."""
         peaks = self.peaks
+        ridge = peaks["bf16_sustained"] * 1e12 / (peaks["hbm"] * 1e9)    # FLOP per byte
         total_ms = sum(c["ms_per_step"] for c in classes)
         per_class = []
         for c in classes:
-            if c["class"].startswith("tc_") and c["gflop_per_step"] > 0:
-                per_class.append({"class": c["class"], "bound": "tensor", "achieved": c["tflops"], "peak": peaks["bf16_sustained"],
-                                  "unit": "TFLOP/s", "frac": c["tflops"] / peaks["bf16_sustained"],
-                                  "avg_launch_us": c["ms_per_step"] / c["launches_per_step"] * 1e3,
-                                  "share_of_step": c["ms_per_step"] / total_ms})
-            elif c["gbyte_per_step"] > 0:
-                per_class.append({"class": c["class"], "bound": "hbm", "achieved": c["gbs"], "peak": peaks["hbm"], "unit": "GB/s",
-                                  "frac": c["gbs"] / peaks["hbm"],
-                                  "avg_launch_us": c["ms_per_step"] / c["launches_per_step"] * 1e3,
-                                  "share_of_step": c["ms_per_step"] / total_ms})
-        tcs = [c for c in classes if c["class"].startswith("tc_")]
-        if not tcs:
+            if c["ms_per_step"] <= 0 or (c["gflop_per_step"] <= 0 and c["gbyte_per_step"] <= 0):
+                continue
+            ai = c["gflop_per_step"] / c["gbyte_per_step"] if c["gbyte_per_step"] > 0 else float("inf")
+            rec = {"class": c["class"], "flop_per_byte": None if ai == float("inf") else ai,
+                   "avg_launch_us": c["ms_per_step"] / c["launches_per_step"] * 1e3, "share_of_step": c["ms_per_step"] / total_ms,
+                   "launches_per_step": c["launches_per_step"]}
+            if c["gflop_per_step"] > 0 and ai >= ridge:
+                rec.update({"bound": "tensor", "achieved": c["tflops"], "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
+                            "frac": c["tflops"] / peaks["bf16_sustained"]})
+            else:
+                rec.update({"bound": "hbm", "achieved": c["gbs"], "peak": peaks["hbm"], "unit": "GB/s", "frac": c["gbs"] / peaks["hbm"]})
+                if c["gflop_per_step"] > 0:
+                    rec["tflops"] = c["tflops"]
+            per_class.append(rec)
+        if not per_class:
             return None, per_class
-        fl = sum(c["gflop_per_step"] for c in tcs) * 1e9
-        tm = sum(c["ms_per_step"] for c in tcs) * 1e-3
-        ln = sum(c["launches_per_step"] for c in tcs)
-        achieved = fl / tm / 1e12
-        # DRAM bytes per launch cannot be measured without a profiler attached: it is taken from THIS round's committed
-        # `ncu --set full` capture of the same command, or reported as null when that capture is absent
+        # DRAM bytes per launch cannot be measured without a profiler attached: taken from THIS round's committed
+        # `ncu --set full` capture of the dominant class at this workload, or null when that capture is absent
         traffic, traffic_src = None, None
         tpath = os.path.join(ROOT, "profiles", "r02_traffic.json")
+        dom = max(per_class, key=lambda d: d["share_of_step"])
         if os.path.exists(tpath):
             with open(tpath) as tf:
                 td = json.load(tf)
-            if td.get("workload") == workload:
-                traffic, traffic_src = td.get("dram_bytes_per_launch"), td.get("source")
-        dom = max(classes, key=lambda d: d["ms_per_step"])
-        roofline = {"bound": "tensor", "kernel": "tc::conv_kernel / tc::pair_kernel / tc::wgrad_kernel (tcgen05 implicit GEMM)",
-                    "achieved": achieved, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
-                    "frac": achieved / peaks["bf16_sustained"], "traffic": traffic, "traffic_source": traffic_src,
-                    "peak_source": f"{peaks['source']} sustained bf16 (kernel timed inside a long step)",
-                    "gflop_per_launch": fl / ln / 1e9, "avg_launch_us": tm / ln * 1e6,
-                    "share_of_step": tm / (total_ms * 1e-3), "dominant_class": dom["class"]}
+            ent = td.get(workload, {}).get(dom["class"])
+            if ent:
+                traffic, traffic_src = ent.get("dram_bytes_per_launch"), ent.get("source")
+        kernel = {"tc_conv_c>=128(fwd+dgrad)": "tc::conv_kernel (tcgen05 implicit GEMM, streamed weights)",
+                  "tc_conv_c<=64(fwd+dgrad,pair)": "tc::conv_kernel / tc::pair_kernel (tcgen05 implicit GEMM, resident weights)",
+                  "tc_wgrad_c>=128": "tc::wgrad_kernel", "tc_wgrad_c<=64": "tc::wgrad_kernel"}.get(dom["class"], dom["class"])
+        tcs = [c for c in classes if c["class"].startswith("tc_")]
+        fl = sum(c["gflop_per_step"] for c in tcs) * 1e9
+        tm = sum(c["ms_per_step"] for c in tcs) * 1e-3
+        roofline = {"bound": dom["bound"], "kernel": kernel, "achieved": dom["achieved"], "peak": dom["peak"], "unit": dom["unit"],
+                    "frac": dom["frac"], "traffic": traffic, "traffic_source": traffic_src,
+                    "peak_source": f"{peaks['source']} ({'sustained bf16' if dom['bound'] == 'tensor' else 'copy bandwidth'}; kernel timed inside a long step)",
+                    "flop_per_byte": dom["flop_per_byte"], "ridge_flop_per_byte": ridge,
+                    "avg_launch_us": dom["avg_launch_us"], "share_of_step": dom["share_of_step"], "dominant_class": dom["class"],
+                    "all_tensor_core_launches": {"tflops": fl / tm / 1e12 if tm > 0 else None,
+                                                 "frac_of_bf16_sustained": fl / tm / 1e12 / peaks["bf16_sustained"] if tm > 0 else None,
+                                                 "launches_per_step": sum(c["launches_per_step"] for c in tcs)}}
         return roofline, per_class
 
     def sub_record(self, name, steps, warmup):

@@ -229,8 +229,14 @@ inline int tc_run_conv(vcd_plan* p, const Layer& L, bool dgrad, const void* in, 
     if (!known) f = 15;
   }
   // EPI_SMEM candidates: bf16 operands in the output's own layout (plain convolution geometry), instantiations 1, 2, 3, 7, 15
-  static const int esmem_on = tc_env_int("VCD_CONV_ESMEM", 1), ne_want = tc_env_int("VCD_CONV_NE", 2),
-                   na_small = tc_env_int("VCD_CONV_NA_SMALL", 4);
+  // Ring depths of the resident-weight (<= 64-channel) launches.  Short launches (a few tiles per CTA, operands in L2:
+  // the training shapes) gain more from a small footprint -- a co-resident CTA of another ResBlock branch -- than from
+  // depth; long launches (inference on seconds of audio: operands stream from HBM) need the bytes in flight.
+  static const int esmem_on = tc_env_int("VCD_CONV_ESMEM", 1), ne_env = tc_env_int("VCD_CONV_NE", 0),
+                   na_env = tc_env_int("VCD_CONV_NA_SMALL", 0);
+  const bool long_launch = 1LL * ((mtiles + MT - 1) / MT) * P.n_tiles_n * B >= 32LL * p->num_sms;
+  const int ne_want = ne_env > 0 ? ne_env : (long_launch ? 4 : 3);
+  const int na_small = na_env > 0 ? na_env : (long_launch ? 8 : 3);
   const int e_nops = ((f & tc::EPI_MASK) && e.mask ? 1 : 0) + ((f & tc::EPI_RES) && e.res_t ? 1 : 0);
   const bool e_cand = esmem_on && e_nops > 0 && g.os == 1 && g.p == 0 && g.creal == g.N &&
                       (f == 1 || f == 2 || f == 3 || f == 7 || f == 15) &&
@@ -551,7 +557,7 @@ inline int tc_run_wgrad(vcd_plan* p, const Layer& L, const void* in, const void*
   // ~48 CTAs per layer for large weight tensors (the split partials are combined with fp32 reductions), up to one
   // CTA per SM when the weight gradient is small (C <= 64: the kernel is bound by the per-SM load rate)
   static const int env_ctas = tc_env_int("VCD_WGRAD_CTAS", 0);
-  static const int env_small = tc_env_int("VCD_WGRAD_CTAS_SMALL", 64), env_big = tc_env_int("VCD_WGRAD_CTAS_BIG", 32);
+  static const int env_small = tc_env_int("VCD_WGRAD_CTAS_SMALL", 48), env_big = tc_env_int("VCD_WGRAD_CTAS_BIG", 32);
   // tail launches (the last weight gradients of a segment: nothing else is left to share the SMs with) may spread wider
   static const int env_tail = tc_env_int("VCD_WGRAD_CTAS_TAIL", 96);
   int target_ctas = env_ctas > 0 ? env_ctas : (static_cast<long long>(g.taps) * g.K * g.N <= 64 * 64 * 11 ? env_small : env_big);

@@ -57,8 +57,11 @@ static int fail(const char* fmt, ...) {
 // optional per-launch profiler (CUDA events around every kernel, grouped by kernel class)
 // ---------------------------------------------------------------------------------------------------
 namespace {
-enum : int { PC_TC_CONV = 0, PC_TC_WGRAD, PC_FFMA_CONV, PC_FFMA_WGRAD, PC_POST, PC_FOLD, PC_MISC, PC_COUNT };
-const char* kProfNames[PC_COUNT] = {"tc_conv(fwd+dgrad)", "tc_wgrad", "ffma_conv", "ffma_wgrad", "conv_post", "weight_norm_fold", "misc"};
+// tensor-core launches are split at 64 channels: below, a layer moves 48-352 FLOP per byte (under the ~215 FLOP/B ridge
+// of the measured peaks: HBM / L2 roofline); above, the tensor pipe is the roofline.  Both carry FLOPs and bytes.
+enum : int { PC_TC_CONV = 0, PC_TC_WGRAD, PC_FFMA_CONV, PC_FFMA_WGRAD, PC_POST, PC_FOLD, PC_MISC, PC_TC_CONV_S, PC_TC_WGRAD_S, PC_COUNT };
+const char* kProfNames[PC_COUNT] = {"tc_conv_c>=128(fwd+dgrad)", "tc_wgrad_c>=128", "ffma_conv", "ffma_wgrad", "conv_post", "weight_norm_fold", "misc",
+                                    "tc_conv_c<=64(fwd+dgrad,pair)", "tc_wgrad_c<=64"};
 struct ProfRec { int cls; cudaEvent_t a, b; double flops, bytes; std::string tag; };
 bool g_prof_on = false;
 std::vector<ProfRec> g_prof;
@@ -865,7 +868,12 @@ int run_conv(const Ctx& c, cudaStream_t st, const Layer& L, bool dgrad, const vo
   static const int dbg_skip = tc_env_int("VCD_DEBUG_SKIP", 0);
   if (dbg_skip & (dgrad ? 2 : 1)) return 0;
   if (c.mode == VCD_MODE_BF16 && (dgrad ? L.tc_ok_dgr : L.tc_ok_fwd)) {
-    ProfScope ps__(PC_TC_CONV, flops, 0, st, (L.name + (dgrad ? ":dgrad" : ":fwd")).c_str());
+    // algorithmic bytes: the input tensor, every bf16 / fp32 epilogue operand and output once, the weights once
+    const double esz = 2.0;
+    const double n_out = static_cast<double>(c.B) * Lout * g.creal;
+    const double bytes = esz * c.B * static_cast<double>(Lin) * g.K + esz * n_out * ((e.out_t ? 1 : 0) + (e.mask ? 1 : 0) + (e.res_t ? 1 : 0)) +
+                         4.0 * n_out * ((e.res2 ? 1 : 0) + (e.out_raw ? 1 : 0)) + esz * g.taps * g.K * g.N;
+    ProfScope ps__(L.cin <= 64 && L.cout <= 64 ? PC_TC_CONV_S : PC_TC_CONV, flops, bytes, st, (L.name + (dgrad ? ":dgrad" : ":fwd")).c_str());
     const int rc = tc_run_conv(c.p, L, dgrad, in, c.B, Lin, Lq, Lout, e, st, g_launches, g_err, sizeof(g_err), wg);
     if (wg && wg->fused && ps__.on) {   // the launch also produced the weight gradient: twice the algorithmic FLOPs
       g_prof.back().flops *= 2.0;
@@ -888,7 +896,8 @@ int run_wgrad(const Ctx& c, cudaStream_t st, const Layer& L, const void* in, con
   static const int dbg_skip = tc_env_int("VCD_DEBUG_SKIP", 0);
   if (dbg_skip & 4) return 0;
   if (c.mode == VCD_MODE_BF16 && L.tc_ok_wgr) {
-    ProfScope ps__(PC_TC_WGRAD, flops, 0, st, (L.name + ":wgrad").c_str());
+    const double bytes = 2.0 * c.B * (static_cast<double>(Lin) * g.K + static_cast<double>(Ld) * g.N) + 4.0 * g.taps * g.K * g.N;
+    ProfScope ps__(L.cin <= 64 && L.cout <= 64 ? PC_TC_WGRAD_S : PC_TC_WGRAD, flops, bytes, st, (L.name + ":wgrad").c_str());
     // the bias gradient (column sums of dout) is produced by the same kernel
     TRY(tc_run_wgrad(c.p, L, in, dout, dwp, L.dbias >= 0 ? c.p->d_gscratch + L.dbias : nullptr, c.B, Lin, Ld, tail, st, g_launches,
                      g_err, sizeof(g_err)));
@@ -1108,7 +1117,8 @@ static int forward_impl(vcd_plan* p, int mode, const float* x, int64_t xs_b, int
             tc_pair_ok(p->layers[sd.convs[j][q][0]], p->layers[sd.convs[j][q][1]])) {
           const Layer& L1 = p->layers[sd.convs[j][q][0]];
           const Layer& L2 = p->layers[sd.convs[j][q][1]];
-          ProfScope ps__(PC_TC_CONV, layer_flops(L1, B, Lcur) + layer_flops(L2, B, Lcur), 0, sj, (L1.name + "+" + L2.name + ":fwd").c_str());
+          const double pbytes = 2.0 * B * static_cast<double>(Lcur) * L1.cin * (save ? 3 : 2) + 4.0 * L1.k * L1.cin * L1.cout;
+          ProfScope ps__(PC_TC_CONV_S, layer_flops(L1, B, Lcur) + layer_flops(L2, B, Lcur), pbytes, sj, (L1.name + "+" + L2.name + ":fwd").c_str());
           TRY(tc_run_pair(p, L1, L2, xin_t, save ? P(sw.ma[j][q]) : nullptr, P(sw.xa[j][q]), p->h_params[L1.p_b], p->h_params[L2.p_b], B, Lcur,
                           kSlope, kInvSlope, sj, g_launches, g_err, sizeof(g_err)));
           xin_t = P(sw.xa[j][q]);
