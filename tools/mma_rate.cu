@@ -133,6 +133,31 @@ int main() {
           snprintf(name, sizeof name, "conv M128 N%-3d K32 warps=%d unroll=%d", N, nw, unroll);
           run(name, P, occ);
         }
+  // weight-gradient operand layout: both operands MN-major (time rows are the contraction, 16-byte rows, LBO = 128 B,
+  // SBO = channel-group stride), as tc::wgrad_kernel reads them
+  for (int M : {64, 128})
+    for (int N : {32, 64, 128, 256}) {
+      RateParams P{};
+      P.M = M; P.N = N; P.a_mn = 1; P.b_mn = 1;
+      P.a_lbo = 128; P.a_sbo = 2048; P.b_lbo = 128; P.b_sbo = 2048;
+      P.n_mma = 22 * 40; P.taps = 11; P.step16 = 0; P.kk = 2; P.a_kk16 = 16; P.b_kk16 = 16; P.ncols = N;
+      P.nwarps = 1; P.unroll = 2;
+      char name[96];
+      snprintf(name, sizeof name, "wgrad MN-major M%-3d N%-3d", M, N);
+      run(name, P, 1);
+    }
+  // same shapes, both operands K-major (for comparison)
+  for (int M : {64, 128})
+    for (int N : {32, 64, 128, 256}) {
+      RateParams P{};
+      P.M = M; P.N = N;
+      P.a_lbo = 2048; P.a_sbo = 128; P.b_lbo = N * 16; P.b_sbo = 128;
+      P.n_mma = 22 * 40; P.taps = 11; P.step16 = 0; P.kk = 2; P.a_kk16 = 256; P.b_kk16 = 2 * N; P.ncols = N;
+      P.nwarps = 1; P.unroll = 2;
+      char name[96];
+      snprintf(name, sizeof name, "K-major M%-3d N%-3d", M, N);
+      run(name, P, 1);
+    }
   // tiny MMAs: pure issue rate
   for (int nw = 1; nw <= 4; ++nw)
     for (int unroll = 0; unroll <= 2; ++unroll) {

@@ -426,9 +426,11 @@ inline bool tc_pair_ok(const Layer& L1, const Layer& L2) {
   return tc_pair_smem(C, L1.k, L1.dil, 2) <= 227 * 1024;
 }
 
-inline int tc_run_pair(vcd_plan* p, const Layer& L1, const Layer& L2, const void* in, void* mid_out, void* out, const float* bias1,
-                       const float* bias2, int B, int Lrows, float act_slope, float res_inv, cudaStream_t stream,
-                       std::atomic<uint64_t>& launches, char* err, size_t errn) {
+// out / out_raw / res2 / tscale / out_slope: see tc::PairParams (a non-final pair stores lrelu(.) with the ResBlock slope;
+// the final pair of a branch joins the fp32 running sum over the branches).
+inline int tc_run_pair(vcd_plan* p, const Layer& L1, const Layer& L2, const void* in, void* mid_out, void* out, const float* res2,
+                       float* out_raw, float tscale, float out_slope, const float* bias1, const float* bias2, int B, int Lrows,
+                       float act_slope, float res_inv, cudaStream_t stream, std::atomic<uint64_t>& launches, char* err, size_t errn) {
   tc::PairParams P{};
   P.in = static_cast<const bf16*>(in);
   P.w1 = p->d_bf16 + L1.tc_fwd;
@@ -436,6 +438,7 @@ inline int tc_run_pair(vcd_plan* p, const Layer& L1, const Layer& L2, const void
   P.bias1 = bias1; P.bias2 = bias2;
   P.mid_out = static_cast<bf16*>(mid_out);
   P.out = static_cast<bf16*>(out);
+  P.res2 = res2; P.out_raw = out_raw; P.tscale = tscale; P.out_slope = out_slope;
   P.B = B; P.L = Lrows; P.C = L1.cin; P.taps = L1.k; P.dil = L1.dil;
   P.h1 = L1.dil * (L1.k - 1) / 2; P.h2 = (L1.k - 1) / 2;
   // MT 128-row MMA tiles per CTA tile: the largest that fits TMEM (4 * MT * C columns) and shared memory (two

@@ -36,7 +36,11 @@ struct PairParams {
   const float* bias1;
   const float* bias2;
   bf16* mid_out;         // lrelu(c1(.)) [B][C/8][L + pads][8], or null (inference)
-  bf16* out;             // lrelu(x + c2(.)) [B][C/8][L + pads][8]
+  bf16* out;             // lrelu((x + c2(.) [+ res2]) * tscale, out_slope) [B][C/8][L + pads][8], or null
+  // final pair of a ResBlock branch: the running fp32 sum over the branches (same blocked layout, 4-byte elements)
+  const float* res2;     // sum of the previous branches, or null
+  float* out_raw;        // x + c2(.) [+ res2] in fp32 (input of the next branch's final pair), or null
+  float tscale, out_slope;
   int B, L, C, taps;
   int dil;               // dilation of c1 (c2: 1)
   int h1, h2;            // dil * (taps - 1) / 2, (taps - 1) / 2
@@ -300,7 +304,7 @@ pair_kernel(const PairParams P) {
           const bool valid = rr < P.R && t < P.L;
           // residual: x recovered from the stored lrelu(x); its row in the activation region is rr + h2 + h1
           const uint8_t* xrow = a_smem + static_cast<size_t>(pa.stage) * a_stage_bytes + static_cast<size_t>(min(rr + P.h2 + P.h1, P.RA - 1)) * 16;
-          bf16* grow = P.out + blk_row(b, 0, valid ? t : 0, C, P.L);
+          const size_t o0 = blk_row(b, 0, valid ? t : 0, C, P.L);
           float acc[NCOL];
           if constexpr (NCOL == 32) tmem_ld32(t_lane + static_cast<uint32_t>(((2 + buf) * P.MT + mt) * C + col0), acc);
           else tmem_ld16(t_lane + static_cast<uint32_t>(((2 + buf) * P.MT + mt) * C + col0), acc);
@@ -311,11 +315,22 @@ pair_kernel(const PairParams P) {
               float xr[8], v[8];
               unpack8(*reinterpret_cast<const uint4*>(xrow + static_cast<size_t>(cg) * cg_bytes), xr);
 #pragma unroll
-              for (int n = 0; n < 8; ++n) {
-                const float x = acc[h * 8 + n] + bias_s[64 + cg * 8 + n] + (xr[n] > 0.f ? xr[n] : xr[n] * P.res_inv);
-                v[n] = fmaxf(x, x * P.act_slope);
+              for (int n = 0; n < 8; ++n) v[n] = acc[h * 8 + n] + bias_s[64 + cg * 8 + n] + (xr[n] > 0.f ? xr[n] : xr[n] * P.res_inv);
+              const size_t o = o0 + cg * chunk_stride;
+              if (P.res2 != nullptr) {
+                const float4 r0 = __ldg(reinterpret_cast<const float4*>(P.res2 + o)), r1 = __ldg(reinterpret_cast<const float4*>(P.res2 + o) + 1);
+                v[0] += r0.x; v[1] += r0.y; v[2] += r0.z; v[3] += r0.w;
+                v[4] += r1.x; v[5] += r1.y; v[6] += r1.z; v[7] += r1.w;
               }
-              store8<bf16>(grow + cg * chunk_stride, v);
+              if (P.out_raw != nullptr) store8<float>(P.out_raw + o, v);
+              if (P.out != nullptr) {
+#pragma unroll
+                for (int n = 0; n < 8; ++n) {
+                  const float x = v[n] * P.tscale;
+                  v[n] = fmaxf(x, x * P.out_slope);
+                }
+                store8<bf16>(P.out + o, v);
+              }
             }
           }
         }

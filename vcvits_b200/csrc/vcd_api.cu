@@ -1113,15 +1113,38 @@ static int forward_impl(vcd_plan* p, int mode, const float* x, int64_t xs_b, int
         const void* conv_in = xin_t;
         // <= 64-channel stages: both convolutions of a non-final pair in ONE launch (tc_pair.cuh); the final pair joins
         // the running sum over branches and keeps its own epilogues
-        if (p->cfg.resblock == 1 && !last && mode == VCD_MODE_BF16 && !pair_off &&
+        if (p->cfg.resblock == 1 && mode == VCD_MODE_BF16 && !pair_off &&
             tc_pair_ok(p->layers[sd.convs[j][q][0]], p->layers[sd.convs[j][q][1]])) {
           const Layer& L1 = p->layers[sd.convs[j][q][0]];
           const Layer& L2 = p->layers[sd.convs[j][q][1]];
-          const double pbytes = 2.0 * B * static_cast<double>(Lcur) * L1.cin * (save ? 3 : 2) + 4.0 * L1.k * L1.cin * L1.cout;
-          ProfScope ps__(PC_TC_CONV_S, layer_flops(L1, B, Lcur) + layer_flops(L2, B, Lcur), pbytes, sj, (L1.name + "+" + L2.name + ":fwd").c_str());
-          TRY(tc_run_pair(p, L1, L2, xin_t, save ? P(sw.ma[j][q]) : nullptr, P(sw.xa[j][q]), p->h_params[L1.p_b], p->h_params[L2.p_b], B, Lcur,
-                          kSlope, kInvSlope, sj, g_launches, g_err, sizeof(g_err)));
-          xin_t = P(sw.xa[j][q]);
+          void* out_t = nullptr;
+          const float* res2 = nullptr;
+          float* out_raw = nullptr;
+          float tscale = 1.f, out_slope = kSlope;
+          if (!last) {
+            out_t = P(sw.xa[j][q]);
+          } else {   // the final pair joins the running sum over branches (same chaining as the unfused path below)
+            if (j > 0) {
+              res2 = PF(w.sum[(j - 1) & 1]);
+              if (sj != c.branch(j - 1)) c.wait(sj, prev_last);
+            }
+            if (j < NB - 1) {
+              out_raw = PF(w.sum[j & 1]);
+            } else {
+              out_t = P(w.a[i + 1]);
+              tscale = 1.f / NB;
+              out_slope = (i == S - 1) ? kFinalSlope : kSlope;
+            }
+          }
+          const double units = (save ? 3 : 2) + (res2 ? 2 : 0) + (out_raw ? 1 : 0);   // bf16 tensor passes (fp32 = 2)
+          const double pbytes = 2.0 * B * static_cast<double>(Lcur) * L1.cin * units + 4.0 * L1.k * L1.cin * L1.cout;
+          {
+            ProfScope ps__(PC_TC_CONV_S, layer_flops(L1, B, Lcur) + layer_flops(L2, B, Lcur), pbytes, sj, (L1.name + "+" + L2.name + ":fwd").c_str());
+            TRY(tc_run_pair(p, L1, L2, xin_t, save ? P(sw.ma[j][q]) : nullptr, out_t, res2, out_raw, tscale, out_slope, p->h_params[L1.p_b],
+                            p->h_params[L2.p_b], B, Lcur, kSlope, kInvSlope, sj, g_launches, g_err, sizeof(g_err)));
+          }
+          if (!last) xin_t = P(sw.xa[j][q]);
+          else if (!c.serial) prev_last = c.record(sj);
           continue;
         }
         if (p->cfg.resblock == 1) {
