@@ -232,8 +232,9 @@ pair_kernel(const PairParams P) {
     const int quad = warp & 3, half = (warp - 2) >> 2, r = quad * 32 + lane;      // accumulator row = TMEM lane
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
     const size_t chunk_stride = static_cast<size_t>(padded_len(P.L)) * 8;
-    auto run = [&](auto ncol_tag) {
+    auto run = [&](auto ncol_tag, auto mt_tag) {
       constexpr int NCOL = decltype(ncol_tag)::value;       // columns per warp = C / 2
+      constexpr int MT = decltype(mt_tag)::value;
       const int col0 = half * NCOL;
       int i = 0;
       for (int tile = blockIdx.x; tile < P.total_tiles; tile += grid, ++i) {
@@ -243,30 +244,41 @@ pair_kernel(const PairParams P) {
         mbar_wait(&mid_empty[buf], (use & 1) ^ 1);
         mbar_wait(&acc1_full[buf], use & 1);
         tc_fence_after();
-        for (int mt = 0; mt < P.MT; ++mt) {
+        // all TMEM loads of the CTA tile first, ONE wait: the load latency is paid once per tile, not once per row tile
+        uint32_t raw[MT][NCOL];
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+#pragma unroll
+          for (int c16 = 0; c16 < NCOL / 16; ++c16)
+            tmem_ld16_issue(t_lane + static_cast<uint32_t>((buf * MT + mt) * C + col0 + c16 * 16), *reinterpret_cast<uint32_t(*)[16]>(&raw[mt][c16 * 16]));
+        }
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+#pragma unroll
+          for (int c16 = 0; c16 < NCOL / 16; ++c16) tmem_wait16(*reinterpret_cast<uint32_t(*)[16]>(&raw[mt][c16 * 16]));
+        }
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
           const int rr = mt * 128 + r;                        // row of the CTA tile's mid region
           const int t = ti * P.R - P.h2 + rr;                 // its global row
           const bool inside = t >= 0 && t < P.L;
           const bool own = SAVE_MID && inside && rr >= P.h2 && rr < P.h2 + P.R;   // the tile stores its own R rows
           uint8_t* mrow = mid_smem + static_cast<size_t>(buf) * mid_bytes + static_cast<size_t>(rr) * 16;
           bf16* grow = SAVE_MID ? P.mid_out + blk_row(b, 0, inside ? t : 0, C, P.L) : nullptr;
-          float acc[NCOL];
-          if constexpr (NCOL == 32) tmem_ld32(t_lane + static_cast<uint32_t>((buf * P.MT + mt) * C + col0), acc);
-          else tmem_ld16(t_lane + static_cast<uint32_t>((buf * P.MT + mt) * C + col0), acc);
 #pragma unroll
           for (int h = 0; h < NCOL / 8; ++h) {
             const int cg = (col0 >> 3) + h;
             float v[8];
 #pragma unroll
             for (int n = 0; n < 8; ++n) {
-              const float x = acc[h * 8 + n] + bias_s[cg * 8 + n];
+              const float x = __uint_as_float(raw[mt][h * 8 + n]) + bias_s[cg * 8 + n];
               v[n] = inside ? fmaxf(x, x * P.act_slope) : 0.f;   // c2 zero-pads the intermediate outside [0, L)
             }
-            uint4 raw;
-            raw.x = pack_bf16x2(v[0], v[1]); raw.y = pack_bf16x2(v[2], v[3]);
-            raw.z = pack_bf16x2(v[4], v[5]); raw.w = pack_bf16x2(v[6], v[7]);
-            *reinterpret_cast<uint4*>(mrow + static_cast<size_t>(cg) * mid_rows * 16) = raw;
-            if (own) *reinterpret_cast<uint4*>(grow + cg * chunk_stride) = raw;
+            uint4 pk;
+            pk.x = pack_bf16x2(v[0], v[1]); pk.y = pack_bf16x2(v[2], v[3]);
+            pk.z = pack_bf16x2(v[4], v[5]); pk.w = pack_bf16x2(v[6], v[7]);
+            *reinterpret_cast<uint4*>(mrow + static_cast<size_t>(cg) * mid_rows * 16) = pk;
+            if (own) *reinterpret_cast<uint4*>(grow + cg * chunk_stride) = pk;
           }
         }
         fence_proxy_async();       // the generic-proxy writes of `mid` must be visible to the tensor core's (async proxy) reads
@@ -278,16 +290,24 @@ pair_kernel(const PairParams P) {
         }
       }
     };
-    if (C == 64) run(std::integral_constant<int, 32>{});
-    else run(std::integral_constant<int, 16>{});
+    using std::integral_constant;
+    if (C == 64) {   // (host: 4 * MT * C <= 512 TMEM columns, so MT <= 2 at 64 channels)
+      if (P.MT == 1) run(integral_constant<int, 32>{}, integral_constant<int, 1>{});
+      else run(integral_constant<int, 32>{}, integral_constant<int, 2>{});
+    } else {
+      if (P.MT == 1) run(integral_constant<int, 16>{}, integral_constant<int, 1>{});
+      else if (P.MT == 2) run(integral_constant<int, 16>{}, integral_constant<int, 2>{});
+      else run(integral_constant<int, 16>{}, integral_constant<int, 4>{});
+    }
   } else {
     // ===================== epilogue 2: acc2 + bias + residual -> out =====================
     const int quad = warp & 3, half = (warp - 10) >> 2, r = quad * 32 + lane;
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
     const size_t chunk_stride = static_cast<size_t>(padded_len(P.L)) * 8;
     const uint32_t cg_bytes = static_cast<uint32_t>(P.RA) * 16;
-    auto run = [&](auto ncol_tag) {
+    auto run = [&](auto ncol_tag, auto mt_tag) {
       constexpr int NCOL = decltype(ncol_tag)::value;
+      constexpr int MT = decltype(mt_tag)::value;
       const int col0 = half * NCOL;
       Pipe pa;
       int i = 0;
@@ -298,16 +318,26 @@ pair_kernel(const PairParams P) {
         mbar_wait(&fullA[pa.stage], pa.phase);              // (long complete; orders this warp's reads after the bulk copies)
         mbar_wait(&acc2_full[buf], use & 1);
         tc_fence_after();
-        for (int mt = 0; mt < P.MT; ++mt) {
+        uint32_t raw[MT][NCOL];
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+#pragma unroll
+          for (int c16 = 0; c16 < NCOL / 16; ++c16)
+            tmem_ld16_issue(t_lane + static_cast<uint32_t>(((2 + buf) * MT + mt) * C + col0 + c16 * 16), *reinterpret_cast<uint32_t(*)[16]>(&raw[mt][c16 * 16]));
+        }
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+#pragma unroll
+          for (int c16 = 0; c16 < NCOL / 16; ++c16) tmem_wait16(*reinterpret_cast<uint32_t(*)[16]>(&raw[mt][c16 * 16]));
+        }
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
           const int rr = mt * 128 + r;
           const int t = ti * P.R + rr;                        // global output row
           const bool valid = rr < P.R && t < P.L;
           // residual: x recovered from the stored lrelu(x); its row in the activation region is rr + h2 + h1
           const uint8_t* xrow = a_smem + static_cast<size_t>(pa.stage) * a_stage_bytes + static_cast<size_t>(min(rr + P.h2 + P.h1, P.RA - 1)) * 16;
           const size_t o0 = blk_row(b, 0, valid ? t : 0, C, P.L);
-          float acc[NCOL];
-          if constexpr (NCOL == 32) tmem_ld32(t_lane + static_cast<uint32_t>(((2 + buf) * P.MT + mt) * C + col0), acc);
-          else tmem_ld16(t_lane + static_cast<uint32_t>(((2 + buf) * P.MT + mt) * C + col0), acc);
           if (valid) {
 #pragma unroll
             for (int h = 0; h < NCOL / 8; ++h) {
@@ -315,7 +345,7 @@ pair_kernel(const PairParams P) {
               float xr[8], v[8];
               unpack8(*reinterpret_cast<const uint4*>(xrow + static_cast<size_t>(cg) * cg_bytes), xr);
 #pragma unroll
-              for (int n = 0; n < 8; ++n) v[n] = acc[h * 8 + n] + bias_s[64 + cg * 8 + n] + (xr[n] > 0.f ? xr[n] : xr[n] * P.res_inv);
+              for (int n = 0; n < 8; ++n) v[n] = __uint_as_float(raw[mt][h * 8 + n]) + bias_s[64 + cg * 8 + n] + (xr[n] > 0.f ? xr[n] : xr[n] * P.res_inv);
               const size_t o = o0 + cg * chunk_stride;
               if (P.res2 != nullptr) {
                 const float4 r0 = __ldg(reinterpret_cast<const float4*>(P.res2 + o)), r1 = __ldg(reinterpret_cast<const float4*>(P.res2 + o) + 1);
@@ -343,8 +373,15 @@ pair_kernel(const PairParams P) {
         pa.advance(P.NA);
       }
     };
-    if (C == 64) run(std::integral_constant<int, 32>{});
-    else run(std::integral_constant<int, 16>{});
+    using std::integral_constant;
+    if (C == 64) {   // (host: 4 * MT * C <= 512 TMEM columns, so MT <= 2 at 64 channels)
+      if (P.MT == 1) run(integral_constant<int, 32>{}, integral_constant<int, 1>{});
+      else run(integral_constant<int, 32>{}, integral_constant<int, 2>{});
+    } else {
+      if (P.MT == 1) run(integral_constant<int, 16>{}, integral_constant<int, 1>{});
+      else if (P.MT == 2) run(integral_constant<int, 16>{}, integral_constant<int, 2>{});
+      else run(integral_constant<int, 16>{}, integral_constant<int, 4>{});
+    }
   }
   tc_fence_before();
   __syncthreads();
