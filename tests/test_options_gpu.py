@@ -41,10 +41,12 @@ def _run(env_extra, path):
     return dict(np.load(path))
 
 
-@pytest.mark.parametrize("option", [{"VCD_WG_FUSE": "1"}, {"VCD_PAIR": "0"}, {"VCD_BWD_WHOLE": "0"}, {"VCD_GRAPHS": "0"}])
+@pytest.mark.parametrize("option", [{"VCD_WG_FUSE": "1", "VCD_PAIR_BWD": "0"}, {"VCD_PAIR": "0"}, {"VCD_PAIR_BWD": "0"}, {"VCD_PAIR_MT": "1"},
+                                    {"VCD_BWD_WHOLE": "0"}, {"VCD_GRAPHS": "0"}])
 def test_option_matches_default_path(option):
-    """VCD_WG_FUSE=1: weight gradients accumulated inside the data-gradient launches (off by default); VCD_PAIR=0: unfused
-    ResBlock pairs; VCD_BWD_WHOLE=0: per-segment backward graphs; VCD_GRAPHS=0: no CUDA-graph replay.  Same results as
+    """VCD_WG_FUSE=1: weight gradients accumulated inside the (unfused) data-gradient launches (off by default); VCD_PAIR=0 /
+    VCD_PAIR_BWD=0: unfused ResBlock pairs (forward and backward / backward only); VCD_PAIR_MT=1: one row tile per CTA
+    tile; VCD_BWD_WHOLE=0: per-segment backward graphs; VCD_GRAPHS=0: no CUDA-graph replay.  Same results as
     the default path: waveform and dz bit for bit (same arithmetic), weight gradients to the fp32 summation order."""
     with tempfile.TemporaryDirectory() as d:
         ref = _run({}, os.path.join(d, "ref.npz"))

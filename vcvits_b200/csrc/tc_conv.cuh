@@ -8,6 +8,8 @@
 #include <cstdlib>
 
 #include "plan.h"
+#include <algorithm>
+
 #include "tc_kernels.cuh"
 #include "tc_pair.cuh"
 
@@ -156,9 +158,11 @@ inline int tc_plan_init(vcd_plan* p) {
   if (e != cudaSuccess) return 1;
   e = cudaFuncSetAttribute(tc::wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   if (e != cudaSuccess) return 1;
-  e = cudaFuncSetAttribute(tc::pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  e = cudaFuncSetAttribute(tc::pair_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   if (e != cudaSuccess) return 1;
-  e = cudaFuncSetAttribute(tc::pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  e = cudaFuncSetAttribute(tc::pair_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (e != cudaSuccess) return 1;
+  e = cudaFuncSetAttribute(tc::pair_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   if (e != cudaSuccess) return 1;
   if (getenv("VCD_KTRACE")) {
     if (cudaMalloc(&p->d_trace, 64 * sizeof(unsigned long long)) != cudaSuccess) return 1;
@@ -402,19 +406,22 @@ inline int tc_run_conv(vcd_plan* p, const Layer& L, bool dgrad, const void* in, 
   return 0;
 }
 
-// Shared-memory bytes of the fused pair kernel for (C, taps, dil) with an NA-deep activation ring; 0 = not eligible.
-inline size_t tc_pair_smem(int C, int taps, int dil, int NA, int MT = 1) {
-  const int h1 = dil * (taps - 1) / 2;
-  const int RA = (MT * 128 + 2 * h1 + 7) / 8 * 8;
+// Shared-memory bytes of the fused pair kernel: phase-A halo hA (input region), phase-B tap over-read `slack` (mid region),
+// an NA-deep activation ring and MT 128-row tiles per CTA tile.
+inline size_t tc_pair_smem(int C, int taps, int hA, int slack, int NA, int MT) {
+  const int RA = (MT * 128 + 2 * hA + 7) / 8 * 8;
   const size_t a_stage = static_cast<size_t>(C / 8) * RA * 16, w = static_cast<size_t>(taps) * (C / 8) * C * 16;
-  const size_t mid = static_cast<size_t>(C / 8) * (MT * 128 + tc::kMidSlack) * 16;
+  const size_t mid = static_cast<size_t>(C / 8) * (MT * 128 + slack) * 16;
   return 128 + NA * a_stage + 2 * w + 2 * mid + 32 * 8 + 16 + 2 * 64 * 4 + 128;
 }
+inline int tc_pair_slack(int hB) { const int s = (2 * hB + 7) / 8 * 8; return s < 16 ? 16 : s; }
 
-// Can the pair (L1 = dilated c1, L2 = c2 with dilation 1) of a ResBlock1 run as ONE fused forward launch?
-inline bool tc_pair_ok(const Layer& L1, const Layer& L2) {
-  static const int on = tc_env_int("VCD_PAIR", 1);
-  if (!on || !L1.tc_ok_fwd || !L2.tc_ok_fwd) return false;
+// Can the pair (L1 = dilated c1, L2 = c2 with dilation 1) of a ResBlock1 run as ONE fused launch?  bwd: the two data
+// gradients (phase A = c2's, phase B = c1's) instead of the two forward convolutions.
+inline bool tc_pair_ok(const Layer& L1, const Layer& L2, bool bwd = false) {
+  static const int on = tc_env_int("VCD_PAIR", 1), on_bwd = tc_env_int("VCD_PAIR_BWD", 1);
+  if (!on || (bwd && !on_bwd)) return false;
+  if (bwd ? (!L1.tc_ok_dgr || !L2.tc_ok_dgr) : (!L1.tc_ok_fwd || !L2.tc_ok_fwd)) return false;
   if (L1.kind != LK_CONV || L2.kind != LK_CONV) return false;
   const int C = L1.cin;
   if (!(C == 32 || C == 64) || L1.cout != C || L2.cin != C || L2.cout != C) return false;
@@ -422,47 +429,72 @@ inline bool tc_pair_ok(const Layer& L1, const Layer& L2) {
   if (L1.p_b < 0 || L2.p_b < 0) return false;
   const int h1 = L1.dil * (L1.k - 1) / 2, h2 = (L1.k - 1) / 2;
   if (h1 + h2 > kPadL || 128 + h1 + h2 + 8 > kPadR) return false;   // the tile halo must stay inside the zero pads
-  if (L1.nt_fwd != C || L2.nt_fwd != C) return false;               // packed as one column tile: [tap][C/8][C][8]
-  return tc_pair_smem(C, L1.k, L1.dil, 2) <= 227 * 1024;
+  if (bwd ? (L1.nt_dgr != C || L2.nt_dgr != C) : (L1.nt_fwd != C || L2.nt_fwd != C)) return false;   // one column tile: [tap][C/8][C][8]
+  const int hA = bwd ? h2 : h1, hB = bwd ? h1 : h2;
+  return tc_pair_smem(C, L1.k, hA, tc_pair_slack(hB), 2, 1) <= 227 * 1024;
 }
 
-// out / out_raw / res2 / tscale / out_slope: see tc::PairParams (a non-final pair stores lrelu(.) with the ResBlock slope;
-// the final pair of a branch joins the fp32 running sum over the branches).
-inline int tc_run_pair(vcd_plan* p, const Layer& L1, const Layer& L2, const void* in, void* mid_out, void* out, const float* res2,
-                       float* out_raw, float tscale, float out_slope, const float* bias1, const float* bias2, int B, int Lrows,
-                       float act_slope, float res_inv, cudaStream_t stream, std::atomic<uint64_t>& launches, char* err, size_t errn) {
+// One fused pair launch.  Forward: out / out_raw / res2 / tscale / out_slope as in tc::PairParams (a non-final pair stores
+// lrelu(.) with the ResBlock slope; the final pair of a branch joins the fp32 running sum over the branches).  Backward
+// (bwd): in = gradient w.r.t. the pair's output, mask1 = stored lrelu(c1 out), mask2 = stored lrelu(pair input),
+// mid_out = gradient w.r.t. c1's output (read by c1's weight gradient), out = gradient w.r.t. the pair's input.
+struct PairCall {
+  const void* in = nullptr;
+  void* mid_out = nullptr;
+  void* out = nullptr;
+  const float* res2 = nullptr;
+  float* out_raw = nullptr;
+  float tscale = 1.f, out_slope = 1.f;
+  const float* bias1 = nullptr;
+  const float* bias2 = nullptr;
+  float act_slope = 1.f, res_inv = 1.f;
+  bool bwd = false;
+  const void* mask1 = nullptr;
+  const void* mask2 = nullptr;
+  float mask_slope = 1.f;
+};
+
+inline int tc_run_pair(vcd_plan* p, const Layer& L1, const Layer& L2, const PairCall& a, int B, int Lrows, cudaStream_t stream,
+                       std::atomic<uint64_t>& launches, char* err, size_t errn) {
   tc::PairParams P{};
-  P.in = static_cast<const bf16*>(in);
-  P.w1 = p->d_bf16 + L1.tc_fwd;
-  P.w2 = p->d_bf16 + L2.tc_fwd;
-  P.bias1 = bias1; P.bias2 = bias2;
-  P.mid_out = static_cast<bf16*>(mid_out);
-  P.out = static_cast<bf16*>(out);
-  P.res2 = res2; P.out_raw = out_raw; P.tscale = tscale; P.out_slope = out_slope;
-  P.B = B; P.L = Lrows; P.C = L1.cin; P.taps = L1.k; P.dil = L1.dil;
-  P.h1 = L1.dil * (L1.k - 1) / 2; P.h2 = (L1.k - 1) / 2;
+  P.in = static_cast<const bf16*>(a.in);
+  // phase A / phase B weights: forward c1, c2; backward c2's and c1's data-gradient formats
+  P.w1 = p->d_bf16 + (a.bwd ? L2.tc_dgr : L1.tc_fwd);
+  P.w2 = p->d_bf16 + (a.bwd ? L1.tc_dgr : L2.tc_fwd);
+  P.bias1 = a.bias1; P.bias2 = a.bias2;
+  P.mid_out = static_cast<bf16*>(a.mid_out);
+  P.out = static_cast<bf16*>(a.out);
+  P.res2 = a.res2; P.out_raw = a.out_raw; P.tscale = a.tscale; P.out_slope = a.out_slope;
+  P.mask1 = static_cast<const bf16*>(a.mask1); P.mask2 = static_cast<const bf16*>(a.mask2); P.mask_slope = a.mask_slope;
+  P.B = B; P.L = Lrows; P.C = L1.cin; P.taps = L1.k;
+  const int h1 = L1.dil * (L1.k - 1) / 2, h2 = (L1.k - 1) / 2;
+  P.dilA = a.bwd ? 1 : L1.dil; P.dilB = a.bwd ? L1.dil : 1;
+  P.hA = a.bwd ? h2 : h1; P.hB = a.bwd ? h1 : h2;
+  P.mid_slack = tc_pair_slack(P.hB);
+  if (a.bwd && (!a.mid_out || !a.out || !a.mask1 || !a.mask2)) { snprintf(err, errn, "tc_run_pair(%s): backward pair needs dm, out and both masks", L1.name.c_str()); return 1; }
   // MT 128-row MMA tiles per CTA tile: the largest that fits TMEM (4 * MT * C columns) and shared memory (two
   // activation stages at least) while every SM still gets a few CTA tiles
   static const int mt_env = tc_env_int("VCD_PAIR_MT", 0), na_want = tc_env_int("VCD_PAIR_NA", 3);
   P.MT = 1;
   for (int mt : {4, 2}) {
     if (mt_env > 0 && mt != mt_env) continue;
-    if (4 * mt * P.C > 512 || tc_pair_smem(P.C, P.taps, P.dil, 2, mt) > 220 * 1024) continue;
-    const long long tiles = 1LL * B * ((Lrows + mt * 128 - P.taps) / (mt * 128 - (P.taps - 1)));
+    if (4 * mt * P.C > 512 || tc_pair_smem(P.C, P.taps, P.hA, P.mid_slack, 2, mt) > 220 * 1024) continue;
+    const int r = mt * 128 - 2 * P.hB;
+    const long long tiles = 1LL * B * ((Lrows + r - 1) / r);
     if (mt_env == 0 && tiles < 3LL * p->num_sms) continue;
     P.MT = mt;
     break;
   }
-  P.R = P.MT * 128 - (L1.k - 1);
-  P.RA = (P.MT * 128 + 2 * P.h1 + 7) / 8 * 8;
+  P.R = P.MT * 128 - 2 * P.hB;
+  P.RA = (P.MT * 128 + 2 * P.hA + 7) / 8 * 8;
   P.NA = na_want < 2 ? 2 : (na_want > 8 ? 8 : na_want);
-  while (P.NA > 2 && tc_pair_smem(P.C, P.taps, P.dil, P.NA, P.MT) > 220 * 1024) --P.NA;
-  const size_t smem = tc_pair_smem(P.C, P.taps, P.dil, P.NA, P.MT);
+  while (P.NA > 2 && tc_pair_smem(P.C, P.taps, P.hA, P.mid_slack, P.NA, P.MT) > 220 * 1024) --P.NA;
+  const size_t smem = tc_pair_smem(P.C, P.taps, P.hA, P.mid_slack, P.NA, P.MT);
   if (smem > 227 * 1024) { snprintf(err, errn, "tc_run_pair(%s): shared memory budget exceeded", L1.name.c_str()); return 1; }
   P.tiles_per_item = (Lrows + P.R - 1) / P.R;
   P.total_tiles = P.tiles_per_item * B;
   P.d_tiles.init(P.tiles_per_item);
-  P.act_slope = act_slope; P.res_inv = res_inv;
+  P.act_slope = a.act_slope; P.res_inv = a.res_inv;
   uint32_t cols = 32;
   while (cols < static_cast<uint32_t>(4 * P.MT * P.C)) cols <<= 1;
   P.tmem_cols = cols;
@@ -478,8 +510,10 @@ inline int tc_run_pair(vcd_plan* p, const Layer& L1, const Layer& L2, const void
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   static const int pdl_mask = tc_env_int("VCD_PDL", 1);
-  cfg.numAttrs = (pdl_mask & 1) ? 1 : 0;
-  const cudaError_t ce = mid_out ? cudaLaunchKernelEx(&cfg, tc::pair_kernel<true>, P) : cudaLaunchKernelEx(&cfg, tc::pair_kernel<false>, P);
+  cfg.numAttrs = (pdl_mask & (a.bwd ? 2 : 1)) ? 1 : 0;
+  cudaError_t ce;
+  if (a.bwd) ce = cudaLaunchKernelEx(&cfg, tc::pair_kernel<true, true>, P);
+  else ce = a.mid_out ? cudaLaunchKernelEx(&cfg, tc::pair_kernel<true, false>, P) : cudaLaunchKernelEx(&cfg, tc::pair_kernel<false, false>, P);
   launches.fetch_add(1, std::memory_order_relaxed);
   if (ce != cudaSuccess) {
     snprintf(err, errn, "launch of tc::pair_kernel(%s) failed: %s", L1.name.c_str(), cudaGetErrorString(ce));

@@ -17,6 +17,13 @@
 // hand-overs per tile (MMA -> epilogue-1 -> MMA -> epilogue-2, ~0.4 us each with two buffers in flight) are what
 // bounds a 128-row tile of these layers, not bandwidth; MT amortises them (and the halo) over more rows.
 //
+// BWD instantiation = the data gradients of the same pair in one launch:
+//     dm = mask(mid) * dgrad_c2(G);   G' = G + mask(x_in) * dgrad_c1(dm)        (mask(a) = a > 0 ? 1 : slope)
+// Same structure with the roles of the dilations swapped (phase A = c2's data gradient, dilation 1, small input halo;
+// phase B = c1's, dilated, reading `dm` from shared memory: R = MT * 128 - 2 h1 output rows), masks instead of bias +
+// activation (loaded from global memory ahead of the accumulator wait), the identity path of `x = xt + x` taken from the
+// gradient tile already in shared memory, `dm` always stored (c1's weight gradient reads it).
+//
 // Warp roles (576 threads): 0 = producer (weights once, activation tiles), 1 = TMEM allocator + MMA issuer,
 // 2..9 = epilogue-1, 10..17 = epilogue-2 (two warps per TMEM lane quadrant each, splitting the columns: with one warp
 // per quadrant the two epilogues, not the memory system, set the time per tile).
@@ -42,11 +49,15 @@ struct PairParams {
   float* out_raw;        // x + c2(.) [+ res2] in fp32 (input of the next branch's final pair), or null
   float tscale, out_slope;
   int B, L, C, taps;
-  int dil;               // dilation of c1 (c2: 1)
-  int h1, h2;            // dil * (taps - 1) / 2, (taps - 1) / 2
+  int dilA, dilB;        // dilation of phase A / phase B (forward: c1's dilation, 1; backward: 1, c1's dilation)
+  int hA, hB;            // halos: dilA * (taps - 1) / 2, dilB * (taps - 1) / 2
+  int mid_slack;         // rows phase B's taps read past the last `mid` row (>= 2 * hB, multiple of 8)
+  const bf16* mask1;     // BWD: stored lrelu(c1 out) -> mask of dm;   mask2: stored lrelu(x_in) -> mask of c1's data gradient
+  const bf16* mask2;
+  float mask_slope;
   int MT;                // 128-row MMA tiles per CTA tile
-  int R;                 // output rows per CTA tile = MT * 128 - (taps - 1)
-  int RA;                // rows of an activation region = MT * 128 + 2 * h1, rounded up to 8
+  int R;                 // output rows per CTA tile = MT * 128 - 2 * hB
+  int RA;                // rows of an activation region = MT * 128 + 2 * hA, rounded up to 8
   int NA;                // activation ring depth
   int tiles_per_item, total_tiles;
   FastDiv d_tiles;       // divider by tiles_per_item
@@ -54,15 +65,16 @@ struct PairParams {
   uint32_t tmem_cols;
 };
 
-template <bool SAVE_MID>
+template <bool SAVE_MID, bool BWD = false>
 __global__ void __launch_bounds__(kPairThreads, 1)
 pair_kernel(const PairParams P) {
+  static_assert(!BWD || SAVE_MID, "the backward pair always stores dm");
   extern __shared__ __align__(128) uint8_t smem_raw[];
   const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int C = P.C, cgs = C >> 3, taps = P.taps;
   const uint32_t a_stage_bytes = static_cast<uint32_t>(cgs) * P.RA * 16;
   const uint32_t w_bytes = static_cast<uint32_t>(taps) * cgs * C * 16;
-  const int mid_rows = P.MT * 128 + kMidSlack;
+  const int mid_rows = P.MT * 128 + P.mid_slack;
   const uint32_t mid_bytes = static_cast<uint32_t>(cgs) * mid_rows * 16;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
   uint8_t* a_smem = smem;
@@ -94,7 +106,7 @@ pair_kernel(const PairParams P) {
   }
   if (warp == 1) tmem_alloc(tmem_slot, P.tmem_cols);
   // biases (older than the stream predecessor's output: no dependency wait) and the never-written slack rows of `mid`
-  if (threadIdx.x >= 64 && threadIdx.x < 64 + 2 * 64) {
+  if (!BWD && threadIdx.x >= 64 && threadIdx.x < 64 + 2 * 64) {
     const int i = threadIdx.x - 64, which = i >> 6, ch = i & 63;
     if (ch < C) bias_s[which * 64 + ch] = __ldg((which ? P.bias2 : P.bias1) + ch);
   }
@@ -125,7 +137,7 @@ pair_kernel(const PairParams P) {
       if (tile + grid >= P.total_tiles) pdl_launch();
       int b, ti;
       P.d_tiles.divmod(tile, b, ti);
-      const int row0 = ti * P.R - P.h2 - P.h1;
+      const int row0 = ti * P.R - P.hB - P.hA;
       mbar_wait(&emptyA[pa.stage], pa.phase ^ 1);
       uint8_t* stage = a_smem + static_cast<size_t>(pa.stage) * a_stage_bytes;
       const bf16* src0 = P.in + blk_row(b, 0, row0, C, P.L);
@@ -149,7 +161,7 @@ pair_kernel(const PairParams P) {
     const uint32_t a_hi = static_cast<uint32_t>(a_desc0 >> 32), m_hi = static_cast<uint32_t>(m_desc0 >> 32), w_hi = static_cast<uint32_t>(w_desc0 >> 32);
     const uint32_t w1_lo = static_cast<uint32_t>(w_desc0) + (smem_u32(w1_smem) >> 4);
     const uint32_t w2_lo = static_cast<uint32_t>(w_desc0) + (smem_u32(w2_smem) >> 4);
-    const uint32_t dil = static_cast<uint32_t>(P.dil);
+    const uint32_t dilA = static_cast<uint32_t>(P.dilA), dilB = static_cast<uint32_t>(P.dilB);
     mbar_wait(w_full, 0);
     tc_fence_after();
     int n_tiles = 0;
@@ -179,7 +191,7 @@ pair_kernel(const PairParams P) {
                                   w_lo + static_cast<uint32_t>(kk) * w_kk16, w_hi, idesc, (j | kk) != 0 ? 1u : 0u);
               }
             }
-            a_tap += dil;
+            a_tap += dilA;
             w_lo += w_tap16;
           }
           if (elect_one()) {
@@ -208,7 +220,7 @@ pair_kernel(const PairParams P) {
                                   w_lo + static_cast<uint32_t>(kk) * w_kk16, w_hi, idesc, (j | kk) != 0 ? 1u : 0u);
               }
             }
-            m_tap += 1u;
+            m_tap += dilB;
             w_lo += w_tap16;
           }
           if (elect_one()) {
@@ -241,6 +253,18 @@ pair_kernel(const PairParams P) {
         const int buf = i & 1, use = i >> 1;
         int b, ti;
         P.d_tiles.divmod(tile, b, ti);
+        // BWD: the leaky-ReLU masks of this thread's rows (stored lrelu(c1 out)), requested ahead of the accumulator wait
+        uint4 mk[BWD ? MT : 1][BWD ? NCOL / 8 : 1];
+        if constexpr (BWD) {
+#pragma unroll
+          for (int mt = 0; mt < MT; ++mt) {
+            const int t = ti * P.R - P.hB + mt * 128 + r;
+            const bool inside = t >= 0 && t < P.L;
+            const bf16* mrow_g = P.mask1 + blk_row(b, col0 >> 3, inside ? t : 0, C, P.L);
+#pragma unroll
+            for (int h = 0; h < NCOL / 8; ++h) mk[mt][h] = __ldg(reinterpret_cast<const uint4*>(mrow_g + h * chunk_stride));
+          }
+        }
         mbar_wait(&mid_empty[buf], (use & 1) ^ 1);
         mbar_wait(&acc1_full[buf], use & 1);
         tc_fence_after();
@@ -260,19 +284,27 @@ pair_kernel(const PairParams P) {
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt) {
           const int rr = mt * 128 + r;                        // row of the CTA tile's mid region
-          const int t = ti * P.R - P.h2 + rr;                 // its global row
+          const int t = ti * P.R - P.hB + rr;                 // its global row
           const bool inside = t >= 0 && t < P.L;
-          const bool own = SAVE_MID && inside && rr >= P.h2 && rr < P.h2 + P.R;   // the tile stores its own R rows
+          const bool own = SAVE_MID && inside && rr >= P.hB && rr < P.hB + P.R;   // the tile stores its own R rows
           uint8_t* mrow = mid_smem + static_cast<size_t>(buf) * mid_bytes + static_cast<size_t>(rr) * 16;
           bf16* grow = SAVE_MID ? P.mid_out + blk_row(b, 0, inside ? t : 0, C, P.L) : nullptr;
 #pragma unroll
           for (int h = 0; h < NCOL / 8; ++h) {
             const int cg = (col0 >> 3) + h;
             float v[8];
+            if constexpr (BWD) {
+              float m[8];
+              unpack8(mk[mt][h], m);
 #pragma unroll
-            for (int n = 0; n < 8; ++n) {
-              const float x = __uint_as_float(raw[mt][h * 8 + n]) + bias_s[cg * 8 + n];
-              v[n] = inside ? fmaxf(x, x * P.act_slope) : 0.f;   // c2 zero-pads the intermediate outside [0, L)
+              for (int n = 0; n < 8; ++n)     // the intermediate gradient outside [0, L) is zero (c2 zero-pads its input)
+                v[n] = inside ? __uint_as_float(raw[mt][h * 8 + n]) * (m[n] > 0.f ? 1.f : P.mask_slope) : 0.f;
+            } else {
+#pragma unroll
+              for (int n = 0; n < 8; ++n) {
+                const float x = __uint_as_float(raw[mt][h * 8 + n]) + bias_s[cg * 8 + n];
+                v[n] = inside ? fmaxf(x, x * P.act_slope) : 0.f;   // c2 zero-pads the intermediate outside [0, L)
+              }
             }
             uint4 pk;
             pk.x = pack_bf16x2(v[0], v[1]); pk.y = pack_bf16x2(v[2], v[3]);
@@ -315,6 +347,17 @@ pair_kernel(const PairParams P) {
         const int buf = i & 1, use = i >> 1;
         int b, ti;
         P.d_tiles.divmod(tile, b, ti);
+        uint4 mk[BWD ? MT : 1][BWD ? NCOL / 8 : 1];   // BWD: masks of this thread's output rows (stored lrelu(x_in))
+        if constexpr (BWD) {
+#pragma unroll
+          for (int mt = 0; mt < MT; ++mt) {
+            const int rr = mt * 128 + r, t = ti * P.R + rr;
+            const bool valid = rr < P.R && t < P.L;
+            const bf16* mrow_g = P.mask2 + blk_row(b, col0 >> 3, valid ? t : 0, C, P.L);
+#pragma unroll
+            for (int h = 0; h < NCOL / 8; ++h) mk[mt][h] = __ldg(reinterpret_cast<const uint4*>(mrow_g + h * chunk_stride));
+          }
+        }
         mbar_wait(&fullA[pa.stage], pa.phase);              // (long complete; orders this warp's reads after the bulk copies)
         mbar_wait(&acc2_full[buf], use & 1);
         tc_fence_after();
@@ -335,8 +378,9 @@ pair_kernel(const PairParams P) {
           const int rr = mt * 128 + r;
           const int t = ti * P.R + rr;                        // global output row
           const bool valid = rr < P.R && t < P.L;
-          // residual: x recovered from the stored lrelu(x); its row in the activation region is rr + h2 + h1
-          const uint8_t* xrow = a_smem + static_cast<size_t>(pa.stage) * a_stage_bytes + static_cast<size_t>(min(rr + P.h2 + P.h1, P.RA - 1)) * 16;
+          // residual: x recovered from the stored lrelu(x) (BWD: the incoming gradient itself); its row in the activation
+          // region is rr + hB + hA
+          const uint8_t* xrow = a_smem + static_cast<size_t>(pa.stage) * a_stage_bytes + static_cast<size_t>(min(rr + P.hB + P.hA, P.RA - 1)) * 16;
           const size_t o0 = blk_row(b, 0, valid ? t : 0, C, P.L);
           if (valid) {
 #pragma unroll
@@ -344,9 +388,17 @@ pair_kernel(const PairParams P) {
               const int cg = (col0 >> 3) + h;
               float xr[8], v[8];
               unpack8(*reinterpret_cast<const uint4*>(xrow + static_cast<size_t>(cg) * cg_bytes), xr);
+              const size_t o = o0 + cg * chunk_stride;
+              if constexpr (BWD) {   // G' = G + mask * dgrad_c1(dm), stored as is
+                float m[8];
+                unpack8(mk[mt][h], m);
+#pragma unroll
+                for (int n = 0; n < 8; ++n) v[n] = xr[n] + __uint_as_float(raw[mt][h * 8 + n]) * (m[n] > 0.f ? 1.f : P.mask_slope);
+                store8<bf16>(P.out + o, v);
+                continue;
+              }
 #pragma unroll
               for (int n = 0; n < 8; ++n) v[n] = __uint_as_float(raw[mt][h * 8 + n]) + bias_s[64 + cg * 8 + n] + (xr[n] > 0.f ? xr[n] : xr[n] * P.res_inv);
-              const size_t o = o0 + cg * chunk_stride;
               if (P.res2 != nullptr) {
                 const float4 r0 = __ldg(reinterpret_cast<const float4*>(P.res2 + o)), r1 = __ldg(reinterpret_cast<const float4*>(P.res2 + o) + 1);
                 v[0] += r0.x; v[1] += r0.y; v[2] += r0.z; v[3] += r0.w;

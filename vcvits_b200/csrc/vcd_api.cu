@@ -12,6 +12,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <memory>
 #include <vector>
 
 #include "plan.h"
@@ -1091,6 +1092,10 @@ static int forward_impl(vcd_plan* p, int mode, const float* x, int64_t xs_b, int
     const StageDesc& sd = p->stages[i];
     const StageWs& sw = w.st[i];
     const Layer& U = p->layers[sd.up_layer];
+    // per-stage device time (VCD_PHASES=1 together with VCD_GRAPHS=0: timing events cannot live inside a captured graph)
+    static const bool stage_phases = phases_on() && tc_env_int("VCD_GRAPHS", 1) == 0;
+    std::unique_ptr<PhaseScope> stage_ph__;
+    if (stage_phases) stage_ph__.reset(new PhaseScope(("forward stage " + std::to_string(i)).c_str(), stream));
     TRY(launch_pads(p, w.pad_fwd[i + 1], mode, B, T, save, i + 1, false, c.ws, stream));
     {  // x = ups[i](lrelu(x)) ; stored as ua = lrelu(x, 0.1)
       Epilogue e = epi();
@@ -1140,8 +1145,12 @@ static int forward_impl(vcd_plan* p, int mode, const float* x, int64_t xs_b, int
           const double pbytes = 2.0 * B * static_cast<double>(Lcur) * L1.cin * units + 4.0 * L1.k * L1.cin * L1.cout;
           {
             ProfScope ps__(PC_TC_CONV_S, layer_flops(L1, B, Lcur) + layer_flops(L2, B, Lcur), pbytes, sj, (L1.name + "+" + L2.name + ":fwd").c_str());
-            TRY(tc_run_pair(p, L1, L2, xin_t, save ? P(sw.ma[j][q]) : nullptr, out_t, res2, out_raw, tscale, out_slope, p->h_params[L1.p_b],
-                            p->h_params[L2.p_b], B, Lcur, kSlope, kInvSlope, sj, g_launches, g_err, sizeof(g_err)));
+            PairCall pc;
+            pc.in = xin_t; pc.mid_out = save ? P(sw.ma[j][q]) : nullptr; pc.out = out_t;
+            pc.res2 = res2; pc.out_raw = out_raw; pc.tscale = tscale; pc.out_slope = out_slope;
+            pc.bias1 = p->h_params[L1.p_b]; pc.bias2 = p->h_params[L2.p_b];
+            pc.act_slope = kSlope; pc.res_inv = kInvSlope;
+            TRY(tc_run_pair(p, L1, L2, pc, B, Lcur, sj, g_launches, g_err, sizeof(g_err)));
           }
           if (!last) xin_t = P(sw.xa[j][q]);
           else if (!c.serial) prev_last = c.record(sj);
@@ -1358,6 +1367,29 @@ static int backward_impl(vcd_plan* p, int mode, const float* dy, const float* y,
           const void* in_first = q == 0 ? P(sw.ua) : P(sw.xa[j][q - 1]);  // input of the pair's first conv
           const void* d_first = Gt_cur;                                   // gradient w.r.t. that conv's output
           cudaEvent_t ev_first = ev_cur;
+          // <= 64-channel stages, pairs behind the first one: both data gradients in ONE launch (tc_pair.cuh, BWD); the
+          // first pair of a branch joins the running sum over branches and keeps its own epilogues
+          static const int dbg_skip_dgrad = tc_env_int("VCD_DEBUG_SKIP", 0) & 2;
+          if (p->cfg.resblock == 1 && q > 0 && c.mode == VCD_MODE_BF16 && !dbg_skip_dgrad &&
+              tc_pair_ok(p->layers[sd.convs[j][q][0]], p->layers[sd.convs[j][q][1]], true)) {
+            const Layer& L1 = p->layers[sd.convs[j][q][0]];
+            const Layer& L2 = p->layers[sd.convs[j][q][1]];
+            TRY(run_wgrad(c, side_after(ev_cur), L2, P(sw.ma[j][q]), Gt_cur, L, L, layer_flops(L2, B, L)));
+            {
+              const double pbytes = 2.0 * B * static_cast<double>(L) * L1.cin * 5 + 4.0 * L1.k * L1.cin * L1.cout;   // G, two masks in; dm, G' out
+              ProfScope ps__(PC_TC_CONV_S, layer_flops(L1, B, L) + layer_flops(L2, B, L), pbytes, sjs, (L2.name + "+" + L1.name + ":dgrad").c_str());
+              PairCall pc;
+              pc.bwd = true;
+              pc.in = Gt_cur; pc.mask1 = P(sw.ma[j][q]); pc.mask2 = in_first; pc.mask_slope = kSlope;
+              pc.mid_out = P(w.dm[i & 1][j][q]); pc.out = P(w.Gt[i & 1][j][q]);
+              TRY(tc_run_pair(p, L1, L2, pc, B, L, sjs, g_launches, g_err, sizeof(g_err)));
+            }
+            cudaEvent_t ev_pair = c.serial ? nullptr : c.record(sjs);
+            TRY(run_wgrad(c, side_after(ev_pair), L1, in_first, P(w.dm[i & 1][j][q]), L, L, layer_flops(L1, B, L)));
+            Gt_cur = P(w.Gt[i & 1][j][q]);
+            ev_cur = ev_pair;
+            continue;
+          }
           if (p->cfg.resblock == 1) {
             const Layer& L2 = p->layers[sd.convs[j][q][1]];
             Epilogue e = epi();
