@@ -332,10 +332,6 @@ inline int tc_run_conv(vcd_plan* p, const Layer& L, bool dgrad, const void* in, 
     return 1;
   }
   P.in = static_cast<const bf16*>(in);
-  {
-    static const int rot_on = tc_env_int("VCD_CONV_ROT", 0);   // off: no gain measured, and results then depend on the batch position
-    P.rot = rot_on && !P.w_resident ? 1 : 0;
-  }
   P.trace = nullptr;
   {
     static const char* want = getenv("VCD_KTRACE");  // e.g. "resblocks.5.convs1.0:fwd"

@@ -247,8 +247,6 @@ struct ConvParams {
   int minshift;           // min over taps of j*step (<= 0)
   int acc_bufs;           // 2: accumulators double-buffered (epilogue overlaps the next tile's MMAs); 1: MT*BN > 256
   uint32_t tmem_cols;
-  int rot;                // ring mode: rotate the (K block, tap group) order by the row-group index, so that the CTAs of a
-                          // launch do not all pull the same weight chunk from the same L2 slices at the same time
   int pdl_late;           // 1: release the stream successor after this CTA's last MMAs are issued (default: at its last tile's loads)
   int NE;                 // EPI_SMEM: stages of the epilogue-operand ring (mask / residual tiles fetched by the bulk-copy engine)
   int e_ops;              // operands per stage (mask, residual)
@@ -451,10 +449,7 @@ conv_kernel(const ConvParams P) {
       // 128-row tiles that start beyond the last output row are not loaded (their accumulators are never stored)
       int mt_live = P.MT;
       while (mt_live > 1 && (mg * P.MT + mt_live - 1) * 128 >= P.Lq) --mt_live;
-      const int rot_k = P.rot ? (P.d_tiles_n.quot(tile) / ngroups_w) % kblocks : 0;
-      for (int kbi = 0; kbi < kblocks; ++kbi) {
-        int kb = kbi + rot_k;
-        if (kb >= kblocks) kb -= kblocks;
+      for (int kb = 0; kb < kblocks; ++kb) {
         mbar_wait(&emptyA[pa.stage], pa.phase ^ 1);
         uint8_t* stage = a_smem + static_cast<size_t>(pa.stage) * a_stage_bytes;
         const bf16* src0 = P.in + blk_row(b, kb * cgs, row0, P.g.K, P.Lin);
@@ -466,7 +461,7 @@ conv_kernel(const ConvParams P) {
                         cg_bytes, &fullA[pa.stage]);
         }
         __syncwarp();
-        if (tile == static_cast<int>(blockIdx.x) && kbi == 0 && lane == 0) ktrace(P.trace, 2);
+        if (tile == static_cast<int>(blockIdx.x) && kb == 0 && lane == 0) ktrace(P.trace, 2);
         pa.advance(P.NA);
       }
     }
@@ -519,14 +514,9 @@ conv_kernel(const ConvParams P) {
       for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
         const int rest = P.d_tiles_n.quot(tile);
         const int nt = tile - rest * P.n_tiles_n;
-        const int rot_j = P.rot ? rest % ngroups_w : 0, rot_k = P.rot ? (rest / ngroups_w) % kblocks : 0;
-        for (int kbi = 0; kbi < kblocks; ++kbi) {
-          int kb = kbi + rot_k;
-          if (kb >= kblocks) kb -= kblocks;
+        for (int kb = 0; kb < kblocks; ++kb) {
           for (int gi = 0; gi < ngroups_w; ++gi) {
-            int grp = gi + rot_j;
-            if (grp >= ngroups_w) grp -= ngroups_w;
-            const int j0 = grp * P.TPS;
+            const int j0 = gi * P.TPS;
             const int nj = min(P.TPS, P.g.taps - j0);
             mbar_wait(&emptyW[pw.stage], pw.phase ^ 1);
             uint8_t* dst = w_smem + static_cast<size_t>(pw.stage) * P.TPS * w_tap_bytes;
@@ -580,16 +570,11 @@ conv_kernel(const ConvParams P) {
         mbar_wait(&acc_empty[buf], (use & 1) ^ 1);
         tc_fence_after();
         const uint32_t d_tile = tmem_base + static_cast<uint32_t>(buf * P.MT * P.BN);
-        const int rest = P.d_tiles_n.quot(tile);
-        const int rot_j = P.rot ? rest % ngroups_w : 0;          // (host: rot only with streamed weights)
-        const int rot_k = P.rot ? (rest / ngroups_w) % kblocks : 0;
         const int ngroups = P.w_resident ? 1 : ngroups_w;
-        for (int kbi = 0; kbi < kblocks; ++kbi) {
-          int kb = kbi + rot_k;
-          if (kb >= kblocks) kb -= kblocks;
+        for (int kb = 0; kb < kblocks; ++kb) {
           mbar_wait(&fullA[pa.stage], pa.phase);
           tc_fence_after();
-          if (it == 0 && kbi == 0 && lane == 0) ktrace(P.trace, 4);
+          if (it == 0 && kb == 0 && lane == 0) ktrace(P.trace, 4);
           const uint32_t a_stage_lo = static_cast<uint32_t>(a_desc0) + (smem_u32(a_smem + static_cast<size_t>(pa.stage) * a_stage_bytes) >> 4);
           for (int gi = 0; gi < ngroups; ++gi) {
             int nj, j0;
@@ -599,16 +584,14 @@ conv_kernel(const ConvParams P) {
               j0 = 0;
               w_lo = w_res_lo + static_cast<uint32_t>(kb) * w_tap16;
             } else {
-              int grp = gi + rot_j;
-              if (grp >= ngroups_w) grp -= ngroups_w;
-              j0 = grp * P.TPS;
+              j0 = gi * P.TPS;
               nj = min(P.TPS, taps - j0);
               mbar_wait(&fullW[pw.stage], pw.phase);
               tc_fence_after();
               w_lo = static_cast<uint32_t>(w_desc0) + (smem_u32(w_smem + static_cast<size_t>(pw.stage) * P.TPS * w_tap_bytes) >> 4);
             }
             uint32_t a_tap = a_stage_lo + static_cast<uint32_t>(-P.minshift) + static_cast<uint32_t>(j0) * a_step;
-            uint32_t first = (kbi | gi) != 0 ? 1u : 0u;    // accumulate flag of the first MMA of this tap group
+            uint32_t first = (kb | gi) != 0 ? 1u : 0u;    // accumulate flag of the first MMA of this tap group
 #pragma unroll 1
             for (int jj = 0; jj < nj; ++jj) {
               if constexpr (MTC > 0) {
