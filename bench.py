@@ -436,6 +436,42 @@ class Bench:
         torch.cuda.empty_cache()
         return rec
 
+    def mel_tail_record(self, B, T, steps=20, warmup=5):
+        """the mel / STFT loss tail behind the decoder (vcd_mel_loss: loss + dy in one call)
+        on the configs[1] segment shape, device-resident inputs; the CPU oracle (torch.stft autograd, fp32) beside it."""
+        torch = self.torch
+        from vcvits_b200 import mel as V
+        kw = dict(n_fft=2048, num_mels=256, sampling_rate=48000, hop_size=512, win_size=2048, fmin=0.0, fmax=None)
+        gen = torch.Generator(device="cpu").manual_seed(77)
+        y_hat = (0.3 * torch.randn(B, 1, T, generator=gen)).clamp(-1, 1).to(self.dev)
+        y_real = (0.3 * torch.randn(B, T, generator=gen)).clamp(-1, 1).to(self.dev)
+        tgt = V.mel_spectrogram_torch(y_real, **kw)
+        plan = V._plan(device=self.dev, **kw)
+
+        def step():
+            return plan.loss_and_grad(y_hat, tgt, 45.0)
+
+        ms = self.timed(step, steps, warmup)
+        rows, nb = B * plan.frames(T), kw["n_fft"] // 2 + 1
+        flops = 2.0 * 2.0 * rows * (kw["n_fft"] * 2 * nb + nb * kw["num_mels"])       # 4 GEMMs: STFT, mel and their transposes
+        from oracle import mel_oracle as M
+        cores = use_all_host_threads()
+        yc, tc = y_hat[:, 0].cpu(), tgt.cpu()
+
+        def cpu_step():
+            yy = yc.clone().requires_grad_(True)
+            (torch.nn.functional.l1_loss(M.log_mel(yy, **kw), tc) * 45.0).backward()
+
+        cpu_step()
+        t0 = time.perf_counter()
+        for _ in range(5):
+            cpu_step()
+        t_cpu = (time.perf_counter() - t0) / 5
+        return {"what": "c_mel * l1(logmel(y_hat), y_mel) + d/dy_hat (vits/light/vcvits.py:96-115)", "B": B, "samples": T,
+                "ms_per_call": ms, "launches_per_call": 6, "dtype": "f32", "gflop_dense_dft": flops / 1e9,
+                "tflops_ffma": flops / (ms * 1e-3) / 1e12,
+                "cpu_oracle": {"ms_per_call": t_cpu * 1e3, "cores": cores, "kind": "port (torch.stft rfft + autograd, fp32)"}}
+
     def run(self):
         from oracle import hifigan_oracle as O
         args, torch, dist, lib = self.args, self.torch, self.dist, self.lib
@@ -463,6 +499,8 @@ class Bench:
         if not args.no_extra and args.workload == "train_base_b16" and args.mode == "bf16":
             extra["train_48k_b32"] = self.sub_record("train_48k_b32", 10, 3)
             extra["infer_10s"] = self.sub_record("infer_10s", 5, 3)
+            if rank == 0 and world == 1:
+                extra["mel_loss_tail"] = self.mel_tail_record(16, 16384)
 
         # ---- rooflines, measured live with CUDA events around every launch (rank 0) ----
         roofline, classes, per_class = None, None, None

@@ -197,6 +197,46 @@ int vcd_debug_tc_paths(int fwd, int dgrad, int wgrad);
  * layer `index` of the forward schedule in `mode`; NULL past the end. */
 const char* vcd_layer_path(const vcd_plan* plan, int mode, int index);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * Mel / STFT loss tail of the generator step: the consumer of the decoder's waveform.
+ * Replaces, with its backward,
+ *     y_spec_hat = spectrogram_torch_audio(y_hat, filter_length, sr, hop_length, win_length, center=False)
+ *                                                                       (vits/mel_processing.py:76-95; call vits/light/vcvits.py:96-100)
+ *     y_mel_hat  = spec_to_mel_torch(y_spec_hat, filter_length, n_mel_channels, sr, mel_fmin, mel_fmax)
+ *                                                                       (mel_processing.py:97-112; call vcvits.py:102-108)
+ *     loss_mel   = F.l1_loss(y_mel_hat, y_mel_slice) * c_mel            (vcvits.py:115)
+ * fp32 throughout (the reference runs torch.stft in fp32).  All reductions have a fixed order: bit-identical results
+ * from run to run.  The Slaney filterbank comes from the caller (the reference takes it from librosa.filters.mel,
+ * mel_processing.py:101-103); the Hann window and the DFT basis are built by the library. */
+typedef struct vcd_mel_config {
+  int32_t n_fft;          /* filter_length  (configs/base.json:32) */
+  int32_t hop;            /* hop_length     (base.json:33)         */
+  int32_t win;            /* win_length     (base.json:34), <= n_fft: the periodic Hann window is centred in the frame */
+  int32_t n_mel;          /* n_mel_channels (base.json:35)         */
+} vcd_mel_config;
+
+typedef struct vcd_mel_plan vcd_mel_plan;
+
+/* mel_basis_host: HOST fp32 [n_mel][n_fft/2 + 1], row-major (what librosa.filters.mel returns). */
+int vcd_mel_plan_create(const vcd_mel_config* cfg, const float* mel_basis_host, vcd_mel_plan** out_plan);
+void vcd_mel_plan_destroy(vcd_mel_plan* plan);
+
+/* Frames per item for T samples: reflect pad (n_fft - hop) / 2 per side, center=False -> T / hop when hop divides T. */
+int vcd_mel_frames(const vcd_mel_plan* plan, int T);
+size_t vcd_mel_workspace_bytes(const vcd_mel_plan* plan, int B, int T);
+
+/* mel_spectrogram_torch(y, ...) (mel_processing.py:115-142) = spec_to_mel_torch(spectrogram_torch_audio(y)):
+ *   y_dev [B, T] fp32 -> mel_dev [B, n_mel, frames] fp32 log-mel. */
+int vcd_mel_spectrogram(vcd_mel_plan* plan, const float* y_dev, float* mel_dev, void* ws_dev, size_t ws_bytes, int B, int T,
+                        void* stream);
+
+/* The loss tail and its gradient in one call:
+ *   y_hat_dev [B, T] (the decoder output [B, 1, T]), mel_target_dev [B, n_mel, frames] (y_mel_slice),
+ *   *loss_dev = c_mel * mean |logmel(y_hat) - mel_target|,
+ *   dy_dev [B, T] = d loss / d y_hat (the decoder's upstream gradient; NULL: loss only). */
+int vcd_mel_loss(vcd_mel_plan* plan, const float* y_hat_dev, const float* mel_target_dev, float c_mel, float* loss_dev,
+                 float* dy_dev, void* ws_dev, size_t ws_bytes, int B, int T, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -15,7 +15,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libvcd.so")
 CSRC = os.path.join(_HERE, "csrc")
 SOURCES = ["vcd_api.cu"]
-HEADERS = ["common.cuh", "simt_kernels.cuh", "fold.cuh", "fold_fast.cuh", "plan.h", "tc_conv.cuh", "tc_kernels.cuh"]
+HEADERS = ["common.cuh", "simt_kernels.cuh", "fold.cuh", "fold_fast.cuh", "plan.h", "tc_conv.cuh", "tc_kernels.cuh", "tc_pair.cuh",
+           "mel_loss.cuh"]
 
 MODE_FP32 = 0
 MODE_BF16 = 1
@@ -119,6 +120,14 @@ _SIGNATURES = {
     "vcd_debug_ws_tensor": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_char_p, C.POINTER(C.c_size_t),
                                       C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "vcd_debug_tc_paths": (C.c_int, [C.c_int, C.c_int, C.c_int]),
+    # mel / STFT loss tail (vcvits_b200/mel.py)
+    "vcd_mel_plan_create": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "vcd_mel_plan_destroy": (None, [C.c_void_p]),
+    "vcd_mel_frames": (C.c_int, [C.c_void_p, C.c_int]),
+    "vcd_mel_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int, C.c_int]),
+    "vcd_mel_spectrogram": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p]),
+    "vcd_mel_loss": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
+                               C.c_int, C.c_int, C.c_void_p]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

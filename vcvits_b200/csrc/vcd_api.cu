@@ -1711,3 +1711,188 @@ extern "C" const char* vcd_layer_path(const vcd_plan* p, int mode, int index) {
            bf && L.tc_ok_wgr ? "tcgen05-bf16" : (bf ? "ffma-bf16io" : "ffma-fp32"));
   return buf;
 }
+
+// ---------------------------------------------------------------------------------------------------
+// Mel / STFT loss tail (include/vcd.h "mel loss tail")
+// ---------------------------------------------------------------------------------------------------
+#include "mel_loss.cuh"
+
+struct vcd_mel_plan {
+  vcd_mel_config cfg;
+  int device = 0;
+  int n_bins = 0, ld_bins = 0, ld_spec = 0;   // n_fft/2 + 1; padded leading dimensions of mag / melW and of S
+  float* d_basis = nullptr;                   // [2 * n_bins][n_fft] window-folded DFT basis
+  float* d_melw = nullptr;                    // [n_mel][ld_bins] filterbank (pad columns zero)
+};
+
+namespace {
+inline size_t mel_align(size_t v) { return (v + 255) & ~static_cast<size_t>(255); }
+struct MelWs {
+  size_t S, mag, dM, dframe, partials, total;
+  int frames, rows, n_partials;
+};
+// frames per item of torch.stft(center=False) on the reflect-padded signal (mel_processing.py:90-93)
+inline int mel_frames(const vcd_mel_config& c, int T) {
+  const int pad = (c.n_fft - c.hop) / 2;
+  const int padded = T + 2 * pad;
+  return padded < c.n_fft ? 0 : (padded - c.n_fft) / c.hop + 1;
+}
+inline MelWs mel_ws_layout(const vcd_mel_plan* p, int B, int T) {
+  MelWs w{};
+  w.frames = mel_frames(p->cfg, T);
+  w.rows = B * w.frames;
+  w.n_partials = ((p->cfg.n_mel + 63) / 64) * ((w.rows + 63) / 64);
+  size_t o = 0;
+  w.S = o; o += mel_align(sizeof(float) * static_cast<size_t>(w.rows) * p->ld_spec);
+  w.mag = o; o += mel_align(sizeof(float) * static_cast<size_t>(w.rows) * p->ld_bins);
+  w.dM = o; o += mel_align(sizeof(float) * static_cast<size_t>(w.rows) * p->cfg.n_mel);
+  w.dframe = o; o += mel_align(sizeof(float) * static_cast<size_t>(w.rows) * p->cfg.n_fft);
+  w.partials = o; o += mel_align(sizeof(float) * static_cast<size_t>(w.n_partials));
+  w.total = o;
+  return w;
+}
+}  // namespace
+
+extern "C" int vcd_mel_plan_create(const vcd_mel_config* cfg, const float* mel_basis_host, vcd_mel_plan** out) {
+  if (!cfg || !mel_basis_host || !out) return fail("vcd_mel_plan_create: null argument");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail("vcd_mel_plan_create: no CUDA device available (this library has no CPU fallback)");
+  if (cfg->n_fft < 16 || (cfg->n_fft & 3)) return fail("n_fft (%d) must be a multiple of 4 and >= 16", cfg->n_fft);
+  if (cfg->win < 1 || cfg->win > cfg->n_fft) return fail("win (%d) must be in [1, n_fft]", cfg->win);
+  if (cfg->hop < 1 || cfg->hop > cfg->n_fft || ((cfg->n_fft - cfg->hop) & 1))
+    return fail("hop (%d) must be in [1, n_fft] with n_fft - hop even (the reflect pad is (n_fft - hop) / 2 per side)", cfg->hop);
+  if (cfg->n_mel < 1 || (cfg->n_mel & 3)) return fail("n_mel (%d) must be a positive multiple of 4", cfg->n_mel);
+  std::unique_ptr<vcd_mel_plan> p(new vcd_mel_plan());
+  p->cfg = *cfg;
+  CU_TRY(cudaGetDevice(&p->device));
+  p->n_bins = cfg->n_fft / 2 + 1;
+  p->ld_bins = (p->n_bins + 3) & ~3;
+  p->ld_spec = (2 * p->n_bins + 3) & ~3;
+  const size_t nb = static_cast<size_t>(2) * p->n_bins * cfg->n_fft, nm = static_cast<size_t>(cfg->n_mel) * p->ld_bins;
+  CU_TRY(cudaMalloc(&p->d_basis, nb * sizeof(float)));
+  if (cudaMalloc(&p->d_melw, nm * sizeof(float)) != cudaSuccess) {
+    cudaFree(p->d_basis);
+    return fail("vcd_mel_plan_create: cudaMalloc of the filterbank failed");
+  }
+  std::vector<float> padded(nm, 0.f);
+  for (int m = 0; m < cfg->n_mel; ++m)
+    memcpy(&padded[static_cast<size_t>(m) * p->ld_bins], mel_basis_host + static_cast<size_t>(m) * p->n_bins, sizeof(float) * p->n_bins);
+  cudaError_t e = cudaMemcpy(p->d_melw, padded.data(), nm * sizeof(float), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) {
+    const long long n = static_cast<long long>(p->n_bins) * cfg->n_fft;
+    mel::basis_kernel<<<static_cast<unsigned>((n + 255) / 256), 256>>>(p->d_basis, cfg->n_fft, cfg->win, p->n_bins);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  }
+  if (e != cudaSuccess) {
+    cudaFree(p->d_basis);
+    cudaFree(p->d_melw);
+    return fail("vcd_mel_plan_create: building the DFT basis failed: %s", cudaGetErrorString(e));
+  }
+  *out = p.release();
+  return 0;
+}
+
+extern "C" void vcd_mel_plan_destroy(vcd_mel_plan* p) {
+  if (!p) return;
+  cudaFree(p->d_basis);
+  cudaFree(p->d_melw);
+  delete p;
+}
+
+extern "C" int vcd_mel_frames(const vcd_mel_plan* p, int T) { return p ? mel_frames(p->cfg, T) : 0; }
+
+extern "C" size_t vcd_mel_workspace_bytes(const vcd_mel_plan* p, int B, int T) {
+  if (!p || B < 1 || T < 1) return 0;
+  return mel_ws_layout(p, B, T).total;
+}
+
+// forward part shared by the two entry points: gemm 1 (spectrum magnitudes) and gemm 2 (log-mel / loss / dM)
+static int mel_forward(vcd_mel_plan* p, const float* y, const float* target, float* mel_out, float scale, bool want_grad,
+                       uint8_t* ws, const MelWs& w, int B, int T, cudaStream_t st) {
+  const vcd_mel_config& c = p->cfg;
+  const int pad = (c.n_fft - c.hop) / 2;
+  float* S = reinterpret_cast<float*>(ws + w.S);
+  float* mag = reinterpret_cast<float*>(ws + w.mag);
+  {
+    mel::Frames A{y, T, w.frames, c.hop, pad, w.rows, c.n_fft};
+    mel::RowsK Bm{p->d_basis, c.n_fft, 2 * p->n_bins, c.n_fft};
+    mel::EpiSpectrum E{want_grad ? S : nullptr, p->ld_spec, mag, p->ld_bins, w.rows, p->n_bins};
+    dim3 grid((2 * p->n_bins + 127) / 128, (w.rows + 63) / 64);
+    mel::gemm_kernel<64, 128, 4, 8><<<grid, 256, 0, st>>>(c.n_fft, A, Bm, E, nullptr);
+    LAUNCH_CHECK("mel::gemm_kernel (stft)");
+  }
+  {
+    mel::RowsK A{mag, p->ld_bins, w.rows, p->n_bins};
+    mel::RowsK Bm{p->d_melw, p->ld_bins, c.n_mel, p->n_bins};
+    mel::EpiLogMel E{mel_out, target, reinterpret_cast<float*>(ws + w.dM), c.n_mel, scale, w.rows, c.n_mel, w.frames};
+    dim3 grid((c.n_mel + 63) / 64, (w.rows + 63) / 64);
+    mel::gemm_kernel<64, 64, 4, 4><<<grid, 256, 0, st>>>(p->n_bins, A, Bm, E, reinterpret_cast<float*>(ws + w.partials));
+    LAUNCH_CHECK("mel::gemm_kernel (mel)");
+  }
+  return 0;
+}
+
+static int mel_check(const char* what, vcd_mel_plan* p, const void* a, const void* b, const void* ws, size_t ws_bytes, int B,
+                     int T, MelWs* w) {
+  if (!p || !a || !b || !ws) return fail("%s: null argument", what);
+  if (B < 1 || T < 1) return fail("%s: B and T must be positive", what);
+  const int pad = (p->cfg.n_fft - p->cfg.hop) / 2;
+  if (T <= pad) return fail("%s: T (%d) must exceed the reflect pad (%d samples)", what, T, pad);
+  *w = mel_ws_layout(p, B, T);
+  if (w->frames < 1) return fail("%s: T (%d) is shorter than one frame", what, T);
+  if (ws_bytes < w->total) return fail("%s: workspace too small (%zu < %zu bytes)", what, ws_bytes, w->total);
+  return 0;
+}
+
+extern "C" int vcd_mel_spectrogram(vcd_mel_plan* p, const float* y_dev, float* mel_dev, void* ws_dev, size_t ws_bytes, int B,
+                                   int T, void* stream) {
+  MelWs w;
+  TRY(mel_check("vcd_mel_spectrogram", p, y_dev, mel_dev, ws_dev, ws_bytes, B, T, &w));
+  return mel_forward(p, y_dev, nullptr, mel_dev, 0.f, false, static_cast<uint8_t*>(ws_dev), w, B, T,
+                     static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int vcd_mel_loss(vcd_mel_plan* p, const float* y_hat_dev, const float* mel_target_dev, float c_mel, float* loss_dev,
+                            float* dy_dev, void* ws_dev, size_t ws_bytes, int B, int T, void* stream) {
+  MelWs w;
+  TRY(mel_check("vcd_mel_loss", p, y_hat_dev, mel_target_dev, ws_dev, ws_bytes, B, T, &w));
+  if (!loss_dev) return fail("vcd_mel_loss: null loss pointer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  uint8_t* ws = static_cast<uint8_t*>(ws_dev);
+  const vcd_mel_config& c = p->cfg;
+  const float scale = c_mel / (static_cast<float>(B) * c.n_mel * w.frames);
+  TRY(mel_forward(p, y_hat_dev, mel_target_dev, nullptr, scale, dy_dev != nullptr, ws, w, B, T, st));
+  mel::loss_finalize_kernel<<<1, 256, 0, st>>>(reinterpret_cast<const float*>(ws + w.partials), w.n_partials, scale, loss_dev);
+  LAUNCH_CHECK("mel::loss_finalize_kernel");
+  if (!dy_dev) return 0;
+  float* S = reinterpret_cast<float*>(ws + w.S);
+  float* mag = reinterpret_cast<float*>(ws + w.mag);
+  float* dM = reinterpret_cast<float*>(ws + w.dM);
+  float* dframe = reinterpret_cast<float*>(ws + w.dframe);
+  {
+    mel::RowsK A{dM, c.n_mel, w.rows, c.n_mel};
+    mel::KCols Bm{p->d_melw, p->ld_bins, c.n_mel, p->n_bins};
+    mel::EpiMagGrad E{S, p->ld_spec, mag, p->ld_bins, w.rows, p->n_bins};
+    dim3 grid((p->n_bins + 63) / 64, (w.rows + 63) / 64);
+    mel::gemm_kernel<64, 64, 4, 4><<<grid, 256, 0, st>>>(c.n_mel, A, Bm, E, nullptr);
+    LAUNCH_CHECK("mel::gemm_kernel (mel backward)");
+  }
+  {
+    mel::RowsK A{S, p->ld_spec, w.rows, 2 * p->n_bins};
+    mel::KCols Bm{p->d_basis, c.n_fft, 2 * p->n_bins, c.n_fft};
+    mel::EpiStore E{dframe, c.n_fft, w.rows, c.n_fft};
+    dim3 grid((c.n_fft + 127) / 128, (w.rows + 63) / 64);
+    mel::gemm_kernel<64, 128, 4, 8><<<grid, 256, 0, st>>>(2 * p->n_bins, A, Bm, E, nullptr);
+    LAUNCH_CHECK("mel::gemm_kernel (stft backward)");
+  }
+  {
+    const long long total = static_cast<long long>(B) * T;
+    mel::overlap_add_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(dframe, c.n_fft, c.hop, (c.n_fft - c.hop) / 2,
+                                                                                        w.frames, T, total, dy_dev);
+    LAUNCH_CHECK("mel::overlap_add_kernel");
+  }
+  return 0;
+}
