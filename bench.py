@@ -451,9 +451,16 @@ class Bench:
         def step():
             return plan.loss_and_grad(y_hat, tgt, 45.0)
 
+        self.lib.vcd_launch_count(1)
         ms = self.timed(step, steps, warmup)
+        launches = self.lib.vcd_launch_count(1) / (steps + warmup)
+        plan.use_gemm_path(True)
+        ms_gemm = self.timed(step, steps, warmup)
+        plan.use_gemm_path(False)
         rows, nb = B * plan.frames(T), kw["n_fft"] // 2 + 1
         flops = 2.0 * 2.0 * rows * (kw["n_fft"] * 2 * nb + nb * kw["num_mels"])       # 4 GEMMs: STFT, mel and their transposes
+        # algorithmic bytes of the fused per-frame kernel + overlap-add: y read once, target read, dframe written and read, dy written
+        abytes = 4.0 * (B * T + rows * kw["num_mels"] + 2 * rows * kw["n_fft"] + B * T)
         from oracle import mel_oracle as M
         cores = use_all_host_threads()
         yc, tc = y_hat[:, 0].cpu(), tgt.cpu()
@@ -468,8 +475,11 @@ class Bench:
             cpu_step()
         t_cpu = (time.perf_counter() - t0) / 5
         return {"what": "c_mel * l1(logmel(y_hat), y_mel) + d/dy_hat (vits/light/vcvits.py:96-115)", "B": B, "samples": T,
-                "ms_per_call": ms, "launches_per_call": 6, "dtype": "f32", "gflop_dense_dft": flops / 1e9,
-                "tflops_ffma": flops / (ms * 1e-3) / 1e12,
+                "ms_per_call": ms, "launches_per_call": launches, "dtype": "f32",
+                "path": "one CTA per frame: shared-memory radix-2 FFT + banded filterbank, forward and backward fused",
+                "algorithmic_bytes": abytes, "gbs_algorithmic": abytes / (ms * 1e-3) / 1e9,
+                "frac_of_hbm_copy_peak": abytes / (ms * 1e-3) / 1e9 / self.peaks["hbm"],
+                "dense_gemm_path": {"ms_per_call": ms_gemm, "gflop": flops / 1e9, "tflops_ffma": flops / (ms_gemm * 1e-3) / 1e12},
                 "cpu_oracle": {"ms_per_call": t_cpu * 1e3, "cores": cores, "kind": "port (torch.stft rfft + autograd, fp32)"}}
 
     def run(self):

@@ -237,6 +237,11 @@ int vcd_mel_spectrogram(vcd_mel_plan* plan, const float* y_dev, float* mel_dev, 
 int vcd_mel_loss(vcd_mel_plan* plan, const float* y_hat_dev, const float* mel_target_dev, float c_mel, float* loss_dev,
                  float* dy_dev, void* ws_dev, size_t ws_bytes, int B, int T, void* stream);
 
+/* Debug / tests only.  Two implementations exist: a per-frame shared-memory FFT kernel (n_fft a power of two; the
+ * default when available) and dense fp32 GEMMs against a DFT basis (any n_fft).  use_gemm != 0 forces the second, so
+ * that the tests can check one against the other. */
+int vcd_mel_debug_path(vcd_mel_plan* plan, int use_gemm);
+
 #ifdef __cplusplus
 }
 #endif

@@ -19,6 +19,27 @@ BASE = dict(n_fft=2048, num_mels=256, sampling_rate=48000, hop_size=512, win_siz
 B48K = dict(BASE, num_mels=128)
 SMALL = dict(n_fft=256, num_mels=40, sampling_rate=16000, hop_size=64, win_size=256, fmin=0.0, fmax=None)
 SHORTWIN = dict(n_fft=512, num_mels=64, sampling_rate=22050, hop_size=128, win_size=400, fmin=30.0, fmax=8000.0)
+NONPOW2 = dict(n_fft=400, num_mels=40, sampling_rate=16000, hop_size=100, win_size=400, fmin=0.0, fmax=None)  # GEMM path only
+PATHS = ("fft", "gemm")   # per-frame shared-memory FFT kernel (default) | dense DFT GEMMs (any n_fft)
+
+
+@pytest.fixture
+def path(request):
+    """Select the implementation for every plan the test touches; always restore the default afterwards."""
+    which = request.param
+    touched = []
+
+    def select(kw):
+        plan = V._plan(device="cuda", **kw)
+        pow2 = kw["n_fft"] & (kw["n_fft"] - 1) == 0
+        if which == "fft" and not pow2:
+            pytest.skip("the FFT path needs a power-of-two n_fft")
+        plan.use_gemm_path(which == "gemm")
+        touched.append((plan, pow2))
+    yield select
+    for plan, pow2 in touched:
+        if pow2:
+            plan.use_gemm_path(False)
 
 
 def audio(B, T, seed, amp=0.3):
@@ -54,8 +75,11 @@ def test_reference_fixture_log_mel(golden_dir):
     (BASE, 1, 769),        # shortest legal input: T = pad + 1 -> 1 frame... (pad = 768)
     (SMALL, 5, 1000),
     (SHORTWIN, 4, 3000),   # win_length < n_fft: window centred in the frame
+    (NONPOW2, 3, 2500),
 ])
-def test_log_mel_matches_oracle(kw, B, T):
+@pytest.mark.parametrize("path", PATHS, indirect=True)
+def test_log_mel_matches_oracle(kw, B, T, path):
+    path(kw)
     y = audio(B, T, seed=B * 1000 + T)
     ref = M.log_mel(y, **kw)
     got = V.mel_spectrogram_torch(y.float().cuda(), **kw).cpu()
@@ -66,8 +90,10 @@ def test_log_mel_matches_oracle(kw, B, T):
 
 
 @pytest.mark.parametrize("kw,B,T", [(BASE, 16, 16384), (B48K, 32, 16384), (BASE, 2, 8192 + 100), (SMALL, 5, 1000),
-                                    (SHORTWIN, 4, 3000)])
-def test_loss_and_gradient_match_oracle(kw, B, T):
+                                    (SHORTWIN, 4, 3000), (NONPOW2, 3, 2500)])
+@pytest.mark.parametrize("path", PATHS, indirect=True)
+def test_loss_and_gradient_match_oracle(kw, B, T, path):
+    path(kw)
     y_hat = audio(B, T, seed=7)
     y_real = audio(B, T, seed=8, amp=0.4)
     tgt = M.log_mel(y_real, **kw)
@@ -107,8 +133,27 @@ def test_upstream_gradient_scaling_and_no_grad():
     assert float(lz) == 0.0 and float(c.grad.abs().max()) == 0.0
 
 
-def test_bit_identical_from_run_to_run():
+def test_the_two_implementations_agree():
     kw, B, T = BASE, 16, 16384
+    plan = V._plan(device="cuda", **kw)
+    y = audio(B, T, seed=31).float().cuda()
+    tgt = V.mel_spectrogram_torch(audio(B, T, seed=32).float().cuda(), **kw)
+    res = {}
+    try:
+        for name in PATHS:
+            plan.use_gemm_path(name == "gemm")
+            res[name] = (V.mel_spectrogram_torch(y, **kw),) + plan.loss_and_grad(y, tgt, 45.0)
+    finally:
+        plan.use_gemm_path(False)
+    assert float((res["fft"][0] - res["gemm"][0]).abs().max()) <= 2e-3     # log of tiny energies amplifies fp32 rounding
+    assert abs(float(res["fft"][1]) - float(res["gemm"][1])) <= 1e-5 * float(res["gemm"][1])
+    assert rel_l2(res["fft"][2], res["gemm"][2]) <= 3e-4     # each is within 1e-4 of the fp64 oracle
+
+
+@pytest.mark.parametrize("path", PATHS, indirect=True)
+def test_bit_identical_from_run_to_run(path):
+    kw, B, T = BASE, 16, 16384
+    path(kw)
     y = audio(B, T, seed=11).float().cuda()
     tgt = V.mel_spectrogram_torch(audio(B, T, seed=12).float().cuda(), **kw)
     outs = []

@@ -333,5 +333,132 @@ __global__ void __launch_bounds__(256) basis_kernel(float* basis, int n_fft, int
   basis[(2LL * k + 1) * n_fft + n] = static_cast<float>(-w * s);
 }
 
+
+// ---------------------------------------------------------------------------------------------------
+// Fast path (n_fft a power of two): ONE CTA per frame does the whole tail of that frame in shared memory --
+//   gather + reflect pad + window  ->  radix-2 Stockham FFT (natural order in and out, one barrier per stage)
+//   -> magnitudes -> banded mel filterbank (each filter only touches its own bins) -> log / L1 / d(mel energy)
+//   -> banded transpose -> d(re, im) -> the SAME FFT applied to conj(dS) (the adjoint of the one-sided real DFT:
+//      dframe[n] = Re sum_k (dRe_k - j dIm_k) e^(-2 pi j k n / N)) -> window -> dframe.
+// The dense GEMM kernels above stay as the general path (any n_fft) and as the in-library cross-check.
+// ---------------------------------------------------------------------------------------------------
+struct FftParams {
+  const float* y; int T, F, hop, pad, rows, n_fft, log2n, n_bins, n_mel;
+  const float* window;        // [n_fft]
+  const float2* tw;           // [n_fft / 2] e^(-2 pi j t / n_fft)
+  const int* f_lo; const int* f_cnt; const int* f_off; const float* f_val;   // per filter: first bin, bins, offset into f_val
+  const int* b_lo; const int* b_cnt; const int* b_off; const float* b_val;   // per bin: first filter, filters, offset into b_val
+  float* out;                 // [B][n_mel][F] log-mel, or null
+  const float* target;        // [B][n_mel][F], or null
+  float scale;
+  float* dframe;              // [rows][n_fft], or null (no gradient wanted)
+  float* partials;            // [rows]
+};
+
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+
+// in-place view: transforms `src` (n complex values) using `dst` as the second buffer; returns the buffer holding the result
+__device__ __forceinline__ float2* fft_stockham(float2* src, float2* dst, const float2* tw, int n, int log2n) {
+  const int half = n >> 1;
+  for (int s = 0; s < log2n; ++s) {
+    const int ns = 1 << s;
+    for (int j = threadIdx.x; j < half; j += blockDim.x) {
+      const int k = j & (ns - 1);
+      const float2 w = tw[k << (log2n - 1 - s)];
+      const float2 v0 = src[j];
+      const float2 v1 = cmul(src[j + half], w);
+      const int j0 = ((j - k) << 1) + k;
+      dst[j0] = make_float2(v0.x + v1.x, v0.y + v1.y);
+      dst[j0 + ns] = make_float2(v0.x - v1.x, v0.y - v1.y);
+    }
+    __syncthreads();
+    float2* t = src; src = dst; dst = t;
+  }
+  return src;
+}
+
+__global__ void __launch_bounds__(256) frame_fft_kernel(const FftParams P) {
+  extern __shared__ __align__(16) uint8_t fft_smem[];
+  const int n = P.n_fft, half = n >> 1;
+  float2* bufA = reinterpret_cast<float2*>(fft_smem);
+  float2* bufB = bufA + n;
+  float2* tw = bufB + n;                                  // [half]
+  float* mag = reinterpret_cast<float*>(tw + half);       // [n_bins]
+  float* dMs = mag + ((P.n_bins + 3) & ~3);               // [n_mel]
+  __shared__ float red[8];
+  const int row = blockIdx.x, tid = threadIdx.x;
+  const int b = row / P.F, f = row - b * P.F;
+  const float* yb = P.y + static_cast<size_t>(b) * P.T;
+  for (int t = tid; t < half; t += 256) tw[t] = __ldg(P.tw + t);
+  for (int i = tid; i < n; i += 256) {
+    int p = f * P.hop + i - P.pad;
+    if (p < 0) p = -p;
+    if (p >= P.T) p = 2 * (P.T - 1) - p;
+    bufA[i] = make_float2(__ldg(yb + p) * __ldg(P.window + i), 0.f);
+  }
+  __syncthreads();
+  float2* X = fft_stockham(bufA, bufB, tw, n, P.log2n);
+  float2* other = X == bufA ? bufB : bufA;
+  for (int k = tid; k < P.n_bins; k += 256) mag[k] = sqrtf(X[k].x * X[k].x + X[k].y * X[k].y + 1e-6f);
+  __syncthreads();
+  float part = 0.f;
+  for (int m = tid; m < P.n_mel; m += 256) {
+    const int lo = __ldg(P.f_lo + m), cnt = __ldg(P.f_cnt + m);
+    const float* v = P.f_val + __ldg(P.f_off + m);
+    float e = 0.f;
+    for (int i = 0; i < cnt; ++i) e = fmaf(__ldg(v + i), mag[lo + i], e);
+    const float lm = logf(fmaxf(e, 1e-5f));
+    const size_t o = (static_cast<size_t>(b) * P.n_mel + m) * P.F + f;
+    if (P.out) P.out[o] = lm;
+    if (P.target) {
+      const float d = lm - __ldg(P.target + o);
+      part += fabsf(d);
+      const float sg = d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f);
+      dMs[m] = e >= 1e-5f ? sg * P.scale / e : 0.f;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+  if ((tid & 31) == 0) red[tid >> 5] = part;
+  __syncthreads();                       // also: dMs complete
+  if (tid == 0) {
+    float s = 0.f;
+    for (int w = 0; w < 8; ++w) s += red[w];
+    P.partials[row] = s;
+  }
+  if (!P.dframe) return;
+  for (int k = tid; k < n; k += 256) {
+    float2 z = make_float2(0.f, 0.f);
+    if (k < P.n_bins) {
+      const int lo = __ldg(P.b_lo + k), cnt = __ldg(P.b_cnt + k);
+      const float* v = P.b_val + __ldg(P.b_off + k);
+      float dmag = 0.f;
+      for (int i = 0; i < cnt; ++i) dmag = fmaf(__ldg(v + i), dMs[lo + i], dmag);
+      const float g = dmag / mag[k];
+      z = make_float2(g * X[k].x, -g * X[k].y);
+    }
+    other[k] = z;
+  }
+  __syncthreads();
+  const float2* R = fft_stockham(other, X, tw, n, P.log2n);
+  float* dst = P.dframe + static_cast<size_t>(row) * n;
+  for (int i = tid; i < n; i += 256) dst[i] = R[i].x * __ldg(P.window + i);
+}
+
+// window [n_fft] and twiddles [n_fft / 2] of the fast path
+__global__ void __launch_bounds__(256) fft_tables_kernel(float* window, float2* tw, int n_fft, int win) {
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= n_fft) return;
+  const int left = (n_fft - win) / 2;
+  double w = 0.0;
+  if (i >= left && i < left + win) w = 0.5 - 0.5 * cospi(2.0 * (i - left) / static_cast<double>(win));
+  window[i] = static_cast<float>(w);
+  if (i < n_fft / 2) {
+    double s, c;
+    sincospi(-2.0 * i / static_cast<double>(n_fft), &s, &c);
+    tw[i] = make_float2(static_cast<float>(c), static_cast<float>(s));
+  }
+}
+
 }  // namespace mel
 }  // namespace vcd

@@ -1723,6 +1723,15 @@ struct vcd_mel_plan {
   int n_bins = 0, ld_bins = 0, ld_spec = 0;   // n_fft/2 + 1; padded leading dimensions of mag / melW and of S
   float* d_basis = nullptr;                   // [2 * n_bins][n_fft] window-folded DFT basis
   float* d_melw = nullptr;                    // [n_mel][ld_bins] filterbank (pad columns zero)
+  // fast path (n_fft a power of two): one CTA per frame, shared-memory FFT + banded filterbank
+  bool fft_ok = false, use_gemm = false;
+  int log2n = 0;
+  size_t fft_smem = 0;
+  float* d_window = nullptr;
+  float2* d_tw = nullptr;
+  int* d_tab = nullptr;                       // f_lo, f_cnt, f_off [n_mel] | b_lo, b_cnt, b_off [n_bins]
+  float* d_vals = nullptr;                    // f_val | b_val
+  size_t f_val_n = 0;
 };
 
 namespace {
@@ -1742,6 +1751,7 @@ inline MelWs mel_ws_layout(const vcd_mel_plan* p, int B, int T) {
   w.frames = mel_frames(p->cfg, T);
   w.rows = B * w.frames;
   w.n_partials = ((p->cfg.n_mel + 63) / 64) * ((w.rows + 63) / 64);
+  if (w.n_partials < w.rows) w.n_partials = w.rows;      // fast path: one partial per frame
   size_t o = 0;
   w.S = o; o += mel_align(sizeof(float) * static_cast<size_t>(w.rows) * p->ld_spec);
   w.mag = o; o += mel_align(sizeof(float) * static_cast<size_t>(w.rows) * p->ld_bins);
@@ -1791,6 +1801,61 @@ extern "C" int vcd_mel_plan_create(const vcd_mel_config* cfg, const float* mel_b
     cudaFree(p->d_melw);
     return fail("vcd_mel_plan_create: building the DFT basis failed: %s", cudaGetErrorString(e));
   }
+  if ((cfg->n_fft & (cfg->n_fft - 1)) == 0) {
+    // banded view of the filterbank: per filter its bin range, per bin its filter range (zeros inside a range are kept,
+    // so any matrix is handled exactly; a triangular filterbank touches ~2 filters per bin)
+    const int nm = cfg->n_mel, nbins = p->n_bins;
+    std::vector<int> tab(3 * static_cast<size_t>(nm) + 3 * static_cast<size_t>(nbins), 0);
+    int* f_lo = tab.data(); int* f_cnt = f_lo + nm; int* f_off = f_cnt + nm;
+    int* b_lo = f_off + nm; int* b_cnt = b_lo + nbins; int* b_off = b_cnt + nbins;
+    std::vector<float> vals;
+    auto W = [&](int m, int k) { return mel_basis_host[static_cast<size_t>(m) * nbins + k]; };
+    for (int m = 0; m < nm; ++m) {
+      int lo = nbins, hi = -1;
+      for (int k = 0; k < nbins; ++k)
+        if (W(m, k) != 0.f) { if (k < lo) lo = k; hi = k; }
+      f_lo[m] = hi < 0 ? 0 : lo;
+      f_cnt[m] = hi < 0 ? 0 : hi - lo + 1;
+      f_off[m] = static_cast<int>(vals.size());
+      for (int k = f_lo[m]; k < f_lo[m] + f_cnt[m]; ++k) vals.push_back(W(m, k));
+    }
+    p->f_val_n = vals.size();
+    for (int k = 0; k < nbins; ++k) {
+      int lo = nm, hi = -1;
+      for (int m = 0; m < nm; ++m)
+        if (W(m, k) != 0.f) { if (m < lo) lo = m; hi = m; }
+      b_lo[k] = hi < 0 ? 0 : lo;
+      b_cnt[k] = hi < 0 ? 0 : hi - lo + 1;
+      b_off[k] = static_cast<int>(vals.size() - p->f_val_n);
+      for (int m = b_lo[k]; m < b_lo[k] + b_cnt[k]; ++m) vals.push_back(W(m, k));
+    }
+    if (vals.empty()) vals.push_back(0.f);
+    int l2 = 0;
+    while ((1 << l2) < cfg->n_fft) ++l2;
+    p->log2n = l2;
+    p->fft_smem = sizeof(float2) * (2 * static_cast<size_t>(cfg->n_fft) + cfg->n_fft / 2) +
+                  sizeof(float) * (static_cast<size_t>((nbins + 3) & ~3) + nm);
+    cudaError_t e2 = cudaMalloc(&p->d_window, sizeof(float) * cfg->n_fft);
+    if (e2 == cudaSuccess) e2 = cudaMalloc(&p->d_tw, sizeof(float2) * (cfg->n_fft / 2));
+    if (e2 == cudaSuccess) e2 = cudaMalloc(&p->d_tab, sizeof(int) * tab.size());
+    if (e2 == cudaSuccess) e2 = cudaMalloc(&p->d_vals, sizeof(float) * vals.size());
+    if (e2 == cudaSuccess) e2 = cudaMemcpy(p->d_tab, tab.data(), sizeof(int) * tab.size(), cudaMemcpyHostToDevice);
+    if (e2 == cudaSuccess) e2 = cudaMemcpy(p->d_vals, vals.data(), sizeof(float) * vals.size(), cudaMemcpyHostToDevice);
+    if (e2 == cudaSuccess && p->fft_smem > 48 * 1024)
+      e2 = cudaFuncSetAttribute(mel::frame_fft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(p->fft_smem));
+    if (e2 == cudaSuccess) {
+      mel::fft_tables_kernel<<<(cfg->n_fft + 255) / 256, 256>>>(p->d_window, p->d_tw, cfg->n_fft, cfg->win);
+      g_launches.fetch_add(1, std::memory_order_relaxed);
+      e2 = cudaGetLastError();
+      if (e2 == cudaSuccess) e2 = cudaDeviceSynchronize();
+    }
+    if (e2 != cudaSuccess) {
+      cudaGetLastError();
+      vcd_mel_plan_destroy(p.release());
+      return fail("vcd_mel_plan_create: building the FFT tables failed: %s", cudaGetErrorString(e2));
+    }
+    p->fft_ok = p->fft_smem <= 200 * 1024;
+  }
   *out = p.release();
   return 0;
 }
@@ -1799,7 +1864,36 @@ extern "C" void vcd_mel_plan_destroy(vcd_mel_plan* p) {
   if (!p) return;
   cudaFree(p->d_basis);
   cudaFree(p->d_melw);
+  cudaFree(p->d_window);
+  cudaFree(p->d_tw);
+  cudaFree(p->d_tab);
+  cudaFree(p->d_vals);
   delete p;
+}
+
+extern "C" int vcd_mel_debug_path(vcd_mel_plan* p, int use_gemm) {
+  if (!p) return fail("vcd_mel_debug_path: null plan");
+  if (!use_gemm && !p->fft_ok) return fail("vcd_mel_debug_path: n_fft (%d) is not a power of two: only the GEMM path exists", p->cfg.n_fft);
+  p->use_gemm = use_gemm != 0;
+  return 0;
+}
+
+// fast path: one launch does everything per frame (see mel_loss.cuh)
+static int mel_fft_launch(vcd_mel_plan* p, const float* y, const float* target, float* mel_out, float scale, float* dframe,
+                          float* partials, const MelWs& w, int T, cudaStream_t st) {
+  const vcd_mel_config& c = p->cfg;
+  const int nm = c.n_mel, nbins = p->n_bins;
+  mel::FftParams P{};
+  P.y = y; P.T = T; P.F = w.frames; P.hop = c.hop; P.pad = (c.n_fft - c.hop) / 2; P.rows = w.rows;
+  P.n_fft = c.n_fft; P.log2n = p->log2n; P.n_bins = nbins; P.n_mel = nm;
+  P.window = p->d_window; P.tw = p->d_tw;
+  P.f_lo = p->d_tab; P.f_cnt = P.f_lo + nm; P.f_off = P.f_cnt + nm;
+  P.b_lo = P.f_off + nm; P.b_cnt = P.b_lo + nbins; P.b_off = P.b_cnt + nbins;
+  P.f_val = p->d_vals; P.b_val = p->d_vals + p->f_val_n;
+  P.out = mel_out; P.target = target; P.scale = scale; P.dframe = dframe; P.partials = partials;
+  mel::frame_fft_kernel<<<static_cast<unsigned>(w.rows), 256, p->fft_smem, st>>>(P);
+  LAUNCH_CHECK("mel::frame_fft_kernel");
+  return 0;
 }
 
 extern "C" int vcd_mel_frames(const vcd_mel_plan* p, int T) { return p ? mel_frames(p->cfg, T) : 0; }
@@ -1851,6 +1945,9 @@ extern "C" int vcd_mel_spectrogram(vcd_mel_plan* p, const float* y_dev, float* m
                                    int T, void* stream) {
   MelWs w;
   TRY(mel_check("vcd_mel_spectrogram", p, y_dev, mel_dev, ws_dev, ws_bytes, B, T, &w));
+  if (p->fft_ok && !p->use_gemm)
+    return mel_fft_launch(p, y_dev, nullptr, mel_dev, 0.f, nullptr, reinterpret_cast<float*>(static_cast<uint8_t*>(ws_dev) + w.partials),
+                          w, T, static_cast<cudaStream_t>(stream));
   return mel_forward(p, y_dev, nullptr, mel_dev, 0.f, false, static_cast<uint8_t*>(ws_dev), w, B, T,
                      static_cast<cudaStream_t>(stream));
 }
@@ -1864,15 +1961,19 @@ extern "C" int vcd_mel_loss(vcd_mel_plan* p, const float* y_hat_dev, const float
   uint8_t* ws = static_cast<uint8_t*>(ws_dev);
   const vcd_mel_config& c = p->cfg;
   const float scale = c_mel / (static_cast<float>(B) * c.n_mel * w.frames);
-  TRY(mel_forward(p, y_hat_dev, mel_target_dev, nullptr, scale, dy_dev != nullptr, ws, w, B, T, st));
-  mel::loss_finalize_kernel<<<1, 256, 0, st>>>(reinterpret_cast<const float*>(ws + w.partials), w.n_partials, scale, loss_dev);
+  float* dframe = reinterpret_cast<float*>(ws + w.dframe);
+  const bool fast = p->fft_ok && !p->use_gemm;
+  if (fast) TRY(mel_fft_launch(p, y_hat_dev, mel_target_dev, nullptr, scale, dy_dev ? dframe : nullptr,
+                               reinterpret_cast<float*>(ws + w.partials), w, T, st));
+  else TRY(mel_forward(p, y_hat_dev, mel_target_dev, nullptr, scale, dy_dev != nullptr, ws, w, B, T, st));
+  const int n_part = fast ? w.rows : ((c.n_mel + 63) / 64) * ((w.rows + 63) / 64);
+  mel::loss_finalize_kernel<<<1, 256, 0, st>>>(reinterpret_cast<const float*>(ws + w.partials), n_part, scale, loss_dev);
   LAUNCH_CHECK("mel::loss_finalize_kernel");
   if (!dy_dev) return 0;
   float* S = reinterpret_cast<float*>(ws + w.S);
   float* mag = reinterpret_cast<float*>(ws + w.mag);
   float* dM = reinterpret_cast<float*>(ws + w.dM);
-  float* dframe = reinterpret_cast<float*>(ws + w.dframe);
-  {
+  if (!fast) {
     mel::RowsK A{dM, c.n_mel, w.rows, c.n_mel};
     mel::KCols Bm{p->d_melw, p->ld_bins, c.n_mel, p->n_bins};
     mel::EpiMagGrad E{S, p->ld_spec, mag, p->ld_bins, w.rows, p->n_bins};
@@ -1880,7 +1981,7 @@ extern "C" int vcd_mel_loss(vcd_mel_plan* p, const float* y_hat_dev, const float
     mel::gemm_kernel<64, 64, 4, 4><<<grid, 256, 0, st>>>(c.n_mel, A, Bm, E, nullptr);
     LAUNCH_CHECK("mel::gemm_kernel (mel backward)");
   }
-  {
+  if (!fast) {
     mel::RowsK A{S, p->ld_spec, w.rows, 2 * p->n_bins};
     mel::KCols Bm{p->d_basis, c.n_fft, 2 * p->n_bins, c.n_fft};
     mel::EpiStore E{dframe, c.n_fft, w.rows, c.n_fft};

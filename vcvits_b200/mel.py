@@ -96,6 +96,10 @@ class MelLossTail:
         except Exception:
             pass
 
+    def use_gemm_path(self, on: bool) -> None:
+        """Debug / tests: force the dense-GEMM implementation (the only one when n_fft is not a power of two)."""
+        _lib.check(_lib.load().vcd_mel_debug_path(self._plan, 1 if on else 0), "vcd_mel_debug_path")
+
     def frames(self, T: int) -> int:
         return int(_lib.load().vcd_mel_frames(self._plan, int(T)))
 
