@@ -137,6 +137,14 @@ int vcd_backward_sliced(vcd_plan* plan, int mode, const float* dy_dev, const flo
  * (train.py:99-100) without a separate scaling pass.  Default 1. */
 int vcd_set_gradient_scale(vcd_plan* plan, float scale);
 
+/* Run-to-run reproducibility of the parameter gradients.  By default the split partial sums of a weight gradient (and
+ * the bias column sums) are combined with fp32 atomics in arrival order: fast, but the last bits vary between runs.
+ * on != 0: the splits of a weight-gradient tile take a ticket and add their partial sums one after the other in
+ * time-range order (the main loops still overlap); the remaining column-sum / conv_post reductions receive at most TWO
+ * atomic contributions onto a zeroed value (a + b == b + a).  All 233 gradients, dx and dg are then bit-identical
+ * from run to run, at a cost in step time (measured in DESIGN.md). */
+int vcd_set_deterministic(vcd_plan* plan, int on);
+
 /* When vcd_backward runs every segment in ONE call (segment_mask = ~0u) the data-gradient chain runs through all stages
  * while the weight gradients / weight-norm backward of finished segments trail behind it; the library then records one
  * event per segment ("its gradients are final").  vcd_stream_wait_segment makes `stream` wait for segment `segment`, so a

@@ -100,6 +100,7 @@ _SIGNATURES = {
                                       C.c_void_p, C.c_void_p, _FLOATPP, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_uint32,
                                       C.c_void_p]),
     "vcd_set_gradient_scale": (C.c_int, [C.c_void_p, C.c_float]),
+    "vcd_set_deterministic": (C.c_int, [C.c_void_p, C.c_int]),
     "vcd_segment_events_valid": (C.c_int, [C.c_void_p]),
     "vcd_stream_wait_segment": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "vcd_num_backward_segments": (C.c_int, [C.c_void_p]),

@@ -111,6 +111,11 @@ struct vcd_plan {
   vcd::NormJob* d_norm_jobs_bf16 = nullptr;
   int n_norm_jobs_bf16 = 0, n_norm_blocks_bf16 = 0;
   float grad_scale = 1.f;                  // multiplies every parameter gradient (vcd_set_gradient_scale)
+  bool deterministic = false;              // vcd_set_deterministic: fixed-order reductions of every parameter gradient
+  static constexpr int kTurnInts = 2048;   // ticket / turn counters per layer for the weight-gradient turnstile
+  int* d_turn = nullptr;                   // [layers][kTurnInts], zero between launches
+  static constexpr int kDetParts = 64, kDetFloats = kDetParts * 512;
+  float* d_det = nullptr;                  // [layers + 1][kDetFloats] partial column sums of the deterministic mode
   std::vector<vcd::SegmentJobs> segments;
 
   // auxiliary streams / events for intra-step concurrency (ResBlock branches, weight-gradient kernels)

@@ -161,6 +161,54 @@ gconv_wgrad_simt_kernel(const T* __restrict__ in, const T* __restrict__ dout, fl
 // Column sums over time (bias gradients): out[(per_batch ? b*cmod : 0) + c % cmod] += sum_t d[b][c][t]
 // (cmod < C folds the u phase groups of a phase-packed ConvTranspose gradient onto the real channels).
 // grid = (C/8, B, splits), block = 256.  `out` must be zeroed by the caller.
+// colsum_det_kernel + sum_parts_kernel: the same sums for the deterministic mode (vcd_set_deterministic).  Grid
+// (cmod / 8, 1, parts): a block walks ALL fold copies and all batch items of its slice of the time range in a fixed
+// order and stores its partial sums parts[z][c]; sum_parts_kernel then adds the parts in index order.  No atomics.
+// -------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+colsum_det_kernel(const T* __restrict__ d, float* __restrict__ parts, int C, int L, int B, int cmod) {
+  const int cgm = blockIdx.x;
+  const int chunk = (L + gridDim.z - 1) / gridDim.z;
+  const int t0 = blockIdx.z * chunk, t1 = min(L, t0 + chunk);
+  float acc[8];
+#pragma unroll
+  for (int n = 0; n < 8; ++n) acc[n] = 0.f;
+  for (int b = 0; b < B; ++b) {
+    for (int cg = cgm; cg < C / 8; cg += cmod / 8) {
+      const T* base = d + blk_row(b, cg, 0, C, L);
+      for (int t = t0 + threadIdx.x; t < t1; t += 256) {
+        float v[8];
+        load8<T>(base + static_cast<size_t>(t) * 8, v);
+#pragma unroll
+        for (int n = 0; n < 8; ++n) acc[n] += v[n];
+      }
+    }
+  }
+  __shared__ float red[8][8];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int n = 0; n < 8; ++n) {
+    const float s = warp_sum(acc[n]);
+    if (lane == 0) red[warp][n] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    float s = 0.f;
+#pragma unroll
+    for (int wv = 0; wv < 8; ++wv) s += red[wv][threadIdx.x];
+    parts[static_cast<size_t>(blockIdx.z) * cmod + cgm * 8 + threadIdx.x] = s;
+  }
+}
+
+__global__ void __launch_bounds__(256) sum_parts_kernel(const float* __restrict__ parts, int nparts, int n, float* __restrict__ out) {
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= n) return;
+  float s = 0.f;
+  for (int p = 0; p < nparts; ++p) s += parts[static_cast<size_t>(p) * n + i];
+  out[i] = s;
+}
+
 // -------------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(256)
@@ -418,12 +466,12 @@ conv_post_dgrad_kernel(const float* __restrict__ dy, const float* __restrict__ y
 }
 
 // Weight gradient of conv_post: dw[c][j] += sum_{b,t} dpost[b][t] * a[b][t + j - 3][c]   (param layout [1][C][7]).
-// grid = (C/8, B, splits), block = 256.  dw must be zeroed.
+// grid = (C/8, B, splits), block = 256 (deterministic mode: (C/8, 1, parts) with per-part partial sums).  dw must be zeroed.
 template <typename T>
 __global__ void __launch_bounds__(256)
 conv_post_wgrad_kernel(const float* __restrict__ dy, const float* __restrict__ y, const T* __restrict__ a,
-                       float* __restrict__ dw, int C, int L) {
-  const int cg = blockIdx.x, b = blockIdx.y;
+                       float* __restrict__ dw, int C, int L, int B, float* __restrict__ parts) {
+  const int cg = blockIdx.x;
   const int chunk = (L + gridDim.z - 1) / gridDim.z;
   const int r0 = blockIdx.z * chunk, r1 = min(L, r0 + chunk);
   float acc[8][7];
@@ -431,6 +479,8 @@ conv_post_wgrad_kernel(const float* __restrict__ dy, const float* __restrict__ y
   for (int c = 0; c < 8; ++c)
 #pragma unroll
     for (int j = 0; j < 7; ++j) acc[c][j] = 0.f;
+  // gridDim.y == B: one item per block; gridDim.y == 1 (deterministic mode): every item, in order
+  for (int b = blockIdx.y; b < B; b += gridDim.y) {
   const T* base = a + blk_row(b, cg, 0, C, L);
   for (int r = r0 + threadIdx.x; r < r1; r += 256) {
     float v[8];
@@ -447,6 +497,7 @@ conv_post_wgrad_kernel(const float* __restrict__ dy, const float* __restrict__ y
       for (int c = 0; c < 8; ++c) acc[c][j] = fmaf(v[c], dp, acc[c][j]);
     }
   }
+  }
   __shared__ float red[8][56];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #pragma unroll
@@ -461,7 +512,8 @@ conv_post_wgrad_kernel(const float* __restrict__ dy, const float* __restrict__ y
     float s = 0.f;
 #pragma unroll
     for (int wv = 0; wv < 8; ++wv) s += red[wv][threadIdx.x];
-    atomicAdd(dw + cg * 56 + threadIdx.x, s);
+    if (parts) parts[static_cast<size_t>(blockIdx.z) * (C * 7) + cg * 56 + threadIdx.x] = s;   // deterministic mode: summed by sum_parts_kernel
+    else atomicAdd(dw + cg * 56 + threadIdx.x, s);
   }
 }
 

@@ -370,7 +370,7 @@ inline int tc_run_conv(vcd_plan* p, const Layer& L, bool dgrad, const void* in, 
   P.wg_dwp = nullptr; P.wg_dbias = nullptr; P.wg_r0 = P.wg_rstep = P.wg_rc = 0; P.wg_col0 = 0;
   static const int wg_env = tc_env_int("VCD_WG_FUSE", 0);   // off: measured slower (see DESIGN.md, round-2 negative results)
   if (wg != nullptr) wg->fused = false;
-  if (wg != nullptr && wg->dwp != nullptr && wg_env && dgrad && lean && (f & tc::EPI_MASK) && (f & tc::EPI_SMEM) && MT == 1 && P.KB == g.K &&
+  if (wg != nullptr && wg->dwp != nullptr && wg_env && !p->deterministic && dgrad && lean && (f & tc::EPI_MASK) && (f & tc::EPI_SMEM) && MT == 1 && P.KB == g.K &&
       g.K == g.N && g.N == P.BN && g.K <= 64 && (g.taps & 1) && L.tc_ok_wgr) {
     const ConvGeo& gw = L.wgr;
     const int r0 = -gw.off0 - g.off0 - P.minshift, rstep = -gw.step, rc = -g.off0 - P.minshift;
@@ -601,6 +601,10 @@ inline int tc_run_wgrad(vcd_plan* p, const Layer& L, const void* in, const void*
   long long want = (target_ctas + base_ctas - 1) / base_ctas;
   const long long max_splits = (total_kb + 7) / 8;
   if (want > max_splits) want = max_splits;
+  // deterministic mode: the splits of a tile add their partial sums in a fixed order (see the turnstile in wgrad_kernel);
+  // fewer splits keep the serialised reduction passes short
+  static const int det_splits = tc_env_int("VCD_DET_SPLITS", 16);
+  if (p->deterministic && want > det_splits) want = det_splits;
   if (want < 1) want = 1;
   P.kb_per_split = static_cast<int>((total_kb + want - 1) / want);
   P.n_splits = static_cast<int>((total_kb + P.kb_per_split - 1) / P.kb_per_split);
@@ -611,6 +615,17 @@ inline int tc_run_wgrad(vcd_plan* p, const Layer& L, const void* in, const void*
   P.Lin = Lin;
   P.dbias = dbias;
   P.cmod = L.cout;
+  P.turn = nullptr;
+  if (p->deterministic && P.n_splits > 1 && !dbg_direct) {
+    const long long li = &L - p->layers.data();
+    const int passes = P.M == 128 ? P.TG : (P.TG + 1) / 2;
+    P.turn_stride = 1 + passes;
+    if (!p->d_turn || base_ctas * P.turn_stride > vcd_plan::kTurnInts) {
+      snprintf(err, errn, "tc_run_wgrad(%s): deterministic mode needs the turn counters (%lld tiles)", L.name.c_str(), base_ctas);
+      return 1;
+    }
+    P.turn = p->d_turn + li * vcd_plan::kTurnInts;
+  }
   P.trace = nullptr;
   {
     static const char* want = getenv("VCD_KTRACE");

@@ -1024,8 +1024,25 @@ struct WgradParams {
   uint32_t tmem_cols;
   float* dbias;           // bias gradient [cmod] (column sums of dout folded modulo cmod), or null
   int cmod;
+  int* turn;              // deterministic mode (n_splits > 1): per output tile of this layer a ticket counter followed by one
+                          // turn counter per accumulator pass (turn_stride ints per tile), else null
+  int turn_stride;
   unsigned long long* trace;
 };
+
+// Deterministic split reduction ("turnstile"): the CTAs of one output tile take their split index from a ticket counter
+// (arrival order, so the holder of ticket s - 1 is already resident when ticket s waits for it -- no dependence on the
+// block dispatch order) and add their partial sums one after the other in ticket = time-range order.  The mainloops
+// still run concurrently; the reduction passes (one per accumulator slot) form a wavefront: split s + 1 adds pass q
+// while split s adds pass q + 1.
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu(int* p, int v) {
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 
 __global__ void __launch_bounds__(kThreads, 1)
 wgrad_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ CUtensorMap tmD, const WgradParams P) {
@@ -1045,7 +1062,8 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ C
 
   // CTA coordinates
   int id = blockIdx.x;
-  const int split = id % P.n_splits; id /= P.n_splits;
+  int split = id % P.n_splits; id /= P.n_splits;
+  const int out_tile = id;               // (mtile, ntile, tap group): the CTAs that reduce into the same elements
   const int tg = id % P.n_tgroups; id /= P.n_tgroups;
   const int ntile = id % P.n_ntiles; id /= P.n_ntiles;
   const int mtile = id;
@@ -1057,12 +1075,14 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ C
     for (int i = 0; i < P.NS; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], do_colsum ? 5 : 1); }
     mbar_init(acc_full, 1);
     fence_barrier_init();
+    if (P.turn) tmem_slot[1] = static_cast<uint32_t>(atomicAdd(P.turn + out_tile * P.turn_stride, 1));   // ticket = split index
   }
   if (warp == 1) tmem_alloc(tmem_slot, P.tmem_cols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+  if (P.turn) split = static_cast<int>(tmem_slot[1]);
   if (threadIdx.x == 0) ktrace(P.trace, 1);
   const int f_begin = split * P.kb_per_split;
   const int f_end = min(P.B * P.kb_per_item, f_begin + P.kb_per_split);
@@ -1136,12 +1156,18 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ C
     if (lane == 0) ktrace(P.trace, 5);
   } else {
     const int quad = warp & 3;
+    float bs[8];
+    const int et = static_cast<int>(threadIdx.x) - 64;
+    const int n_cg = P.NT / 8, RG = 128 / n_cg;
+    const int cg = et / RG, rg = et - cg * RG;
+    auto add_bias = [&]() {
+      if (rg == 0) {
+#pragma unroll
+        for (int n = 0; n < 8; ++n) atomicAdd(P.dbias + (ntile * P.NT + cg * 8 + n) % P.cmod, bs[n]);
+      }
+    };
     if (do_colsum) {
       // thread -> (channel group cg, row group rg); consecutive threads read consecutive 16-byte rows (conflict-free)
-      const int et = static_cast<int>(threadIdx.x) - 64;
-      const int n_cg = P.NT / 8, RG = 128 / n_cg;
-      const int cg = et / RG, rg = et - cg * RG;
-      float bs[8];
 #pragma unroll
       for (int n = 0; n < 8; ++n) bs[n] = 0.f;
       Pipe ps;
@@ -1163,16 +1189,15 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ C
       for (int n = 0; n < 8; ++n) {
         for (int o = RG >> 1; o > 0; o >>= 1) bs[n] += __shfl_xor_sync(0xffffffffu, bs[n], o);
       }
-      if (rg == 0) {
-#pragma unroll
-        for (int n = 0; n < 8; ++n) atomicAdd(P.dbias + (ntile * P.NT + cg * 8 + n) % P.cmod, bs[n]);
-      }
+      if (!P.turn) add_bias();
     }
     mbar_wait(acc_full, 0);
     tc_fence_after();
     if (warp == 2 && lane == 0) ktrace(P.trace, 12);
     // the scratch below aliases pipeline stage 0: every epilogue warp must be done with its column sums first
     asm volatile("bar.sync 2, 128;" ::: "memory");
+    int* const turns = P.turn ? P.turn + out_tile * P.turn_stride : nullptr;
+    const bool last_split = split == P.n_splits - 1;
     // Accumulators -> global.  A thread owns one accumulator row (TMEM lane); writing it out directly would scatter
     // every warp-level reduction over 32 rows (32 half-used sectors per instruction).  Each 32-row x 32-column block
     // is transposed through a per-warp scratch in the (drained) pipeline stages, so one red.v4 covers four rows x
@@ -1180,6 +1205,18 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ C
     float* scratch = reinterpret_cast<float*>(smem) + (warp - 2) * (32 * 36);   // [32 rows][36]: conflict-free v4 access
     const int passes = P.M == 128 ? nslots : (nslots + 1) / 2;
     for (int ps = 0; ps < passes; ++ps) {
+      if (turns) {   // wait until the previous time range has added this pass
+        if (threadIdx.x == 64) {
+          uint32_t spins = 0;
+          while (ld_acquire_gpu(turns + 1 + ps) != split) {
+            __nanosleep(32);
+            if (++spins > kSpinLimit) __trap();
+          }
+          if (ps == 0 && last_split) turns[0] = 0;   // every ticket of this launch has been taken: reset for the next one
+        }
+        asm volatile("bar.sync 2, 128;" ::: "memory");
+        if (ps == 0 && do_colsum) add_bias();
+      }
       // this lane's accumulator row: tap slot, tap j, input channel c
       int tl, row;
       uint32_t col0;
@@ -1239,6 +1276,11 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ C
           }
         }
         __syncwarp();
+      }
+      if (turns) {   // pass this pass on (every thread's reductions are ordered before the release)
+        __threadfence();
+        asm volatile("bar.sync 2, 128;" ::: "memory");
+        if (threadIdx.x == 64) st_release_gpu(turns + 1 + ps, last_split ? 0 : split + 1);
       }
     }
     if (warp == 2 && lane == 0) ktrace(P.trace, 21);

@@ -536,7 +536,7 @@ extern "C" void vcd_plan_destroy(vcd_plan* p) {
   cudaFree(p->d_params); cudaFree(p->d_dparams); cudaFree(p->d_norm_jobs);
   cudaFree(p->d_pack_jobs[0]); cudaFree(p->d_pack_jobs[1]);
   for (auto& s : p->segments) { cudaFree(s.d_jobs); cudaFree(s.d_fast); }
-  cudaFree(p->d_fast_pack); cudaFree(p->d_norm_jobs_bf16);
+  cudaFree(p->d_fast_pack); cudaFree(p->d_norm_jobs_bf16); cudaFree(p->d_turn); cudaFree(p->d_det);
   for (auto& kv : p->graphs) cudaGraphExecDestroy(kv.second);
   for (auto& kv : p->pad_tables) cudaFree(kv.second);
   if (p->own) cudaStreamDestroy(p->own);
@@ -900,14 +900,18 @@ int run_wgrad(const Ctx& c, cudaStream_t st, const Layer& L, const void* in, con
     const double bytes = 2.0 * c.B * (static_cast<double>(Lin) * g.K + static_cast<double>(Ld) * g.N) + 4.0 * g.taps * g.K * g.N;
     ProfScope ps__(L.cin <= 64 && L.cout <= 64 ? PC_TC_WGRAD_S : PC_TC_WGRAD, flops, bytes, st, (L.name + ":wgrad").c_str());
     // the bias gradient (column sums of dout) is produced by the same kernel
-    TRY(tc_run_wgrad(c.p, L, in, dout, dwp, L.dbias >= 0 ? c.p->d_gscratch + L.dbias : nullptr, c.B, Lin, Ld, tail, st, g_launches,
+    // deterministic mode: the in-kernel column sums add once per (column tile, split); a phase-packed ConvTranspose
+    // gradient folds u column tiles onto one bias element, which would be more than two contributions
+    const bool bias_in_kernel = L.dbias >= 0 && !(c.p->deterministic && g.N != L.cout);
+    TRY(tc_run_wgrad(c.p, L, in, dout, dwp, bias_in_kernel ? c.p->d_gscratch + L.dbias : nullptr, c.B, Lin, Ld, tail, st, g_launches,
                      g_err, sizeof(g_err)));
-    return 0;
+    if (bias_in_kernel || L.dbias < 0) return 0;
   } else {
     const long long total = 1LL * c.B * Ld;
     const int blocks_x = g.taps * (g.K / 8) * (g.N / 8);
     long long splits = std::max<long long>(1, std::min<long long>((total + 2047) / 2048,
                                                                     std::max(1, 4 * c.p->num_sms * 8 / blocks_x)));
+    if (c.p->deterministic && splits > 2) splits = 2;
     const int rows_per_split = static_cast<int>((total + splits - 1) / splits);
     splits = (total + rows_per_split - 1) / rows_per_split;
     dim3 grid(blocks_x, static_cast<unsigned>(splits));
@@ -924,6 +928,20 @@ int run_wgrad(const Ctx& c, cudaStream_t st, const Layer& L, const void* in, con
     const int splits = std::max(1, std::min(64, Ld / 2048));
     dim3 grid(g.N / 8, c.B, splits);
     ProfScope ps__(PC_MISC, 0, esize(c.mode) * static_cast<double>(c.B) * g.N * Ld, st);
+    if (c.p->deterministic) {   // per-part partial sums (plain stores), then one fixed-order sum
+      float* parts = c.p->d_det + (&L - c.p->layers.data()) * vcd_plan::kDetFloats;
+      const int nparts = std::max(1, std::min(vcd_plan::kDetParts, Ld / 256));
+      if (L.cout > 512) return fail("deterministic bias gradient: %d channels", L.cout);
+      dim3 gdet(L.cout / 8, 1, nparts);
+      if (c.mode == VCD_MODE_FP32)
+        colsum_det_kernel<float><<<gdet, 256, 0, st>>>(static_cast<const float*>(dout), parts, g.N, Ld, c.B, L.cout);
+      else
+        colsum_det_kernel<bf16><<<gdet, 256, 0, st>>>(static_cast<const bf16*>(dout), parts, g.N, Ld, c.B, L.cout);
+      LAUNCH_CHECK("colsum_det_kernel");
+      sum_parts_kernel<<<(L.cout + 255) / 256, 256, 0, st>>>(parts, nparts, L.cout, c.p->d_gscratch + L.dbias);
+      LAUNCH_CHECK("sum_parts_kernel");
+      return 0;
+    }
     if (c.mode == VCD_MODE_FP32)
       colsum_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(dout), c.p->d_gscratch + L.dbias, g.N, Ld, 0, L.cout);
     else
@@ -1292,6 +1310,12 @@ static int backward_impl(vcd_plan* p, int mode, const float* dy, const float* y,
       const int C = p->stages[S - 1].cout, L = Ls[S];
       const int splits = std::max(1, std::min(64, L / 2048));
       dim3 gw(C / 8, B, splits);
+      float* post_parts = nullptr;
+      if (p->deterministic) {   // per-part partial sums, then one fixed-order sum
+        gw = dim3(C / 8, 1, std::max(1, std::min(static_cast<int>(vcd_plan::kDetParts), L / 256)));
+        post_parts = p->d_det + p->layers.size() * vcd_plan::kDetFloats;
+        if (C * 7 > 512) return fail("deterministic conv_post gradient: %d channels", C);
+      }
       dim3 gd((L + 127) / 128, C / 8, B);
       const float* wpost = p->h_params[p->p_post_w];
       const int slot = (S - 1) % 3;
@@ -1300,13 +1324,21 @@ static int backward_impl(vcd_plan* p, int mode, const float* dy, const float* y,
       c.order(stream, wst);
       post_forked = wst != stream;
       if (f32) {
-        conv_post_wgrad_kernel<float><<<gw, 256, 0, wst>>>(dy, y, static_cast<const float*>(P(w.a[S])), p->d_gscratch + p->post_dw, C, L);
+        conv_post_wgrad_kernel<float><<<gw, 256, 0, wst>>>(dy, y, static_cast<const float*>(P(w.a[S])), p->d_gscratch + p->post_dw, C, L, B, post_parts);
         LAUNCH_CHECK("conv_post_wgrad_kernel");
+        if (post_parts) {
+          sum_parts_kernel<<<(C * 7 + 255) / 256, 256, 0, wst>>>(post_parts, static_cast<int>(gw.z), C * 7, p->d_gscratch + p->post_dw);
+          LAUNCH_CHECK("sum_parts_kernel");
+        }
         conv_post_dgrad_kernel<float><<<gd, 128, 0, stream>>>(dy, y, wpost, static_cast<const float*>(P(w.a[S])), kFinalSlope, 1.f / NB,
                                                                nullptr, static_cast<float*>(P(w.Gi[slot])), C, L);
       } else {
-        conv_post_wgrad_kernel<bf16><<<gw, 256, 0, wst>>>(dy, y, static_cast<const bf16*>(P(w.a[S])), p->d_gscratch + p->post_dw, C, L);
+        conv_post_wgrad_kernel<bf16><<<gw, 256, 0, wst>>>(dy, y, static_cast<const bf16*>(P(w.a[S])), p->d_gscratch + p->post_dw, C, L, B, post_parts);
         LAUNCH_CHECK("conv_post_wgrad_kernel");
+        if (post_parts) {
+          sum_parts_kernel<<<(C * 7 + 255) / 256, 256, 0, wst>>>(post_parts, static_cast<int>(gw.z), C * 7, p->d_gscratch + p->post_dw);
+          LAUNCH_CHECK("sum_parts_kernel");
+        }
         conv_post_dgrad_kernel<bf16><<<gd, 128, 0, stream>>>(dy, y, wpost, static_cast<const bf16*>(P(w.a[S])), kFinalSlope, 1.f / NB,
                                                               nullptr, static_cast<bf16*>(P(w.Gi[slot])), C, L);
       }
@@ -1456,7 +1488,7 @@ static int backward_impl(vcd_plan* p, int mode, const float* dy, const float* y,
       CU_TRY(cudaMemsetAsync(PF(w.dcb), 0, sizeof(float) * B * C0, stream));
       {
         ProfScope ps__(PC_MISC, 0, 0, stream);
-        const int splits = std::max(1, std::min(64, T / 2048));
+        const int splits = std::max(1, std::min(p->deterministic ? 2 : 64, T / 2048));
         dim3 grid(C0 / 8, B, splits);
         if (f32) colsum_kernel<float><<<grid, 256, 0, stream>>>(static_cast<const float*>(P(w.d0)), PF(w.dcb), C0, T, 1, C0);
         else colsum_kernel<bf16><<<grid, 256, 0, stream>>>(static_cast<const bf16*>(P(w.d0)), PF(w.dcb), C0, T, 1, C0);
@@ -1530,7 +1562,7 @@ static int backward_impl(vcd_plan* p, int mode, const float* dy, const float* y,
   };
   uint32_t scale_bits;
   memcpy(&scale_bits, &p->grad_scale, sizeof(scale_bits));   // baked into the captured unfold launches
-  const uint64_t gver = p->params_version ^ (static_cast<uint64_t>(scale_bits) << 32);
+  const uint64_t gver = p->params_version ^ (static_cast<uint64_t>(scale_bits) << 32) ^ (p->deterministic ? 1ull << 31 : 0ull);
   if (whole) {
     for (int seg = 0; seg <= S; ++seg) TRY(zero_scratch(seg, stream));
     TRY(pre_part(0));
@@ -1676,6 +1708,18 @@ extern "C" int vcd_debug_ws_tensor(const vcd_plan* p, int mode, int B, int T, in
 extern "C" int vcd_set_gradient_scale(vcd_plan* p, float scale) {
   if (!p) return fail("vcd_set_gradient_scale: null plan");
   p->grad_scale = scale;
+  return 0;
+}
+
+extern "C" int vcd_set_deterministic(vcd_plan* p, int on) {
+  if (!p) return fail("vcd_set_deterministic: null plan");
+  if (on && !p->d_turn) {
+    const size_t n = p->layers.size() * vcd_plan::kTurnInts * sizeof(int);
+    CU_TRY(cudaMalloc(&p->d_turn, n));
+    CU_TRY(cudaMemset(p->d_turn, 0, n));
+    CU_TRY(cudaMalloc(&p->d_det, (p->layers.size() + 1) * vcd_plan::kDetFloats * sizeof(float)));
+  }
+  p->deterministic = on != 0;
   return 0;
 }
 

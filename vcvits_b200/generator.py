@@ -322,6 +322,7 @@ class Generator(nn.Module):
         # instead of routing 233 tensors through autograd; set False when something must observe the parameters as
         # autograd leaves of this call (``torch.autograd.grad`` w.r.t. parameters, DistributedDataParallel hooks).
         self.fused_param_grads = True
+        self._deterministic = False
         self._anchors = {}
         self._comm_streams = {}
         self._grad_templates = None
@@ -363,6 +364,18 @@ class Generator(nn.Module):
         self._param_cache = None
         return self
 
+    @property
+    def deterministic(self) -> bool:
+        """True: parameter gradients are bit-identical from run to run (``vcd_set_deterministic``: at most two atomic
+        contributions per gradient element; slower weight-gradient launches).  Default False."""
+        return self._deterministic
+
+    @deterministic.setter
+    def deterministic(self, on: bool) -> None:
+        self._deterministic = bool(on)
+        for plan in self._plans.values():
+            _lib.check(_lib.load().vcd_set_deterministic(plan, 1 if self._deterministic else 0), "vcd_set_deterministic")
+
     def invalidate_weights(self) -> "Generator":
         """Forget the cached weight fold.  Training-mode forwards always re-fold; inference (``torch.no_grad``)
         caches the fold keyed on the parameters' (address, version) -- an in-place edit through ``p.data`` does not
@@ -401,6 +414,8 @@ class Generator(nn.Module):
                 _lib.check(lib.vcd_plan_create(C.byref(cfg), C.byref(handle)), "vcd_plan_create")
             plan = handle
             self._plans[key] = plan
+            if self._deterministic:
+                _lib.check(lib.vcd_set_deterministic(plan, 1), "vcd_set_deterministic")
             n = lib.vcd_num_params(plan)
             names, numels = [], []
             for i in range(n):
