@@ -245,6 +245,14 @@ int vcd_mel_spectrogram(vcd_mel_plan* plan, const float* y_dev, float* mel_dev, 
 int vcd_mel_loss(vcd_mel_plan* plan, const float* y_hat_dev, const float* mel_target_dev, float c_mel, float* loss_dev,
                  float* dy_dev, void* ws_dev, size_t ws_bytes, int B, int T, void* stream);
 
+/* The same with y_mel_slice = commons.slice_segments(y_mel, ids_slice, segment_size // hop_length) (vits/commons.py:48-55;
+ * call vcvits.py:110) folded into the target read: mel_full_dev [B, n_mel, frames_full] is the whole-utterance log-mel,
+ * starts_dev B int64 first frames (ids_slice, on the device); frames starts[b] .. starts[b] + frames - 1 are compared.
+ * The caller guarantees starts[b] + frames <= frames_full (rand_slice_segments does). */
+int vcd_mel_loss_sliced(vcd_mel_plan* plan, const float* y_hat_dev, const float* mel_full_dev, int64_t frames_full,
+                        const int64_t* starts_dev, float c_mel, float* loss_dev, float* dy_dev, void* ws_dev, size_t ws_bytes,
+                        int B, int T, void* stream);
+
 /* Debug / tests only.  Two implementations exist: a per-frame shared-memory FFT kernel (n_fft a power of two; the
  * default when available) and dense fp32 GEMMs against a DFT basis (any n_fft).  use_gemm != 0 forces the second, so
  * that the tests can check one against the other. */

@@ -202,3 +202,24 @@ def test_decoder_into_loss_tail_end_to_end():
     loss.backward()
     assert abs(float(loss) - float(lr)) <= 1e-4 * abs(float(lr))
     assert rel_l2(xc.grad.cpu(), xr.grad) <= 2e-3
+
+
+@pytest.mark.parametrize("path", PATHS, indirect=True)
+def test_sliced_target_equals_slice_segments_then_loss(path):
+    """``ids_slice`` folds ``commons.slice_segments(y_mel, ids_slice, frames)`` (vits/commons.py:48-55) into the target read."""
+    kw, B, T, T_full = BASE, 6, 16384, 60000
+    path(kw)
+    y_hat = audio(B, T, seed=41).float().cuda().requires_grad_(True)
+    mel_full = V.mel_spectrogram_torch(audio(B, T_full, seed=42).float().cuda(), **kw)
+    frames = T // kw["hop_size"]
+    g = torch.Generator().manual_seed(5)
+    ids = torch.randint(0, mel_full.shape[2] - frames + 1, (B,), generator=g)
+    ids[0], ids[1] = 0, mel_full.shape[2] - frames            # both ends
+    sliced = torch.stack([mel_full[b, :, int(ids[b]):int(ids[b]) + frames] for b in range(B)])
+    a = V.mel_l1_loss(y_hat, sliced, c_mel=45.0, **kw)
+    (ga,) = torch.autograd.grad(a, y_hat)
+    b = V.mel_l1_loss(y_hat, mel_full, c_mel=45.0, ids_slice=ids.cuda(), **kw)
+    (gb,) = torch.autograd.grad(b, y_hat)
+    assert torch.equal(a, b) and torch.equal(ga, gb)
+    with pytest.raises(RuntimeError, match="full-length mel"):
+        V.mel_l1_loss(y_hat, mel_full[:, :, :frames - 1], c_mel=1.0, ids_slice=ids.cuda(), **kw)

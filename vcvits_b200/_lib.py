@@ -128,6 +128,8 @@ _SIGNATURES = {
     "vcd_mel_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int, C.c_int]),
     "vcd_mel_spectrogram": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p]),
     "vcd_mel_debug_path": (C.c_int, [C.c_void_p, C.c_int]),
+    "vcd_mel_loss_sliced": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p,
+                                      C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p]),
     "vcd_mel_loss": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
                                C.c_int, C.c_int, C.c_void_p]),
 }

@@ -105,9 +105,11 @@ struct EpiLogMel {     // gemm 2: log-mel, optionally the L1 loss against the ta
   float* dM; int ldM;    // [rows][ldM] gradient w.r.t. the (pre-log) mel energies, or null
   float scale;           // c_mel / (B * n_mel * F)
   int rows, n_mel, F;
+  const long long* starts; int F_tgt;   // target [B][n_mel][F_tgt] read at frame starts[b] + f (slice_segments folded in), or null / F
   __device__ __forceinline__ float operator()(int m, int n, const float (&v)[4]) const {
     if (m >= rows) return 0.f;
     const int b = m / F, f = m - b * F;
+    const long long ft = starts ? __ldg(starts + b) + f : f;
     float part = 0.f;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -118,7 +120,7 @@ struct EpiLogMel {     // gemm 2: log-mel, optionally the L1 loss against the ta
       const size_t o = (static_cast<size_t>(b) * n_mel + c) * F + f;
       if (out) out[o] = lm;
       if (target) {
-        const float d = lm - __ldg(target + o);
+        const float d = lm - __ldg(target + (static_cast<size_t>(b) * n_mel + c) * F_tgt + ft);
         part += fabsf(d);
         const float sg = d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f);
         dM[static_cast<size_t>(m) * ldM + c] = e >= 1e-5f ? sg * scale / e : 0.f;
@@ -349,7 +351,9 @@ struct FftParams {
   const int* f_lo; const int* f_cnt; const int* f_off; const float* f_val;   // per filter: first bin, bins, offset into f_val
   const int* b_lo; const int* b_cnt; const int* b_off; const float* b_val;   // per bin: first filter, filters, offset into b_val
   float* out;                 // [B][n_mel][F] log-mel, or null
-  const float* target;        // [B][n_mel][F], or null
+  const float* target;        // [B][n_mel][F_tgt] read at frame starts[b] + f, or null
+  const long long* starts;    // per-item first target frame (ids_slice), or null
+  int F_tgt;
   float scale;
   float* dframe;              // [rows][n_fft], or null (no gradient wanted)
   float* partials;            // [rows]
@@ -411,7 +415,8 @@ __global__ void __launch_bounds__(256) frame_fft_kernel(const FftParams P) {
     const size_t o = (static_cast<size_t>(b) * P.n_mel + m) * P.F + f;
     if (P.out) P.out[o] = lm;
     if (P.target) {
-      const float d = lm - __ldg(P.target + o);
+      const long long ft = P.starts ? __ldg(P.starts + b) + f : f;
+      const float d = lm - __ldg(P.target + (static_cast<size_t>(b) * P.n_mel + m) * P.F_tgt + ft);
       part += fabsf(d);
       const float sg = d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f);
       dMs[m] = e >= 1e-5f ? sg * P.scale / e : 0.f;

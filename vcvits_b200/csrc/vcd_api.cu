@@ -1923,8 +1923,8 @@ extern "C" int vcd_mel_debug_path(vcd_mel_plan* p, int use_gemm) {
 }
 
 // fast path: one launch does everything per frame (see mel_loss.cuh)
-static int mel_fft_launch(vcd_mel_plan* p, const float* y, const float* target, float* mel_out, float scale, float* dframe,
-                          float* partials, const MelWs& w, int T, cudaStream_t st) {
+static int mel_fft_launch(vcd_mel_plan* p, const float* y, const float* target, const long long* starts, int F_tgt, float* mel_out,
+                          float scale, float* dframe, float* partials, const MelWs& w, int T, cudaStream_t st) {
   const vcd_mel_config& c = p->cfg;
   const int nm = c.n_mel, nbins = p->n_bins;
   mel::FftParams P{};
@@ -1934,7 +1934,7 @@ static int mel_fft_launch(vcd_mel_plan* p, const float* y, const float* target, 
   P.f_lo = p->d_tab; P.f_cnt = P.f_lo + nm; P.f_off = P.f_cnt + nm;
   P.b_lo = P.f_off + nm; P.b_cnt = P.b_lo + nbins; P.b_off = P.b_cnt + nbins;
   P.f_val = p->d_vals; P.b_val = p->d_vals + p->f_val_n;
-  P.out = mel_out; P.target = target; P.scale = scale; P.dframe = dframe; P.partials = partials;
+  P.out = mel_out; P.target = target; P.starts = starts; P.F_tgt = F_tgt; P.scale = scale; P.dframe = dframe; P.partials = partials;
   mel::frame_fft_kernel<<<static_cast<unsigned>(w.rows), 256, p->fft_smem, st>>>(P);
   LAUNCH_CHECK("mel::frame_fft_kernel");
   return 0;
@@ -1948,8 +1948,8 @@ extern "C" size_t vcd_mel_workspace_bytes(const vcd_mel_plan* p, int B, int T) {
 }
 
 // forward part shared by the two entry points: gemm 1 (spectrum magnitudes) and gemm 2 (log-mel / loss / dM)
-static int mel_forward(vcd_mel_plan* p, const float* y, const float* target, float* mel_out, float scale, bool want_grad,
-                       uint8_t* ws, const MelWs& w, int B, int T, cudaStream_t st) {
+static int mel_forward(vcd_mel_plan* p, const float* y, const float* target, const long long* starts, int F_tgt, float* mel_out,
+                       float scale, bool want_grad, uint8_t* ws, const MelWs& w, int B, int T, cudaStream_t st) {
   const vcd_mel_config& c = p->cfg;
   const int pad = (c.n_fft - c.hop) / 2;
   float* S = reinterpret_cast<float*>(ws + w.S);
@@ -1965,7 +1965,7 @@ static int mel_forward(vcd_mel_plan* p, const float* y, const float* target, flo
   {
     mel::RowsK A{mag, p->ld_bins, w.rows, p->n_bins};
     mel::RowsK Bm{p->d_melw, p->ld_bins, c.n_mel, p->n_bins};
-    mel::EpiLogMel E{mel_out, target, reinterpret_cast<float*>(ws + w.dM), c.n_mel, scale, w.rows, c.n_mel, w.frames};
+    mel::EpiLogMel E{mel_out, target, reinterpret_cast<float*>(ws + w.dM), c.n_mel, scale, w.rows, c.n_mel, w.frames, starts, F_tgt};
     dim3 grid((c.n_mel + 63) / 64, (w.rows + 63) / 64);
     mel::gemm_kernel<64, 64, 4, 4><<<grid, 256, 0, st>>>(p->n_bins, A, Bm, E, reinterpret_cast<float*>(ws + w.partials));
     LAUNCH_CHECK("mel::gemm_kernel (mel)");
@@ -1990,26 +1990,44 @@ extern "C" int vcd_mel_spectrogram(vcd_mel_plan* p, const float* y_dev, float* m
   MelWs w;
   TRY(mel_check("vcd_mel_spectrogram", p, y_dev, mel_dev, ws_dev, ws_bytes, B, T, &w));
   if (p->fft_ok && !p->use_gemm)
-    return mel_fft_launch(p, y_dev, nullptr, mel_dev, 0.f, nullptr, reinterpret_cast<float*>(static_cast<uint8_t*>(ws_dev) + w.partials),
-                          w, T, static_cast<cudaStream_t>(stream));
-  return mel_forward(p, y_dev, nullptr, mel_dev, 0.f, false, static_cast<uint8_t*>(ws_dev), w, B, T,
+    return mel_fft_launch(p, y_dev, nullptr, nullptr, 0, mel_dev, 0.f, nullptr,
+                          reinterpret_cast<float*>(static_cast<uint8_t*>(ws_dev) + w.partials), w, T, static_cast<cudaStream_t>(stream));
+  return mel_forward(p, y_dev, nullptr, nullptr, 0, mel_dev, 0.f, false, static_cast<uint8_t*>(ws_dev), w, B, T,
                      static_cast<cudaStream_t>(stream));
 }
 
+static int mel_loss_impl(vcd_mel_plan* p, const float* y_hat_dev, const float* mel_target_dev, const long long* starts, int F_tgt,
+                         float c_mel, float* loss_dev, float* dy_dev, void* ws_dev, size_t ws_bytes, int B, int T, void* stream);
+
 extern "C" int vcd_mel_loss(vcd_mel_plan* p, const float* y_hat_dev, const float* mel_target_dev, float c_mel, float* loss_dev,
                             float* dy_dev, void* ws_dev, size_t ws_bytes, int B, int T, void* stream) {
+  return mel_loss_impl(p, y_hat_dev, mel_target_dev, nullptr, 0, c_mel, loss_dev, dy_dev, ws_dev, ws_bytes, B, T, stream);
+}
+
+extern "C" int vcd_mel_loss_sliced(vcd_mel_plan* p, const float* y_hat_dev, const float* mel_full_dev, int64_t frames_full,
+                                   const int64_t* starts_dev, float c_mel, float* loss_dev, float* dy_dev, void* ws_dev,
+                                   size_t ws_bytes, int B, int T, void* stream) {
+  if (!starts_dev) return fail("vcd_mel_loss_sliced: null starts");
+  if (!p || frames_full < mel_frames(p->cfg, T)) return fail("vcd_mel_loss_sliced: the full-length mel has fewer frames than one segment");
+  return mel_loss_impl(p, y_hat_dev, mel_full_dev, reinterpret_cast<const long long*>(starts_dev), static_cast<int>(frames_full), c_mel,
+                       loss_dev, dy_dev, ws_dev, ws_bytes, B, T, stream);
+}
+
+static int mel_loss_impl(vcd_mel_plan* p, const float* y_hat_dev, const float* mel_target_dev, const long long* starts, int F_tgt,
+                         float c_mel, float* loss_dev, float* dy_dev, void* ws_dev, size_t ws_bytes, int B, int T, void* stream) {
   MelWs w;
   TRY(mel_check("vcd_mel_loss", p, y_hat_dev, mel_target_dev, ws_dev, ws_bytes, B, T, &w));
   if (!loss_dev) return fail("vcd_mel_loss: null loss pointer");
+  if (!starts) F_tgt = w.frames;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   uint8_t* ws = static_cast<uint8_t*>(ws_dev);
   const vcd_mel_config& c = p->cfg;
   const float scale = c_mel / (static_cast<float>(B) * c.n_mel * w.frames);
   float* dframe = reinterpret_cast<float*>(ws + w.dframe);
   const bool fast = p->fft_ok && !p->use_gemm;
-  if (fast) TRY(mel_fft_launch(p, y_hat_dev, mel_target_dev, nullptr, scale, dy_dev ? dframe : nullptr,
+  if (fast) TRY(mel_fft_launch(p, y_hat_dev, mel_target_dev, starts, F_tgt, nullptr, scale, dy_dev ? dframe : nullptr,
                                reinterpret_cast<float*>(ws + w.partials), w, T, st));
-  else TRY(mel_forward(p, y_hat_dev, mel_target_dev, nullptr, scale, dy_dev != nullptr, ws, w, B, T, st));
+  else TRY(mel_forward(p, y_hat_dev, mel_target_dev, starts, F_tgt, nullptr, scale, dy_dev != nullptr, ws, w, B, T, st));
   const int n_part = fast ? w.rows : ((c.n_mel + 63) / 64) * ((w.rows + 63) / 64);
   mel::loss_finalize_kernel<<<1, 256, 0, st>>>(reinterpret_cast<const float*>(ws + w.partials), n_part, scale, loss_dev);
   LAUNCH_CHECK("mel::loss_finalize_kernel");

@@ -130,24 +130,38 @@ class MelLossTail:
                                                        T, stream), "vcd_mel_spectrogram")
         return out
 
-    def loss_and_grad(self, y_hat: torch.Tensor, y_mel: torch.Tensor, c_mel: float, want_grad: bool = True
-                      ) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+    def loss_and_grad(self, y_hat: torch.Tensor, y_mel: torch.Tensor, c_mel: float, want_grad: bool = True,
+                      ids_slice: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+        """``ids_slice`` (int64 [B], device): ``y_mel`` is the whole-utterance mel and frames
+        ``ids_slice[b] : ids_slice[b] + frames`` are the target (``commons.slice_segments`` folded into the read)."""
         y2 = self._as_2d(y_hat.detach())
         if y2.device != self.device:
             raise RuntimeError(f"audio on {y2.device}, plan on {self.device}")
         B, T = y2.shape
         F_ = self.frames(T)
         tgt = y_mel.detach().contiguous().float()
-        if tuple(tgt.shape) != (B, self.num_mels, F_):
-            raise RuntimeError(f"mel target of shape {tuple(tgt.shape)}, expected {(B, self.num_mels, F_)}")
+        if ids_slice is None:
+            if tuple(tgt.shape) != (B, self.num_mels, F_):
+                raise RuntimeError(f"mel target of shape {tuple(tgt.shape)}, expected {(B, self.num_mels, F_)}")
+        else:
+            if tgt.dim() != 3 or tuple(tgt.shape[:2]) != (B, self.num_mels) or tgt.shape[2] < F_:
+                raise RuntimeError(f"full-length mel of shape {tuple(tgt.shape)}, expected {(B, self.num_mels)} + (>= {F_},)")
+            ids_slice = ids_slice.detach().to(device=self.device, dtype=torch.int64).contiguous()
+            if tuple(ids_slice.shape) != (B,):
+                raise RuntimeError(f"ids_slice of shape {tuple(ids_slice.shape)}, expected {(B,)}")
         with torch.cuda.device(self.device):
             ws = self._workspace(B, T)
             loss = torch.empty((), dtype=torch.float32, device=self.device)
             dy = torch.empty(B, T, dtype=torch.float32, device=self.device) if want_grad else None
             stream = torch.cuda.current_stream().cuda_stream
-            _lib.check(_lib.load().vcd_mel_loss(self._plan, y2.data_ptr(), tgt.data_ptr(), float(c_mel), loss.data_ptr(),
-                                                dy.data_ptr() if dy is not None else None, ws.data_ptr(), ws.numel(), B, T,
-                                                stream), "vcd_mel_loss")
+            dyp = dy.data_ptr() if dy is not None else None
+            if ids_slice is None:
+                _lib.check(_lib.load().vcd_mel_loss(self._plan, y2.data_ptr(), tgt.data_ptr(), float(c_mel), loss.data_ptr(), dyp,
+                                                    ws.data_ptr(), ws.numel(), B, T, stream), "vcd_mel_loss")
+            else:
+                _lib.check(_lib.load().vcd_mel_loss_sliced(self._plan, y2.data_ptr(), tgt.data_ptr(), int(tgt.shape[2]),
+                                                           ids_slice.data_ptr(), float(c_mel), loss.data_ptr(), dyp, ws.data_ptr(),
+                                                           ws.numel(), B, T, stream), "vcd_mel_loss_sliced")
         return loss, dy
 
 
@@ -176,8 +190,8 @@ def mel_spectrogram_torch(y: torch.Tensor, n_fft: int, num_mels: int, sampling_r
 
 class _MelL1(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, y_hat, y_mel, plan: MelLossTail, c_mel: float):
-        loss, dy = plan.loss_and_grad(y_hat, y_mel, c_mel, want_grad=y_hat.requires_grad)
+    def forward(ctx, y_hat, y_mel, plan: MelLossTail, c_mel: float, ids_slice=None):
+        loss, dy = plan.loss_and_grad(y_hat, y_mel, c_mel, want_grad=y_hat.requires_grad, ids_slice=ids_slice)
         ctx.shape = y_hat.shape
         ctx.in_dtype = y_hat.dtype
         ctx.save_for_backward(dy if dy is not None else torch.empty(0, device=y_hat.device))
@@ -187,13 +201,15 @@ class _MelL1(torch.autograd.Function):
     def backward(ctx, grad_out):
         (dy,) = ctx.saved_tensors
         if dy.numel() == 0:
-            return None, None, None, None
-        return (dy * grad_out).reshape(ctx.shape).to(ctx.in_dtype), None, None, None
+            return None, None, None, None, None
+        return (dy * grad_out).reshape(ctx.shape).to(ctx.in_dtype), None, None, None, None
 
 
 def mel_l1_loss(y_hat: torch.Tensor, y_mel: torch.Tensor, n_fft: int, num_mels: int, sampling_rate: int, hop_size: int,
-                win_size: int, fmin, fmax, c_mel: float = 1.0) -> torch.Tensor:
+                win_size: int, fmin, fmax, c_mel: float = 1.0, ids_slice: Optional[torch.Tensor] = None) -> torch.Tensor:
     """``F.l1_loss(spec_to_mel_torch(spectrogram_torch_audio(y_hat, ...), ...), y_mel) * c_mel`` (vcvits.py:96-115);
-    differentiable w.r.t. ``y_hat`` (the gradient is computed in the same library call as the loss)."""
+    differentiable w.r.t. ``y_hat`` (the gradient is computed in the same library call as the loss).  With ``ids_slice``
+    (the second result of ``commons.rand_slice_segments``), ``y_mel`` is the whole-utterance mel and
+    ``commons.slice_segments(y_mel, ids_slice, frames)`` (vcvits.py:110) happens inside the kernel's target read."""
     plan = _plan(n_fft, num_mels, sampling_rate, hop_size, win_size, fmin, fmax, y_hat.device)
-    return _MelL1.apply(y_hat, y_mel, plan, float(c_mel))
+    return _MelL1.apply(y_hat, y_mel, plan, float(c_mel), ids_slice)
