@@ -207,7 +207,11 @@ inline int tc_run_conv(vcd_plan* p, const Layer& L, bool dgrad, const void* in, 
     if (cand * P.BN > 512 || cand > mtiles) continue;
     const int cb = 2 * cand * P.BN <= 512 ? 2 : 1;
     const long long tiles = 1LL * ((mtiles + cand - 1) / cand) * P.n_tiles_n * B;
-    const double waves = static_cast<double>((tiles + p->num_sms - 1) / p->num_sms);
+    // streamed-weight launches of a training step share the SMs with the other ResBlock branches and the trailing weight
+    // gradients: plan their waves on a share of the machine (VCD_CONV_SHARE; 1 = the whole machine)
+    static const int share = tc_env_int("VCD_CONV_SHARE", 1);
+    const int eff_sms = can_reside || share <= 1 ? p->num_sms : (p->num_sms + share - 1) / share;
+    const double waves = static_cast<double>((tiles + eff_sms - 1) / eff_sms);
     const double t_mma = 1.0 * cand * g.taps * (g.K / 16) * ((128 + P.BN) / 4);   // operand fetch at 128 B/clk
     const double a_bytes = 2.0 * cand * P.RA * g.K;
     const double t_load = (a_bytes + (can_reside ? 0.0 : w_tile_bytes)) / 27.0;
