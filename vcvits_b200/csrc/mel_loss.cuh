@@ -347,7 +347,7 @@ __global__ void __launch_bounds__(256) basis_kernel(float* basis, int n_fft, int
 struct FftParams {
   const float* y; int T, F, hop, pad, rows, n_fft, log2n, n_bins, n_mel;
   const float* window;        // [n_fft]
-  const float2* tw;           // [n_fft / 2] e^(-2 pi j t / n_fft)
+  const float2* tw;           // [n_fft - 1] per-stage twiddles: entry (ns - 1) + k = e^(-2 pi j k / (2 ns)), ns = 1, 2, 4, ... n_fft/2
   const int* f_lo; const int* f_cnt; const int* f_off; const float* f_val;   // per filter: first bin, bins, offset into f_val
   const int* b_lo; const int* b_cnt; const int* b_off; const float* b_val;   // per bin: first filter, filters, offset into b_val
   float* out;                 // [B][n_mel][F] log-mel, or null
@@ -368,7 +368,7 @@ __device__ __forceinline__ float2* fft_stockham(float2* src, float2* dst, const 
     const int ns = 1 << s;
     for (int j = threadIdx.x; j < half; j += blockDim.x) {
       const int k = j & (ns - 1);
-      const float2 w = tw[k << (log2n - 1 - s)];
+      const float2 w = tw[ns - 1 + k];     // stage tables are contiguous in k: conflict-free (a strided n_fft/2 table is up to 32-way conflicted)
       const float2 v0 = src[j];
       const float2 v1 = cmul(src[j + half], w);
       const int j0 = ((j - k) << 1) + k;
@@ -386,14 +386,14 @@ __global__ void __launch_bounds__(256) frame_fft_kernel(const FftParams P) {
   const int n = P.n_fft, half = n >> 1;
   float2* bufA = reinterpret_cast<float2*>(fft_smem);
   float2* bufB = bufA + n;
-  float2* tw = bufB + n;                                  // [half]
-  float* mag = reinterpret_cast<float*>(tw + half);       // [n_bins]
+  float2* tw = bufB + n;                                  // [n - 1] (+1 pad)
+  float* mag = reinterpret_cast<float*>(tw + n);          // [n_bins]
   float* dMs = mag + ((P.n_bins + 3) & ~3);               // [n_mel]
   __shared__ float red[8];
   const int row = blockIdx.x, tid = threadIdx.x;
   const int b = row / P.F, f = row - b * P.F;
   const float* yb = P.y + static_cast<size_t>(b) * P.T;
-  for (int t = tid; t < half; t += 256) tw[t] = __ldg(P.tw + t);
+  for (int t = tid; t < n - 1; t += 256) tw[t] = __ldg(P.tw + t);
   for (int i = tid; i < n; i += 256) {
     int p = f * P.hop + i - P.pad;
     if (p < 0) p = -p;
@@ -450,7 +450,7 @@ __global__ void __launch_bounds__(256) frame_fft_kernel(const FftParams P) {
   for (int i = tid; i < n; i += 256) dst[i] = R[i].x * __ldg(P.window + i);
 }
 
-// window [n_fft] and twiddles [n_fft / 2] of the fast path
+// window [n_fft] and per-stage twiddles [n_fft - 1] of the fast path
 __global__ void __launch_bounds__(256) fft_tables_kernel(float* window, float2* tw, int n_fft, int win) {
   const int i = blockIdx.x * 256 + threadIdx.x;
   if (i >= n_fft) return;
@@ -458,9 +458,12 @@ __global__ void __launch_bounds__(256) fft_tables_kernel(float* window, float2* 
   double w = 0.0;
   if (i >= left && i < left + win) w = 0.5 - 0.5 * cospi(2.0 * (i - left) / static_cast<double>(win));
   window[i] = static_cast<float>(w);
-  if (i < n_fft / 2) {
+  if (i < n_fft - 1) {       // entry i = (ns - 1) + k with ns the largest power of two <= i + 1
+    int ns = 1;
+    while (2 * ns <= i + 1) ns *= 2;
+    const int k = i - (ns - 1);
     double s, c;
-    sincospi(-2.0 * i / static_cast<double>(n_fft), &s, &c);
+    sincospi(-static_cast<double>(k) / ns, &s, &c);          // e^(-2 pi j k / (2 ns))
     tw[i] = make_float2(static_cast<float>(c), static_cast<float>(s));
   }
 }

@@ -1877,16 +1877,17 @@ extern "C" int vcd_mel_plan_create(const vcd_mel_config* cfg, const float* mel_b
     int l2 = 0;
     while ((1 << l2) < cfg->n_fft) ++l2;
     p->log2n = l2;
-    p->fft_smem = sizeof(float2) * (2 * static_cast<size_t>(cfg->n_fft) + cfg->n_fft / 2) +
+    p->fft_smem = sizeof(float2) * (3 * static_cast<size_t>(cfg->n_fft)) +
                   sizeof(float) * (static_cast<size_t>((nbins + 3) & ~3) + nm);
     cudaError_t e2 = cudaMalloc(&p->d_window, sizeof(float) * cfg->n_fft);
-    if (e2 == cudaSuccess) e2 = cudaMalloc(&p->d_tw, sizeof(float2) * (cfg->n_fft / 2));
+    if (e2 == cudaSuccess) e2 = cudaMalloc(&p->d_tw, sizeof(float2) * cfg->n_fft);
     if (e2 == cudaSuccess) e2 = cudaMalloc(&p->d_tab, sizeof(int) * tab.size());
     if (e2 == cudaSuccess) e2 = cudaMalloc(&p->d_vals, sizeof(float) * vals.size());
     if (e2 == cudaSuccess) e2 = cudaMemcpy(p->d_tab, tab.data(), sizeof(int) * tab.size(), cudaMemcpyHostToDevice);
     if (e2 == cudaSuccess) e2 = cudaMemcpy(p->d_vals, vals.data(), sizeof(float) * vals.size(), cudaMemcpyHostToDevice);
-    if (e2 == cudaSuccess && p->fft_smem > 48 * 1024)
-      e2 = cudaFuncSetAttribute(mel::frame_fft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(p->fft_smem));
+    // opt-in limit of the kernel = the largest request of any plan (a later, smaller plan must not lower it)
+    if (e2 == cudaSuccess && p->fft_smem <= 200 * 1024)
+      e2 = cudaFuncSetAttribute(mel::frame_fft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e2 == cudaSuccess) {
       mel::fft_tables_kernel<<<(cfg->n_fft + 255) / 256, 256>>>(p->d_window, p->d_tw, cfg->n_fft, cfg->win);
       g_launches.fetch_add(1, std::memory_order_relaxed);
