@@ -100,6 +100,7 @@ inline bool tc_make_rows_map(CUtensorMap* map, const void* base, int B, int C, i
 template <int F, int UW = 16, bool LEAN = false, bool WG = false>
 inline cudaError_t tc_conv_launch_one(const tc::ConvParams* P, int grid, size_t smem, cudaStream_t stream, bool pdl) {
   if (!P) return cudaFuncSetAttribute(tc::conv_kernel<F, UW, LEAN, WG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  const bool cluster = P->cl != 0;
   // programmatic dependent launch: the prologue (barrier init, TMEM allocation, weight loads) overlaps the tail of the
   // previous kernel of the stream; the kernel's activation / epilogue-operand readers call griddepcontrol.wait
   cudaLaunchConfig_t cfg{};
@@ -107,11 +108,22 @@ inline cudaError_t tc_conv_launch_one(const tc::ConvParams* P, int grid, size_t 
   cfg.blockDim = dim3(tc::kConvThreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (pdl) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  if (cluster) {   // pairs of CTAs sharing their weight stages by multicast (ConvParams::cl)
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = 2;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = pdl ? 1 : 0;
+  cfg.numAttrs = na;
   return cudaLaunchKernelEx(&cfg, tc::conv_kernel<F, UW, LEAN, WG>, *P);
 }
 // f: epilogue feature set (tc::EPI_*); bit 5 (32) selects the 32-column epilogue units
@@ -201,6 +213,16 @@ inline int tc_run_conv(vcd_plan* p, const Layer& L, bool dgrad, const void* in, 
   //   t_epi  = MT * BN/16 units * 450 clk        (8 epilogue warps)
   const double w_tile_bytes = 2.0 * g.taps * g.K * P.BN;
   const bool can_reside = (P.n_tiles_n == 1 && w_tile_bytes <= 100 * 1024);
+  // 2-CTA clusters with multicast weight stages for the streamed-weight launches (ConvParams::cl).  VCD_CONV_CLUSTER:
+  // 0 (default) = off, 1 = whenever eligible, 2 = whenever eligible and the cost model below counts on the halved weight
+  // traffic when it picks the rows per CTA tile, -1 = like 2 but only for long launches (>= 8 tiles per SM).  Bit-identical
+  // results (tests/test_options_gpu.py).  Measured (DESIGN.md, round-2 notes): the >= 128-channel launches of the 10 s
+  // inference batch run 5 % faster in isolation (938 -> 985 TFLOP/s), the concurrent step does not (71.8 -> 72.5 ms), and
+  // at the training shapes a CTA owns one or two tiles, so the cluster start-up costs more than it saves (2.78 -> 2.80 ms).
+  static const int cl_env = tc_env_int("VCD_CONV_CLUSTER", 0);
+  const bool cl_long = 1LL * mtiles * P.n_tiles_n * B >= 8LL * p->num_sms;
+  const bool cl_want = cl_env > 0 || (cl_env < 0 && cl_long);
+  const bool cl_model = (cl_env >= 2 || cl_env < 0) && cl_want && !can_reside && (B % 2 == 0);
   int MT = 1, bufs = 2;
   double best = 1e30;
   for (int cand : {1, 2, 4}) {
@@ -214,7 +236,7 @@ inline int tc_run_conv(vcd_plan* p, const Layer& L, bool dgrad, const void* in, 
     const double waves = static_cast<double>((tiles + eff_sms - 1) / eff_sms);
     const double t_mma = 1.0 * cand * g.taps * (g.K / 16) * ((128 + P.BN) / 4);   // operand fetch at 128 B/clk
     const double a_bytes = 2.0 * cand * P.RA * g.K;
-    const double t_load = (a_bytes + (can_reside ? 0.0 : w_tile_bytes)) / 27.0;
+    const double t_load = (a_bytes + (can_reside ? 0.0 : w_tile_bytes / (cl_model ? 2.0 : 1.0))) / 27.0;
     const double t_epi = cand * (P.BN / 16) * 450.0;
     const double body = t_mma > t_load ? t_mma : t_load;
     const double per_tile = cb == 2 ? (body > t_epi ? body : t_epi) : body + t_epi;
@@ -350,7 +372,11 @@ inline int tc_run_conv(vcd_plan* p, const Layer& L, bool dgrad, const void* in, 
   static const int occ2 = tc_env_int("VCD_CONV_OCC2", 0);
   const int ctas_per_sm = (occ2 && smem <= 110 * 1024 && P.tmem_cols <= 256) ? 2 : 1;
   const int max_ctas = p->num_sms * ctas_per_sm;
-  const int grid = P.total_tiles < max_ctas ? P.total_tiles : max_ctas;
+  int grid = P.total_tiles < max_ctas ? P.total_tiles : max_ctas;
+  // 2-CTA clusters: streamed weights, generic epilogue with global operands, an even number of (batch item, row group)s
+  P.cl = (cl_want && !P.w_resident && P.NE == 0 && !(wg != nullptr && wg->dwp != nullptr) &&
+          (static_cast<long long>(B) * P.n_mgroups) % 2 == 0 && P.total_tiles >= 2) ? 1 : 0;
+  if (P.cl) grid &= ~1;
   if (blk_elems(B, g.creal, Lout) >= (1ull << 31)) {  // the epilogue addresses its operands with 32-bit element offsets
     snprintf(err, errn, "tc_run_conv(%s): output tensor of %zu elements exceeds the 2^31-element limit of the tensor-core path",
              L.name.c_str(), blk_elems(B, g.creal, Lout));

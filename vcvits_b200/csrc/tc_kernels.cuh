@@ -108,6 +108,27 @@ __device__ __forceinline__ void umma_bf16_split(uint32_t tmem_d, uint32_t a_lo, 
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// ---- thread-block cluster helpers (weight stages shared by the CTAs of a cluster, see ConvParams::cl) ----
+// The same arrive on the barrier at this shared-memory offset in every CTA of `mask`.
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+// One global read, delivered (data and complete_tx) to the same shared-memory offsets of every CTA of `mask`.
+__device__ __forceinline__ void bulk_load_mc(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint16_t mask) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
+               ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(smem_u32(bar)), "h"(mask)
+               : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
   uint32_t r[16];
@@ -157,6 +178,11 @@ __device__ __forceinline__ void tmem_wait16(uint32_t (&r)[16]) {
 }
 
 // Shared-memory matrix descriptor, SWIZZLE_NONE, version 1 (sm_100).  All byte quantities multiples of 16.
+// Start-address field (16-byte units, 14 bits) of a shared-memory matrix descriptor.  In a cluster launch the shared::cta
+// address of a CTA with a non-zero cluster rank carries the rank above the 256 KB window offset: adding the unmasked
+// address to a descriptor word corrupts its leading-byte-offset field (found the hard way: rank 1 computed garbage).
+__device__ __forceinline__ uint32_t desc_addr16(const void* p) { return (smem_u32(p) & 0x3ffffu) >> 4; }
+
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
   uint64_t d = 0;
   d |= static_cast<uint64_t>((saddr >> 4) & 0x3fffu);
@@ -247,6 +273,9 @@ struct ConvParams {
   int minshift;           // min over taps of j*step (<= 0)
   int acc_bufs;           // 2: accumulators double-buffered (epilogue overlaps the next tile's MMAs); 1: MT*BN > 256
   uint32_t tmem_cols;
+  int cl;                 // 1: launched as clusters of two CTAs that own the SAME column tile and neighbouring row groups: each
+                          // CTA fetches half of every streamed weight stage and multicasts it to both (half the L2 -> SM weight
+                          // traffic per CTA).  Tile index v -> pair q = v >> 1 (column tile, row-group pair), rank v & 1.
   int pdl_late;           // 1: release the stream successor after this CTA's last MMAs are issued (default: at its last tile's loads)
   int NE;                 // EPI_SMEM: stages of the epilogue-operand ring (mask / residual tiles fetched by the bulk-copy engine)
   int e_ops;              // operands per stage (mask, residual)
@@ -262,6 +291,17 @@ struct ConvParams {
   uint32_t wg_col0;       // first TMEM column of the weight-gradient accumulators
   unsigned long long* trace;  // debug: %globaltimer stamps of CTA 0 (null = off)
 };
+
+// tile index -> (batch item * row groups + row group, column tile)
+__device__ __forceinline__ void tile_decode(const ConvParams& P, int tile, int& rest, int& nt) {
+  if (P.cl) {
+    int r2;
+    P.d_tiles_n.divmod(tile >> 1, r2, nt);
+    rest = 2 * r2 + (tile & 1);
+  } else {
+    P.d_tiles_n.divmod(tile, rest, nt);
+  }
+}
 
 __device__ __forceinline__ void ktrace(unsigned long long* buf, int slot) {
   if (buf != nullptr && blockIdx.x == 0) {
@@ -413,7 +453,7 @@ conv_kernel(const ConvParams P) {
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < P.NA; ++i) { mbar_init(&fullA[i], 1); mbar_init(&emptyA[i], 1); }
-    for (int i = 0; i < 8; ++i) { mbar_init(&fullW[i], 1); mbar_init(&emptyW[i], 1); }
+    for (int i = 0; i < 8; ++i) { mbar_init(&fullW[i], 1); mbar_init(&emptyW[i], P.cl ? 2 : 1); }   // cluster: both CTAs' MMA warps release a slot
     for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 8); }
     for (int i = 0; i < 8; ++i) { mbar_init(&fullE[i], 1); mbar_init(&emptyE[i], WG ? 9 : 8); }   // WG: + the MMA warp's commit
     fence_barrier_init();
@@ -427,6 +467,7 @@ conv_kernel(const ConvParams P) {
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  if (P.cl) cluster_sync_all();   // the peer's barriers exist before anything is multicast to them
   // shfl-broadcast: provably warp-uniform, so TMEM addresses stay in uniform registers in the MMA issue loop
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
   if (threadIdx.x == 0) ktrace(P.trace, 1);
@@ -443,8 +484,9 @@ conv_kernel(const ConvParams P) {
     for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
       // last tile of this CTA: the successor kernel may start its prologue (barriers, TMEM, weight loads) now
       if (!P.pdl_late && tile + static_cast<int>(gridDim.x) >= P.total_tiles) pdl_launch();
-      int b, mg;
-      P.d_mgroups.divmod(P.d_tiles_n.quot(tile), b, mg);
+      int b, mg, rest_a, nt_a;
+      tile_decode(P, tile, rest_a, nt_a);
+      P.d_mgroups.divmod(rest_a, b, mg);
       const int row0 = mg * 128 * P.MT + P.g.off0 + P.minshift;
       // 128-row tiles that start beyond the last output row are not loaded (their accumulators are never stored)
       int mt_live = P.MT;
@@ -511,20 +553,31 @@ conv_kernel(const ConvParams P) {
     } else {
       Pipe pw;
       const size_t tap_stride_g = static_cast<size_t>(P.g.K / 8) * P.BN * 8;
+      const uint32_t crank = P.cl ? cluster_ctarank() : 0u;
       for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
-        const int rest = P.d_tiles_n.quot(tile);
-        const int nt = tile - rest * P.n_tiles_n;
+        int rest, nt;
+        tile_decode(P, tile, rest, nt);
         for (int kb = 0; kb < kblocks; ++kb) {
           for (int gi = 0; gi < ngroups_w; ++gi) {
             const int j0 = gi * P.TPS;
             const int nj = min(P.TPS, P.g.taps - j0);
-            mbar_wait(&emptyW[pw.stage], pw.phase ^ 1);
+            mbar_wait(&emptyW[pw.stage], pw.phase ^ 1);   // cluster: released by the MMA warps of BOTH CTAs
             uint8_t* dst = w_smem + static_cast<size_t>(pw.stage) * P.TPS * w_tap_bytes;
             const bf16* src = P.w + ((static_cast<size_t>(nt) * P.g.taps + j0) * (P.g.K / 8) +
                                      static_cast<size_t>(kb) * (P.KB / 8)) * P.BN * 8;
             if (elect_one()) {
               mbar_expect_tx(&fullW[pw.stage], nj * w_tap_bytes);
-              if (kblocks == 1) {  // taps are contiguous in the packed weights: one copy per stage
+              if (P.cl) {          // this CTA's half of every copy, delivered to both CTAs (whose barriers each expect the whole stage)
+                if (kblocks == 1) {
+                  const uint32_t hb = (nj * w_tap_bytes) >> 1;
+                  bulk_load_mc(dst + crank * hb, reinterpret_cast<const uint8_t*>(src) + crank * hb, hb, &fullW[pw.stage], 3);
+                } else {
+                  const uint32_t hb = w_tap_bytes >> 1;
+                  for (int jj = 0; jj < nj; ++jj)
+                    bulk_load_mc(dst + jj * w_tap_bytes + crank * hb,
+                                 reinterpret_cast<const uint8_t*>(src + jj * tap_stride_g) + crank * hb, hb, &fullW[pw.stage], 3);
+                }
+              } else if (kblocks == 1) {  // taps are contiguous in the packed weights: one copy per stage
                 bulk_load(dst, src, nj * w_tap_bytes, &fullW[pw.stage]);
               } else {
                 for (int jj = 0; jj < nj; ++jj)
@@ -561,7 +614,7 @@ conv_kernel(const ConvParams P) {
       constexpr int MTC = decltype(mt_tag)::value;     // 0 = runtime P.MT
       const uint32_t a_hi = static_cast<uint32_t>(a_desc0 >> 32), w_hi = static_cast<uint32_t>(w_desc0 >> 32);
       const uint32_t tap_stride16 = P.w_resident ? w_tap16 * kblocks : w_tap16;   // resident layout: [tap][K/8][BN][8]
-      const uint32_t w_res_lo = static_cast<uint32_t>(w_desc0) + (smem_u32(w_smem) >> 4);
+      const uint32_t w_res_lo = static_cast<uint32_t>(w_desc0) + desc_addr16(w_smem);
       const uint32_t a_step = static_cast<uint32_t>(P.g.step), bn = static_cast<uint32_t>(P.BN);
       const int taps = P.g.taps;
       for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++it) {
@@ -575,7 +628,7 @@ conv_kernel(const ConvParams P) {
           mbar_wait(&fullA[pa.stage], pa.phase);
           tc_fence_after();
           if (it == 0 && kb == 0 && lane == 0) ktrace(P.trace, 4);
-          const uint32_t a_stage_lo = static_cast<uint32_t>(a_desc0) + (smem_u32(a_smem + static_cast<size_t>(pa.stage) * a_stage_bytes) >> 4);
+          const uint32_t a_stage_lo = static_cast<uint32_t>(a_desc0) + desc_addr16(a_smem + static_cast<size_t>(pa.stage) * a_stage_bytes);
           for (int gi = 0; gi < ngroups; ++gi) {
             int nj, j0;
             uint32_t w_lo;
@@ -588,7 +641,7 @@ conv_kernel(const ConvParams P) {
               nj = min(P.TPS, taps - j0);
               mbar_wait(&fullW[pw.stage], pw.phase);
               tc_fence_after();
-              w_lo = static_cast<uint32_t>(w_desc0) + (smem_u32(w_smem + static_cast<size_t>(pw.stage) * P.TPS * w_tap_bytes) >> 4);
+              w_lo = static_cast<uint32_t>(w_desc0) + desc_addr16(w_smem + static_cast<size_t>(pw.stage) * P.TPS * w_tap_bytes);
             }
             uint32_t a_tap = a_stage_lo + static_cast<uint32_t>(-P.minshift) + static_cast<uint32_t>(j0) * a_step;
             uint32_t first = (kb | gi) != 0 ? 1u : 0u;    // accumulate flag of the first MMA of this tap group
@@ -623,7 +676,10 @@ conv_kernel(const ConvParams P) {
               a_tap += a_step;
             }
             if (!P.w_resident) {
-              if (elect_one()) umma_commit(&emptyW[pw.stage]);
+              if (elect_one()) {
+                if (P.cl) umma_commit_mc(&emptyW[pw.stage], 3);   // the slot is free for both producers once both consumers are done
+                else umma_commit(&emptyW[pw.stage]);
+              }
               pw.advance(P.NW);
             }
           }
@@ -857,7 +913,7 @@ conv_kernel(const ConvParams P) {
     auto tile_coords = [&](int tile, int it) {
       TileC t;
       int rest, nt, mg;
-      P.d_tiles_n.divmod(tile, rest, nt);
+      tile_decode(P, tile, rest, nt);
       P.d_mgroups.divmod(rest, t.b, mg);
       const int buf = P.acc_bufs == 2 ? (it & 1) : 0;
       t.r_phase = P.d_creal.quot(nt * P.BN);            // scatter phase of this column tile (os > 1)
@@ -987,6 +1043,7 @@ conv_kernel(const ConvParams P) {
 
   tc_fence_before();
   __syncthreads();
+  if (P.cl) cluster_sync_all();   // the peer's last multicast arrivals on this CTA's barriers precede its own arrival here
   if (warp == 1) tmem_dealloc(tmem_base, P.tmem_cols);
   if (threadIdx.x == 0) ktrace(P.trace, 6);
 }
