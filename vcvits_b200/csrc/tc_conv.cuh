@@ -97,10 +97,10 @@ inline bool tc_make_rows_map(CUtensorMap* map, const void* base, int B, int C, i
 
 // Epilogue-specialised instantiations of the convolution kernel.  P == nullptr: only raise the dynamic shared
 // memory limit of instantiation `f` (plan creation); otherwise launch it.
-template <int F, int UW = 16, bool LEAN = false, bool WG = false>
+template <int F, int UW = 16, bool LEAN = false, bool WG = false, bool CL = false>
 inline cudaError_t tc_conv_launch_one(const tc::ConvParams* P, int grid, size_t smem, cudaStream_t stream, bool pdl) {
-  if (!P) return cudaFuncSetAttribute(tc::conv_kernel<F, UW, LEAN, WG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-  const bool cluster = P->cl != 0;
+  if (!P) return cudaFuncSetAttribute(tc::conv_kernel<F, UW, LEAN, WG, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  const bool cluster = CL;
   // programmatic dependent launch: the prologue (barrier init, TMEM allocation, weight loads) overlaps the tail of the
   // previous kernel of the stream; the kernel's activation / epilogue-operand readers call griddepcontrol.wait
   cudaLaunchConfig_t cfg{};
@@ -124,12 +124,22 @@ inline cudaError_t tc_conv_launch_one(const tc::ConvParams* P, int grid, size_t 
   }
   cfg.attrs = attr;
   cfg.numAttrs = na;
-  return cudaLaunchKernelEx(&cfg, tc::conv_kernel<F, UW, LEAN, WG>, *P);
+  return cudaLaunchKernelEx(&cfg, tc::conv_kernel<F, UW, LEAN, WG, CL>, *P);
 }
 // f: epilogue feature set (tc::EPI_*); bit 5 (32) selects the 32-column epilogue units
 constexpr int kUw32 = 32, kLean = 64, kWg = 128;   // kWg: fused weight gradient (data-gradient launches, lean + mask staged)
+constexpr int kCl = 256;                            // 2-CTA clusters with multicast weight stages (generic epilogues only)
 inline cudaError_t tc_conv_dispatch(int f, const tc::ConvParams* P, int grid, size_t smem, cudaStream_t stream, bool pdl) {
   switch (f) {
+    case kCl | 0: return tc_conv_launch_one<0, 16, false, false, true>(P, grid, smem, stream, pdl);
+    case kCl | 1: return tc_conv_launch_one<1, 16, false, false, true>(P, grid, smem, stream, pdl);
+    case kCl | 2: return tc_conv_launch_one<2, 16, false, false, true>(P, grid, smem, stream, pdl);
+    case kCl | 3: return tc_conv_launch_one<3, 16, false, false, true>(P, grid, smem, stream, pdl);
+    case kCl | 6: return tc_conv_launch_one<6, 16, false, false, true>(P, grid, smem, stream, pdl);
+    case kCl | 7: return tc_conv_launch_one<7, 16, false, false, true>(P, grid, smem, stream, pdl);
+    case kCl | 8: return tc_conv_launch_one<8, 16, false, false, true>(P, grid, smem, stream, pdl);
+    case kCl | 14: return tc_conv_launch_one<14, 16, false, false, true>(P, grid, smem, stream, pdl);
+    case kCl | 15: return tc_conv_launch_one<15, 16, false, false, true>(P, grid, smem, stream, pdl);
     case kWg | kLean | 17: return tc_conv_launch_one<17, 16, true, true>(P, grid, smem, stream, pdl);
     case kWg | kLean | 19: return tc_conv_launch_one<19, 16, true, true>(P, grid, smem, stream, pdl);
     case kWg | kLean | kUw32 | 17: return tc_conv_launch_one<17, 32, true, true>(P, grid, smem, stream, pdl);
@@ -166,7 +176,7 @@ inline cudaError_t tc_conv_dispatch(int f, const tc::ConvParams* P, int grid, si
 
 inline int tc_plan_init(vcd_plan* p) {
   cudaError_t e = cudaSuccess;
-  for (int f = 0; f < 256 && e == cudaSuccess; ++f) e = tc_conv_dispatch(f, nullptr, 0, 0, 0, false);
+  for (int f = 0; f < 512 && e == cudaSuccess; ++f) e = tc_conv_dispatch(f, nullptr, 0, 0, 0, false);
   if (e != cudaSuccess) return 1;
   e = cudaFuncSetAttribute(tc::wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   if (e != cudaSuccess) return 1;
@@ -422,7 +432,8 @@ inline int tc_run_conv(vcd_plan* p, const Layer& L, bool dgrad, const void* in, 
       wg->fused = true;
     }
   }
-  const cudaError_t ce = tc_conv_dispatch(f | (uw32 ? kUw32 : 0) | (lean ? kLean : 0) | (wg_on ? kWg : 0), &P, grid, smem, stream,
+  if (P.cl && (uw32 || lean || wg_on || (f & tc::EPI_SMEM))) { P.cl = 0; grid = P.total_tiles < max_ctas ? P.total_tiles : max_ctas; }
+  const cudaError_t ce = tc_conv_dispatch(f | (uw32 ? kUw32 : 0) | (lean ? kLean : 0) | (wg_on ? kWg : 0) | (P.cl ? kCl : 0), &P, grid, smem, stream,
                                           (pdl_mask & (dgrad ? 2 : 1)) != 0);
   launches.fetch_add(1, std::memory_order_relaxed);
   if (ce != cudaSuccess) {

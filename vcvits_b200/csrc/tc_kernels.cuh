@@ -181,7 +181,8 @@ __device__ __forceinline__ void tmem_wait16(uint32_t (&r)[16]) {
 // Start-address field (16-byte units, 14 bits) of a shared-memory matrix descriptor.  In a cluster launch the shared::cta
 // address of a CTA with a non-zero cluster rank carries the rank above the 256 KB window offset: adding the unmasked
 // address to a descriptor word corrupts its leading-byte-offset field (found the hard way: rank 1 computed garbage).
-__device__ __forceinline__ uint32_t desc_addr16(const void* p) { return (smem_u32(p) & 0x3ffffu) >> 4; }
+template <bool CL>
+__device__ __forceinline__ uint32_t desc_addr16(const void* p) { return CL ? (smem_u32(p) & 0x3ffffu) >> 4 : smem_u32(p) >> 4; }
 
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
   uint64_t d = 0;
@@ -293,8 +294,9 @@ struct ConvParams {
 };
 
 // tile index -> (batch item * row groups + row group, column tile)
+template <bool CL>
 __device__ __forceinline__ void tile_decode(const ConvParams& P, int tile, int& rest, int& nt) {
-  if (P.cl) {
+  if constexpr (CL) {
     int r2;
     P.d_tiles_n.divmod(tile >> 1, r2, nt);
     rest = 2 * r2 + (tile & 1);
@@ -416,10 +418,13 @@ __device__ __forceinline__ void epi_finish(const Epilogue& e, const ConvGeo& g, 
 // whose long dependent chains (~100 UIMAD / USEL / LDCU per unit) cost more than the arithmetic of a 128 x 32 tile
 // (in-kernel trace: 0.67 us per tile of which 0.13 us MMA).  Here the tile walk is incremental (b, row group advance by
 // the grid stride), offsets are one IMAD per unit, and a warp sweeps all its units of a tile in one straight loop.
-template <int F, int UW = 16, bool LEAN = false, bool WG = false>
+// CL: the launch runs as 2-CTA clusters with multicast weight stages (ConvParams::cl; streamed weights, generic epilogue).
+// Compile-time so that the plain instantiations carry none of it (as runtime branches it cost 1.9 % of the training step).
+template <int F, int UW = 16, bool LEAN = false, bool WG = false, bool CL = false>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_kernel(const ConvParams P) {
   static_assert(!WG || (LEAN && (F & EPI_SMEM) && (F & EPI_MASK)), "WG rides on the lean, smem-staged data-gradient epilogues");
+  static_assert(!CL || (!LEAN && !WG && !(F & EPI_SMEM)), "clusters: streamed weights, generic epilogue");
   extern __shared__ __align__(128) uint8_t smem_raw[];
   // shfl-broadcast warp index: provably warp-uniform, so role branches are uniform and the compiler may use the
   // uniform datapath (UR registers) for descriptor / address arithmetic inside them
@@ -453,7 +458,7 @@ conv_kernel(const ConvParams P) {
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < P.NA; ++i) { mbar_init(&fullA[i], 1); mbar_init(&emptyA[i], 1); }
-    for (int i = 0; i < 8; ++i) { mbar_init(&fullW[i], 1); mbar_init(&emptyW[i], P.cl ? 2 : 1); }   // cluster: both CTAs' MMA warps release a slot
+    for (int i = 0; i < 8; ++i) { mbar_init(&fullW[i], 1); mbar_init(&emptyW[i], CL ? 2 : 1); }   // cluster: both CTAs' MMA warps release a slot
     for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 8); }
     for (int i = 0; i < 8; ++i) { mbar_init(&fullE[i], 1); mbar_init(&emptyE[i], WG ? 9 : 8); }   // WG: + the MMA warp's commit
     fence_barrier_init();
@@ -467,7 +472,7 @@ conv_kernel(const ConvParams P) {
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  if (P.cl) cluster_sync_all();   // the peer's barriers exist before anything is multicast to them
+  if constexpr (CL) cluster_sync_all();   // the peer's barriers exist before anything is multicast to them
   // shfl-broadcast: provably warp-uniform, so TMEM addresses stay in uniform registers in the MMA issue loop
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
   if (threadIdx.x == 0) ktrace(P.trace, 1);
@@ -485,7 +490,7 @@ conv_kernel(const ConvParams P) {
       // last tile of this CTA: the successor kernel may start its prologue (barriers, TMEM, weight loads) now
       if (!P.pdl_late && tile + static_cast<int>(gridDim.x) >= P.total_tiles) pdl_launch();
       int b, mg, rest_a, nt_a;
-      tile_decode(P, tile, rest_a, nt_a);
+      tile_decode<CL>(P, tile, rest_a, nt_a);
       P.d_mgroups.divmod(rest_a, b, mg);
       const int row0 = mg * 128 * P.MT + P.g.off0 + P.minshift;
       // 128-row tiles that start beyond the last output row are not loaded (their accumulators are never stored)
@@ -553,10 +558,10 @@ conv_kernel(const ConvParams P) {
     } else {
       Pipe pw;
       const size_t tap_stride_g = static_cast<size_t>(P.g.K / 8) * P.BN * 8;
-      const uint32_t crank = P.cl ? cluster_ctarank() : 0u;
+      const uint32_t crank = CL ? cluster_ctarank() : 0u;
       for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
         int rest, nt;
-        tile_decode(P, tile, rest, nt);
+        tile_decode<CL>(P, tile, rest, nt);
         for (int kb = 0; kb < kblocks; ++kb) {
           for (int gi = 0; gi < ngroups_w; ++gi) {
             const int j0 = gi * P.TPS;
@@ -567,7 +572,7 @@ conv_kernel(const ConvParams P) {
                                      static_cast<size_t>(kb) * (P.KB / 8)) * P.BN * 8;
             if (elect_one()) {
               mbar_expect_tx(&fullW[pw.stage], nj * w_tap_bytes);
-              if (P.cl) {          // this CTA's half of every copy, delivered to both CTAs (whose barriers each expect the whole stage)
+              if constexpr (CL) {          // this CTA's half of every copy, delivered to both CTAs (whose barriers each expect the whole stage)
                 if (kblocks == 1) {
                   const uint32_t hb = (nj * w_tap_bytes) >> 1;
                   bulk_load_mc(dst + crank * hb, reinterpret_cast<const uint8_t*>(src) + crank * hb, hb, &fullW[pw.stage], 3);
@@ -614,7 +619,7 @@ conv_kernel(const ConvParams P) {
       constexpr int MTC = decltype(mt_tag)::value;     // 0 = runtime P.MT
       const uint32_t a_hi = static_cast<uint32_t>(a_desc0 >> 32), w_hi = static_cast<uint32_t>(w_desc0 >> 32);
       const uint32_t tap_stride16 = P.w_resident ? w_tap16 * kblocks : w_tap16;   // resident layout: [tap][K/8][BN][8]
-      const uint32_t w_res_lo = static_cast<uint32_t>(w_desc0) + desc_addr16(w_smem);
+      const uint32_t w_res_lo = static_cast<uint32_t>(w_desc0) + desc_addr16<CL>(w_smem);
       const uint32_t a_step = static_cast<uint32_t>(P.g.step), bn = static_cast<uint32_t>(P.BN);
       const int taps = P.g.taps;
       for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++it) {
@@ -628,7 +633,7 @@ conv_kernel(const ConvParams P) {
           mbar_wait(&fullA[pa.stage], pa.phase);
           tc_fence_after();
           if (it == 0 && kb == 0 && lane == 0) ktrace(P.trace, 4);
-          const uint32_t a_stage_lo = static_cast<uint32_t>(a_desc0) + desc_addr16(a_smem + static_cast<size_t>(pa.stage) * a_stage_bytes);
+          const uint32_t a_stage_lo = static_cast<uint32_t>(a_desc0) + desc_addr16<CL>(a_smem + static_cast<size_t>(pa.stage) * a_stage_bytes);
           for (int gi = 0; gi < ngroups; ++gi) {
             int nj, j0;
             uint32_t w_lo;
@@ -641,7 +646,7 @@ conv_kernel(const ConvParams P) {
               nj = min(P.TPS, taps - j0);
               mbar_wait(&fullW[pw.stage], pw.phase);
               tc_fence_after();
-              w_lo = static_cast<uint32_t>(w_desc0) + desc_addr16(w_smem + static_cast<size_t>(pw.stage) * P.TPS * w_tap_bytes);
+              w_lo = static_cast<uint32_t>(w_desc0) + desc_addr16<CL>(w_smem + static_cast<size_t>(pw.stage) * P.TPS * w_tap_bytes);
             }
             uint32_t a_tap = a_stage_lo + static_cast<uint32_t>(-P.minshift) + static_cast<uint32_t>(j0) * a_step;
             uint32_t first = (kb | gi) != 0 ? 1u : 0u;    // accumulate flag of the first MMA of this tap group
@@ -677,7 +682,7 @@ conv_kernel(const ConvParams P) {
             }
             if (!P.w_resident) {
               if (elect_one()) {
-                if (P.cl) umma_commit_mc(&emptyW[pw.stage], 3);   // the slot is free for both producers once both consumers are done
+                if constexpr (CL) umma_commit_mc(&emptyW[pw.stage], 3);   // the slot is free for both producers once both consumers are done
                 else umma_commit(&emptyW[pw.stage]);
               }
               pw.advance(P.NW);
@@ -913,7 +918,7 @@ conv_kernel(const ConvParams P) {
     auto tile_coords = [&](int tile, int it) {
       TileC t;
       int rest, nt, mg;
-      tile_decode(P, tile, rest, nt);
+      tile_decode<CL>(P, tile, rest, nt);
       P.d_mgroups.divmod(rest, t.b, mg);
       const int buf = P.acc_bufs == 2 ? (it & 1) : 0;
       t.r_phase = P.d_creal.quot(nt * P.BN);            // scatter phase of this column tile (os > 1)
@@ -1043,7 +1048,7 @@ conv_kernel(const ConvParams P) {
 
   tc_fence_before();
   __syncthreads();
-  if (P.cl) cluster_sync_all();   // the peer's last multicast arrivals on this CTA's barriers precede its own arrival here
+  if constexpr (CL) cluster_sync_all();   // the peer's last multicast arrivals on this CTA's barriers precede its own arrival here
   if (warp == 1) tmem_dealloc(tmem_base, P.tmem_cols);
   if (threadIdx.x == 0) ktrace(P.trace, 6);
 }
