@@ -426,6 +426,9 @@ conv_kernel(const ConvParams P) {
   static_assert(!WG || (LEAN && (F & EPI_SMEM) && (F & EPI_MASK)), "WG rides on the lean, smem-staged data-gradient epilogues");
   static_assert(!CL || (!LEAN && !WG && !(F & EPI_SMEM)), "clusters: streamed weights, generic epilogue");
   extern __shared__ __align__(128) uint8_t smem_raw[];
+  // weights resident in shared memory for the whole launch?  Known at compile time for the lean (always resident) and
+  // cluster (always streamed) instantiations: their dead ring / resident code and its checks vanish.
+  const int w_res = LEAN ? 1 : (CL ? 0 : P.w_resident);
   // shfl-broadcast warp index: provably warp-uniform, so role branches are uniform and the compiler may use the
   // uniform datapath (UR registers) for descriptor / address arithmetic inside them
   const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
@@ -437,7 +440,7 @@ conv_kernel(const ConvParams P) {
   const int kblocks = P.g.K / P.KB;
   const int kk_per_block = P.KB / 16;
   const int ngroups_w = (P.g.taps + P.TPS - 1) / P.TPS;   // weight stages per K block (ring mode)
-  const uint32_t w_region_bytes = P.w_resident ? w_tap_bytes * P.g.taps * kblocks : w_tap_bytes * P.TPS * P.NW;
+  const uint32_t w_region_bytes = w_res ? w_tap_bytes * P.g.taps * kblocks : w_tap_bytes * P.TPS * P.NW;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
   uint8_t* a_smem = smem;
   uint8_t* w_smem = a_smem + static_cast<size_t>(P.NA) * a_stage_bytes;
@@ -514,7 +517,7 @@ conv_kernel(const ConvParams P) {
     }
   } else if (warp == 10) {
     // ===================== weight producer (own warp: never queues behind the activation copies) =====================
-    if (P.w_resident) {  // whole weight set of column tile 0 (n_tiles_n == 1), loaded once
+    if (w_res) {  // whole weight set of column tile 0 (n_tiles_n == 1), loaded once
       const uint32_t total = w_region_bytes;
       if (elect_one()) {
         mbar_expect_tx(&fullW[0], total);
@@ -605,7 +608,7 @@ conv_kernel(const ConvParams P) {
     const uint64_t a_desc0 = make_desc(0, a_lbo, 128), w_desc0 = make_desc(0, w_lbo, 128);
     Pipe pa, pw;
     int it = 0;
-    if (P.w_resident) {
+    if (w_res) {
       mbar_wait(&fullW[0], 0);
       tc_fence_after();
       if (lane == 0) ktrace(P.trace, 3);
@@ -618,7 +621,7 @@ conv_kernel(const ConvParams P) {
       constexpr int KK = decltype(kk_tag)::value;
       constexpr int MTC = decltype(mt_tag)::value;     // 0 = runtime P.MT
       const uint32_t a_hi = static_cast<uint32_t>(a_desc0 >> 32), w_hi = static_cast<uint32_t>(w_desc0 >> 32);
-      const uint32_t tap_stride16 = P.w_resident ? w_tap16 * kblocks : w_tap16;   // resident layout: [tap][K/8][BN][8]
+      const uint32_t tap_stride16 = w_res ? w_tap16 * kblocks : w_tap16;   // resident layout: [tap][K/8][BN][8]
       const uint32_t w_res_lo = static_cast<uint32_t>(w_desc0) + desc_addr16<CL>(w_smem);
       const uint32_t a_step = static_cast<uint32_t>(P.g.step), bn = static_cast<uint32_t>(P.BN);
       const int taps = P.g.taps;
@@ -628,7 +631,7 @@ conv_kernel(const ConvParams P) {
         mbar_wait(&acc_empty[buf], (use & 1) ^ 1);
         tc_fence_after();
         const uint32_t d_tile = tmem_base + static_cast<uint32_t>(buf * P.MT * P.BN);
-        const int ngroups = P.w_resident ? 1 : ngroups_w;
+        const int ngroups = w_res ? 1 : ngroups_w;
         for (int kb = 0; kb < kblocks; ++kb) {
           mbar_wait(&fullA[pa.stage], pa.phase);
           tc_fence_after();
@@ -637,7 +640,7 @@ conv_kernel(const ConvParams P) {
           for (int gi = 0; gi < ngroups; ++gi) {
             int nj, j0;
             uint32_t w_lo;
-            if (P.w_resident) {
+            if (w_res) {
               nj = taps;
               j0 = 0;
               w_lo = w_res_lo + static_cast<uint32_t>(kb) * w_tap16;
@@ -680,7 +683,7 @@ conv_kernel(const ConvParams P) {
               w_lo += tap_stride16;
               a_tap += a_step;
             }
-            if (!P.w_resident) {
+            if (!w_res) {
               if (elect_one()) {
                 if constexpr (CL) umma_commit_mc(&emptyW[pw.stage], 3);   // the slot is free for both producers once both consumers are done
                 else umma_commit(&emptyW[pw.stage]);
