@@ -33,3 +33,19 @@ def test_cpu_tensors_raise():
         V.mel_spectrogram_torch(y, 2048, 256, 48000, 512, 2048, 0.0, None)
     with pytest.raises(RuntimeError):
         V.mel_l1_loss(y, torch.zeros(1, 256, 8), 2048, 256, 48000, 512, 2048, 0.0, None)
+
+
+def test_c_abi_fails_loudly_without_a_device_and_on_null_plans():
+    import ctypes as C
+    from vcvits_b200 import _lib
+    lib = _lib.load()
+    assert lib.vcd_set_deterministic(None, 1) != 0 and b"null plan" in lib.vcd_last_error()
+    assert lib.vcd_mel_debug_path(None, 1) != 0 and b"null plan" in lib.vcd_last_error()
+    assert lib.vcd_mel_frames(None, 4096) == 0 and lib.vcd_mel_workspace_bytes(None, 1, 4096) == 0
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: plan creation succeeds")
+    fb = np.ascontiguousarray(V.slaney_mel_filterbank(48000, 2048, 256, 0.0, None))
+    cfg = V._MelConfig(2048, 512, 2048, 256)
+    handle = C.c_void_p()
+    assert lib.vcd_mel_plan_create(C.byref(cfg), fb.ctypes.data_as(C.c_void_p), C.byref(handle)) != 0
+    assert b"no CUDA device" in lib.vcd_last_error()
